@@ -1,0 +1,196 @@
+/*
+ * pbn_b200.h -- C ABI of the B200-native batched Probabilistic Boolean Network environment.
+ *
+ * This is the drop-in boundary for the hot path of jakub-zarzycki2022/pbn-rl: the PBN
+ * environment its agents drive through gym's reset()/step().  In the reference that env is
+ * pure Python inside the third-party gym-PBN fork (requirements.txt:11); there is no FFI in
+ * the reference, so each entry point below cites the *call site* whose work it takes over.
+ * The Python shim pbn_rl_b200/_cabi.py is the only in-tree caller (ctypes); see
+ * INTEGRATION.md for the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Every function returns 0 (PBN_OK) or a negative pbn_status; nothing throws.
+ *     pbn_last_error() returns a thread-local message for the last failure.
+ *   - All array arguments are DEVICE pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()), except the descriptor/table arguments of pbn_create and
+ *     pbn_update_attractors, which are HOST pointers copied during the call.
+ *   - Launches go to the caller's stream (a cudaStream_t passed as void*); the library never
+ *     synchronises the device.  One handle per GPU; a handle may be used from one thread at
+ *     a time.  No global state except the thread-local error string.
+ *   - State packing: bit i of a state = gene i (order of the network's Vars: section);
+ *     W = 1 64-bit word for N <= 64 genes, W = 2 for N <= 128; env e's words are
+ *     state[e*W .. e*W+W-1].
+ *
+ * One env step (pbn_step), per env instance -- the contract the oracle restates
+ * (oracle/pbn_oracle.py: batched_step):
+ *   1. flip  = OR over the env's `bins` action bytes a of (1 <= a <= N ? 1<<(a-1) : 0)
+ *              (0 = no-op, duplicates do not cancel; bdq_model/__init__.py:82-84,176)
+ *      s1    = s XOR flip
+ *   2. sel_i = index of the predictor gene i uses this step (injected, or drawn from the
+ *              Philox stream with the gene's cumulative selection thresholds)
+ *   3. f_i   = LUT[i][sel_i](s1)                        -- synchronous update of all genes
+ *   4. perturbation with mask pert (injected, or each gene independently with prob. p):
+ *        PBN_PERT_NONE: s' = f
+ *        PBN_PERT_A   : s' = pert ? s1 XOR pert : f      (Shmulevich: a perturbed step skips the update)
+ *        PBN_PERT_B   : s' = f XOR pert
+ *        PBN_PERT_C   : s'_i = pert_i ? NOT s1_i : f_i
+ *   5. hit        = target_id in [0, A) and s' matches an entry (care, value) of that attractor
+ *   6. t'         = min(t + 1, 65535); terminated = hit;
+ *      truncated  = !hit && horizon > 0 && t' >= horizon
+ *   7. reward     = (r_step + r_action * popcount(flip)) + (hit ? r_success : 0)   [fp32, no FMA]
+ *   8. with PBN_STEP_AUTORESET, envs with terminated|truncated are re-initialised as by
+ *      pbn_reset (new source state / target / t = 0) after their outputs were written.
+ *
+ * Random streams (own-RNG mode): Philox4x32-10, key = (seed_lo, seed_hi),
+ *   counter = (id_lo, id_hi, step_lo, (step_hi & 0xFFFF) | (kind << 28) | (idx << 16)),
+ *   kind in {PBN_RNG_SELECT=0, PBN_RNG_PERTURB=1, PBN_RNG_RESET=2}, idx = block index < 4096.
+ *   Scalar kernel: id = global env id (env_offset + e).  Gene i uses word i&3 of block
+ *   (SELECT, i>>2): sel_i = #{k < K_i-1 : cum[k] <= word}.  Perturbation positions are drawn
+ *   by geometric skipping: words of blocks (PERTURB, 0..) in order, skip = #{j in 1..N :
+ *   word < survival[j]}, pos += skip + 1, stop when pos >= N.
+ *   Sliced kernel: id = global slice-group id; see DESIGN.md "Sliced random stream".
+ *   Results therefore do not depend on how envs are sharded over GPUs.
+ */
+#ifndef PBN_B200_H
+#define PBN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBN_MAX_GENES 128
+#define PBN_MAX_ARITY 6
+#define PBN_MAX_BINS 8
+#define PBN_FUNC_INPUT_STRIDE 8
+
+typedef enum {
+  PBN_OK = 0,
+  PBN_ERR_INVALID = -1,     /* bad argument / descriptor */
+  PBN_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  PBN_ERR_UNSUPPORTED = -3, /* network outside what the requested kernel supports */
+  PBN_ERR_NO_ATTRACTORS = -4, /* reset/auto-reset requested before pbn_update_attractors */
+  PBN_ERR_JIT = -5          /* run-time specialisation (NVRTC) failed */
+} pbn_status;
+
+enum { PBN_PERT_NONE = 0, PBN_PERT_A = 1, PBN_PERT_B = 2, PBN_PERT_C = 3 };
+enum { PBN_KERNEL_AUTO = 0, PBN_KERNEL_SCALAR = 1, PBN_KERNEL_SLICED = 2 };
+enum { PBN_RNG_SELECT = 0, PBN_RNG_PERTURB = 1, PBN_RNG_RESET = 2 };
+enum { PBN_STEP_AUTORESET = 1u };
+enum { PBN_UNPACK_U8 = 0, PBN_UNPACK_F32 = 1 };
+
+/* episode statistics accumulated by pbn_step when args->stats != NULL (u64 counters) */
+enum {
+  PBN_STAT_STEPS = 0,       /* env-steps executed */
+  PBN_STAT_EPISODES = 1,    /* episodes finished (terminated | truncated) */
+  PBN_STAT_TERMINATED = 2,  /* ... that reached their target attractor */
+  PBN_STAT_TRUNCATED = 3,   /* ... that ran into the horizon */
+  PBN_STAT_EP_LEN_SUM = 4,  /* sum of t' over finished episodes */
+  PBN_STAT_FLIPS = 5,       /* genes flipped by actions */
+  PBN_STAT_PERTURBED = 6,   /* genes perturbed */
+  PBN_STAT_RESERVED = 7,
+  PBN_N_STATS = 8
+};
+
+typedef struct pbn_handle pbn_handle;
+
+/* Network + env constants.  Replaces the construction work of
+ * gym.make("gym-PBN/BittnerMultiGeneral"|"PBNEnv", ...) (train_BDQ.py:50, train_assa_BQN.py:121-124):
+ * the ISPL/logic-function parsing stays in Python, the truth tables arrive here. */
+typedef struct {
+  int32_t n_genes;              /* N, 1..PBN_MAX_GENES */
+  int32_t n_funcs;              /* F = total number of predictor functions */
+  const int32_t* func_offset;   /* [N+1] CSR: gene i owns functions func_offset[i]..func_offset[i+1]-1 */
+  const uint8_t* func_arity;    /* [F] 0..PBN_MAX_ARITY */
+  const uint8_t* func_inputs;   /* [F*8] gene index feeding bit j of the truth-table index */
+  const uint64_t* func_lut;     /* [F] truth table: bit a = value for input assignment a */
+  const uint32_t* func_cum;     /* [F] cumulative selection thresholds in 2^-32 units (last of a gene ignored) */
+  const uint32_t* survival;     /* [N+1] floor((1-p)^j 2^32) or NULL: computed from perturb_p */
+  int32_t bins;                 /* action bytes per env per step, 1..PBN_MAX_BINS (bdq_model/utils.py:48: 3) */
+  int32_t horizon;              /* steps until truncation; 0 = never (train_BDQ.py:50: 20) */
+  int32_t perturb_mode;         /* PBN_PERT_* */
+  float perturb_p;              /* per-gene perturbation probability */
+  float r_success, r_step, r_action;
+  uint64_t seed;                /* Philox key */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t kernel;               /* PBN_KERNEL_* */
+} pbn_net_desc;
+
+/* Arguments of one step over n_envs instances (device pointers). */
+typedef struct {
+  uint64_t* state;              /* [E*W] in/out */
+  const uint8_t* actions;       /* [E*bins] in; NULL = no interventions (env.step([]), graph_classifier/__init__.py:148) */
+  int32_t* target_id;           /* [E] in (written on auto-reset); NULL = no target test */
+  int32_t* source_id;           /* [E] or NULL; written on auto-reset */
+  uint16_t* t;                  /* [E] in/out episode step counters (env.n_steps) */
+  float* reward;                /* [E] out */
+  uint8_t* terminated;          /* [E] out */
+  uint8_t* truncated;           /* [E] out */
+  uint64_t* final_state;        /* [E*W] or NULL; with auto-reset: the pre-reset next state of every env */
+  const uint64_t* pert_mask;    /* [E*W] injected perturbation masks (pbn_step_injected), may be NULL = none */
+  const uint8_t* sel;           /* [E*N] injected predictor choices (pbn_step_injected) */
+  unsigned long long* stats;    /* [PBN_N_STATS] or NULL */
+  uint64_t* step_ctr_dev;       /* device counter or NULL.  If given, the step uses step_ctr + *step_ctr_dev
+                                   and the launch increments *step_ctr_dev when it completes, so a CUDA graph
+                                   of captured steps keeps advancing the random streams on every replay */
+  uint64_t step_ctr;            /* Philox step counter; the caller increments it every step */
+  int64_t env_offset;           /* global id of env 0 of this call (multiple of 1024) */
+  int64_t n_envs;               /* E */
+  uint32_t flags;               /* PBN_STEP_* */
+  uint32_t reserved;
+} pbn_step_args;
+
+/* gym.make(...) construction: upload truth tables and constants, pick the kernel. */
+int pbn_create(const pbn_net_desc* desc, pbn_handle** out);
+void pbn_destroy(pbn_handle* h);
+
+/* (Re-)upload the attractor table: env.all_attractors may grow during training
+ * (bdq_model/__init__.py:182-184); env.setTarget / in_target / is_attracting_state
+ * (model_tester.py:614-616, graph_classifier/__init__.py:129) read it.
+ * attr_offset[A+1] CSR into care/value [S*W] (HOST pointers).  pair_cum: [A*A] cumulative
+ * u32 thresholds over (source*A + target) pairs for reset sampling -- the curriculum of
+ * env.rework_probas (bdq_model/__init__.py:203) -- or NULL = uniform over source != target. */
+int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint64_t* care,
+                          const uint64_t* value, int32_t n_attractors, const uint32_t* pair_cum,
+                          void* stream);
+
+/* env.step(action) for every instance (bdq_model/__init__.py:177; ddqn_per/__init__.py:354),
+ * randomness from the handle's Philox stream.  args->sel and args->pert_mask must be NULL. */
+int pbn_step(pbn_handle* h, const pbn_step_args* args, void* stream);
+
+/* The same step with injected predictor choices / perturbation masks: the parity entry point
+ * (deterministic core T of SURVEY.md 8a-4).  args->sel must be non-NULL. */
+int pbn_step_injected(pbn_handle* h, const pbn_step_args* args, void* stream);
+
+/* env.reset() (bdq_model/__init__.py:161,204): for envs with done_mask[e] != 0 (all if NULL)
+ * draw (source, target) from the pair table, set state to a random state of the source
+ * attractor ('*' -> 0, model_tester.py:609), t = 0. */
+int pbn_reset(pbn_handle* h, uint64_t* state, int32_t* target_id, int32_t* source_id, uint16_t* t,
+              const uint8_t* done_mask, uint64_t step_ctr, int64_t env_offset, int64_t n_envs,
+              void* stream);
+
+/* env.render() / observation for the agent (bdq_model/__init__.py:92): packed words ->
+ * [E,N] uint8 or float32. */
+int pbn_unpack(pbn_handle* h, const uint64_t* state, void* out, int32_t out_kind, int64_t n_envs,
+               void* stream);
+
+/* Inverse of pbn_unpack: [E,N] uint8 -> packed words (env.graph.setState, model_tester.py:611). */
+int pbn_pack(pbn_handle* h, const uint8_t* bits, uint64_t* state, int64_t n_envs, void* stream);
+
+/* env.is_attracting_state / state_attractor_id: index of the first attractor containing each
+ * state, -1 if none (graph_classifier/__init__.py:129-134; bdq_model/__init__.py:180). */
+int pbn_attractor_id(pbn_handle* h, const uint64_t* state, int32_t* attr_id, int64_t n_envs,
+                     void* stream);
+
+/* Introspection. */
+int pbn_kernel_kind(const pbn_handle* h);            /* PBN_KERNEL_SCALAR or PBN_KERNEL_SLICED */
+int pbn_words_per_state(const pbn_handle* h);        /* W */
+int pbn_launch_count(const pbn_handle* h, uint64_t* out); /* kernels launched through this handle */
+const char* pbn_last_error(void);
+const char* pbn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBN_B200_H */

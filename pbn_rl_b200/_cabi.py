@@ -1,0 +1,141 @@
+"""ctypes binding of libpbn_b200.so (include/pbn_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a call fails, this module
+raises.  PyTorch only lends device memory (``tensor.data_ptr()``) and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+__all__ = ["lib", "load_library", "PbnError", "NetDesc", "StepArgs", "check", "LIB_PATH", "EXPORTS"]
+
+LIB_PATH = Path(__file__).resolve().parent / "libpbn_b200.so"
+
+PBN_OK = 0
+PERT_MODES = {"none": 0, "A": 1, "B": 2, "C": 3}
+KERNEL_KINDS = {"auto": 0, "scalar": 1, "sliced": 2}
+STEP_AUTORESET = 1
+UNPACK_U8, UNPACK_F32 = 0, 1
+N_STATS = 8
+STAT_NAMES = ("steps", "episodes", "terminated", "truncated", "ep_len_sum", "flips", "perturbed", "reserved")
+
+# every symbol include/pbn_b200.h declares (tests check the built library exports them all)
+EXPORTS = (
+    "pbn_create", "pbn_destroy", "pbn_update_attractors", "pbn_step", "pbn_step_injected", "pbn_reset",
+    "pbn_unpack", "pbn_pack", "pbn_attractor_id", "pbn_kernel_kind", "pbn_words_per_state",
+    "pbn_launch_count", "pbn_last_error", "pbn_version",
+)
+
+
+class PbnError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__("pbn_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class NetDesc(C.Structure):
+    _fields_ = [
+        ("n_genes", C.c_int32),
+        ("n_funcs", C.c_int32),
+        ("func_offset", C.c_void_p),
+        ("func_arity", C.c_void_p),
+        ("func_inputs", C.c_void_p),
+        ("func_lut", C.c_void_p),
+        ("func_cum", C.c_void_p),
+        ("survival", C.c_void_p),
+        ("bins", C.c_int32),
+        ("horizon", C.c_int32),
+        ("perturb_mode", C.c_int32),
+        ("perturb_p", C.c_float),
+        ("r_success", C.c_float),
+        ("r_step", C.c_float),
+        ("r_action", C.c_float),
+        ("seed", C.c_uint64),
+        ("device", C.c_int32),
+        ("kernel", C.c_int32),
+    ]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ("state", C.c_void_p),
+        ("actions", C.c_void_p),
+        ("target_id", C.c_void_p),
+        ("source_id", C.c_void_p),
+        ("t", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("terminated", C.c_void_p),
+        ("truncated", C.c_void_p),
+        ("final_state", C.c_void_p),
+        ("pert_mask", C.c_void_p),
+        ("sel", C.c_void_p),
+        ("stats", C.c_void_p),
+        ("step_ctr_dev", C.c_void_p),
+        ("step_ctr", C.c_uint64),
+        ("env_offset", C.c_int64),
+        ("n_envs", C.c_int64),
+        ("flags", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
+    """dlopen the C-ABI library and declare its prototypes.  Raises if it has not been built
+    (``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C pbn_rl_b200/csrc``)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path is not None else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(
+            "%s not found: the CUDA extension is not built (run __graft_entry__.build()); "
+            "pbn_rl_b200 has no CPU fallback" % p)
+    lib = C.CDLL(str(p))
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    lib.pbn_create.argtypes = [C.POINTER(NetDesc), C.POINTER(vp)]
+    lib.pbn_create.restype = C.c_int
+    lib.pbn_destroy.argtypes = [vp]
+    lib.pbn_destroy.restype = None
+    lib.pbn_update_attractors.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    lib.pbn_update_attractors.restype = C.c_int
+    lib.pbn_step.argtypes = [vp, C.POINTER(StepArgs), vp]
+    lib.pbn_step.restype = C.c_int
+    lib.pbn_step_injected.argtypes = [vp, C.POINTER(StepArgs), vp]
+    lib.pbn_step_injected.restype = C.c_int
+    lib.pbn_reset.argtypes = [vp, vp, vp, vp, vp, vp, u64, i64, i64, vp]
+    lib.pbn_reset.restype = C.c_int
+    lib.pbn_unpack.argtypes = [vp, vp, vp, i32, i64, vp]
+    lib.pbn_unpack.restype = C.c_int
+    lib.pbn_pack.argtypes = [vp, vp, vp, i64, vp]
+    lib.pbn_pack.restype = C.c_int
+    lib.pbn_attractor_id.argtypes = [vp, vp, vp, i64, vp]
+    lib.pbn_attractor_id.restype = C.c_int
+    lib.pbn_kernel_kind.argtypes = [vp]
+    lib.pbn_kernel_kind.restype = C.c_int
+    lib.pbn_words_per_state.argtypes = [vp]
+    lib.pbn_words_per_state.restype = C.c_int
+    lib.pbn_launch_count.argtypes = [vp, C.POINTER(u64)]
+    lib.pbn_launch_count.restype = C.c_int
+    lib.pbn_last_error.argtypes = []
+    lib.pbn_last_error.restype = C.c_char_p
+    lib.pbn_version.argtypes = []
+    lib.pbn_version.restype = C.c_char_p
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def lib() -> C.CDLL:
+    return load_library()
+
+
+def check(code: int) -> None:
+    if code != PBN_OK:
+        msg = lib().pbn_last_error()
+        raise PbnError(code, msg.decode("utf-8", "replace") if msg else "")

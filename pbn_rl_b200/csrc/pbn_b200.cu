@@ -1,0 +1,375 @@
+// C-ABI of libpbn_b200.so (include/pbn_b200.h): handle management, table upload, launches.
+// The only translation unit; kernels live in the .cuh files next to it.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pbn_common.cuh"
+#include "step_scalar.cuh"
+
+using namespace pbn;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PBN_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(PBN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+int upload(T** dptr, const T* host, size_t count, cudaStream_t stream = nullptr) {
+  if (*dptr) {
+    cudaFree(*dptr);
+    *dptr = nullptr;
+  }
+  if (count == 0) return PBN_OK;
+  PBN_CUDA(cudaMalloc(reinterpret_cast<void**>(dptr), count * sizeof(T)));
+  PBN_CUDA(cudaMemcpyAsync(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+  PBN_CUDA(cudaStreamSynchronize(stream));  // host buffers are the caller's temporaries
+  return PBN_OK;
+}
+
+}  // namespace
+
+struct pbn_handle {
+  int device = 0;
+  int W = 1;
+  int kernel = PBN_KERNEL_SCALAR;
+  int num_sms = 148;
+  NetParams net{};
+  // owned device tables
+  int32_t* d_func_offset = nullptr;
+  FuncDesc* d_funcs = nullptr;
+  uint32_t* d_func_cum = nullptr;
+  uint32_t* d_survival = nullptr;
+  int32_t* d_attr_offset = nullptr;
+  uint64_t* d_attr_care = nullptr;
+  uint64_t* d_attr_val = nullptr;
+  uint32_t* d_pair_cum = nullptr;
+  unsigned int* d_ticket = nullptr;
+  uint64_t launches = 0;
+  bool scalar_smem_opted = false;
+};
+
+extern "C" {
+
+const char* pbn_last_error(void) { return g_err; }
+const char* pbn_version(void) { return "pbn_b200 0.1 (sm_100a)"; }
+
+int pbn_kernel_kind(const pbn_handle* h) { return h ? h->kernel : PBN_ERR_INVALID; }
+int pbn_words_per_state(const pbn_handle* h) { return h ? h->W : PBN_ERR_INVALID; }
+int pbn_launch_count(const pbn_handle* h, uint64_t* out) {
+  if (!h || !out) return fail(PBN_ERR_INVALID, "pbn_launch_count: null argument");
+  *out = h->launches;
+  return PBN_OK;
+}
+
+void pbn_destroy(pbn_handle* h) {
+  if (!h) return;
+  {
+    DeviceGuard g(h->device);
+    cudaFree(h->d_func_offset);
+    cudaFree(h->d_funcs);
+    cudaFree(h->d_func_cum);
+    cudaFree(h->d_survival);
+    cudaFree(h->d_attr_offset);
+    cudaFree(h->d_attr_care);
+    cudaFree(h->d_attr_val);
+    cudaFree(h->d_pair_cum);
+    cudaFree(h->d_ticket);
+  }
+  delete h;
+}
+
+int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
+  if (!d || !out) return fail(PBN_ERR_INVALID, "pbn_create: null argument");
+  *out = nullptr;
+  const int N = d->n_genes, F = d->n_funcs;
+  if (N < 1 || N > PBN_MAX_GENES) return fail(PBN_ERR_INVALID, "n_genes=%d outside 1..%d", N, PBN_MAX_GENES);
+  if (F < N || !d->func_offset || !d->func_arity || !d->func_inputs || !d->func_lut || !d->func_cum)
+    return fail(PBN_ERR_INVALID, "function tables missing or n_funcs=%d < n_genes=%d", F, N);
+  if (d->bins < 1 || d->bins > PBN_MAX_BINS) return fail(PBN_ERR_INVALID, "bins=%d outside 1..%d", d->bins, PBN_MAX_BINS);
+  if (d->horizon < 0 || d->horizon > 65535) return fail(PBN_ERR_INVALID, "horizon=%d outside 0..65535", d->horizon);
+  if (d->perturb_mode < PBN_PERT_NONE || d->perturb_mode > PBN_PERT_C)
+    return fail(PBN_ERR_INVALID, "perturb_mode=%d unknown", d->perturb_mode);
+  if (!(d->perturb_p >= 0.0f && d->perturb_p < 1.0f)) return fail(PBN_ERR_INVALID, "perturb_p=%g outside [0,1)", d->perturb_p);
+  if (d->func_offset[0] != 0 || d->func_offset[N] != F) return fail(PBN_ERR_INVALID, "func_offset is not a CSR over n_funcs");
+  if (N > 4 * 32) return fail(PBN_ERR_INVALID, "too many genes");
+
+  std::vector<FuncDesc> funcs(F);
+  uint32_t sel_block_mask = 0, max_arity = 0;
+  for (int i = 0; i < N; ++i) {
+    const int f0 = d->func_offset[i], f1 = d->func_offset[i + 1];
+    if (f1 <= f0 || f1 > F) return fail(PBN_ERR_INVALID, "gene %d has no predictor function", i);
+    if (f1 - f0 > 1) sel_block_mask |= 1u << (i >> 2);
+    for (int f = f0; f < f1; ++f) {
+      const int k = d->func_arity[f];
+      if (k > PBN_MAX_ARITY) return fail(PBN_ERR_UNSUPPORTED, "function %d has arity %d > %d", f, k, PBN_MAX_ARITY);
+      max_arity = k > (int)max_arity ? (uint32_t)k : max_arity;
+      uint8_t in[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < k; ++j) {
+        in[j] = d->func_inputs[f * PBN_FUNC_INPUT_STRIDE + j];
+        if (in[j] >= N) return fail(PBN_ERR_INVALID, "function %d input %d out of range", f, j);
+      }
+      const uint64_t lut = d->func_lut[f];
+      const uint64_t kmask = (1ull << k) - 1ull;
+      uint64_t rep = 0;
+      for (int a = 0; a < 64; ++a) rep |= ((lut >> (a & kmask)) & 1ull) << a;
+      funcs[f].lut_lo = (uint32_t)rep;
+      funcs[f].lut_hi = (uint32_t)(rep >> 32);
+      funcs[f].in03 = in[0] | (in[1] << 8) | (in[2] << 16) | ((uint32_t)in[3] << 24);
+      funcs[f].in47 = in[4] | (in[5] << 8) | (in[6] << 16) | ((uint32_t)in[7] << 24);
+    }
+  }
+  std::vector<uint32_t> surv(N + 1);
+  for (int j = 0; j <= N; ++j) {
+    if (d->survival) {
+      surv[j] = d->survival[j];
+    } else {
+      const double v = std::pow(1.0 - (double)d->perturb_p, (double)j) * 4294967296.0;
+      surv[j] = v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
+    }
+  }
+
+  int kernel = d->kernel == PBN_KERNEL_AUTO ? PBN_KERNEL_SCALAR : d->kernel;
+  if (kernel != PBN_KERNEL_SCALAR) return fail(PBN_ERR_UNSUPPORTED, "kernel kind %d not available", d->kernel);
+
+  int ndev = 0;
+  PBN_CUDA(cudaGetDeviceCount(&ndev));
+  if (d->device < 0 || d->device >= ndev) return fail(PBN_ERR_INVALID, "device %d not present (%d visible)", d->device, ndev);
+  DeviceGuard guard(d->device);
+  if (!guard.ok) return fail(PBN_ERR_CUDA, "cannot select device %d", d->device);
+
+  pbn_handle* h = new (std::nothrow) pbn_handle();
+  if (!h) return fail(PBN_ERR_INVALID, "out of host memory");
+  h->device = d->device;
+  h->W = N <= 64 ? 1 : 2;
+  h->kernel = kernel;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, d->device);
+
+  int rc;
+  if ((rc = upload(&h->d_func_offset, d->func_offset, (size_t)N + 1)) != PBN_OK ||
+      (rc = upload(&h->d_funcs, funcs.data(), (size_t)F)) != PBN_OK ||
+      (rc = upload(&h->d_func_cum, d->func_cum, (size_t)F)) != PBN_OK ||
+      (rc = upload(&h->d_survival, surv.data(), (size_t)N + 1)) != PBN_OK) {
+    pbn_destroy(h);
+    return rc;
+  }
+  {
+    const unsigned int zero = 0;
+    if ((rc = upload(&h->d_ticket, &zero, 1)) != PBN_OK) {
+      pbn_destroy(h);
+      return rc;
+    }
+  }
+  NetParams& n = h->net;
+  n.func_offset = h->d_func_offset;
+  n.funcs = h->d_funcs;
+  n.func_cum = h->d_func_cum;
+  n.survival = h->d_survival;
+  n.n_genes = N;
+  n.n_funcs = F;
+  n.bins = d->bins;
+  n.horizon = d->horizon;
+  n.pert_mode = d->perturb_mode;  // injected masks apply even when perturb_p == 0
+  n.pert_rng = d->perturb_p > 0.0f ? 1u : 0u;
+  n.r_success = d->r_success;
+  n.r_step = d->r_step;
+  n.r_action = d->r_action;
+  n.k0 = (uint32_t)d->seed;
+  n.k1 = (uint32_t)(d->seed >> 32);
+  n.sel_block_mask = sel_block_mask;
+  n.max_arity = max_arity;
+  n.pair_last = 0;
+  *out = h;
+  return PBN_OK;
+}
+
+int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint64_t* care, const uint64_t* value,
+                          int32_t n_attractors, const uint32_t* pair_cum, void* stream_) {
+  if (!h) return fail(PBN_ERR_INVALID, "null handle");
+  if (n_attractors < 0 || n_attractors > 46340) return fail(PBN_ERR_INVALID, "n_attractors=%d out of range", n_attractors);
+  if (n_attractors > 0 && (!attr_offset || !care || !value)) return fail(PBN_ERR_INVALID, "attractor tables missing");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int A = n_attractors;
+  const int S = A > 0 ? attr_offset[A] : 0;
+  if (A > 0) {
+    if (attr_offset[0] != 0) return fail(PBN_ERR_INVALID, "attr_offset[0] != 0");
+    for (int a = 0; a < A; ++a)
+      if (attr_offset[a + 1] <= attr_offset[a]) return fail(PBN_ERR_INVALID, "attractor %d is empty", a);
+  }
+  // the previous tables may still be read by kernels in flight on the caller's stream
+  PBN_CUDA(cudaStreamSynchronize(stream));
+  int rc;
+  if ((rc = upload(&h->d_attr_offset, attr_offset, (size_t)(A > 0 ? A + 1 : 0), stream)) != PBN_OK) return rc;
+  if ((rc = upload(&h->d_attr_care, care, (size_t)S * h->W, stream)) != PBN_OK) return rc;
+  if ((rc = upload(&h->d_attr_val, value, (size_t)S * h->W, stream)) != PBN_OK) return rc;
+  int pair_last = 0;
+  if (pair_cum && A > 0) {
+    uint32_t prev = 0;
+    for (int k = 0; k < A * A; ++k) {
+      if (pair_cum[k] < prev) return fail(PBN_ERR_INVALID, "pair_cum is not non-decreasing at %d", k);
+      if (pair_cum[k] > prev || (k == 0 && pair_cum[0] > 0)) pair_last = k;
+      prev = pair_cum[k];
+    }
+    if ((rc = upload(&h->d_pair_cum, pair_cum, (size_t)A * A, stream)) != PBN_OK) return rc;
+  } else if (h->d_pair_cum) {
+    cudaFree(h->d_pair_cum);
+    h->d_pair_cum = nullptr;
+  }
+  NetParams& n = h->net;
+  n.attr_offset = h->d_attr_offset;
+  n.attr_care = h->d_attr_care;
+  n.attr_val = h->d_attr_val;
+  n.pair_cum = h->d_pair_cum;
+  n.n_attr = A;
+  n.n_attr_states = S;
+  n.pair_last = pair_last;
+  return PBN_OK;
+}
+
+static int grid_for(const pbn_handle* h, int64_t n, int block, int per_sm) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = (int64_t)h->num_sms * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, bool injected) {
+  if (!h || !a) return fail(PBN_ERR_INVALID, "null argument");
+  if (a->n_envs < 0) return fail(PBN_ERR_INVALID, "n_envs=%lld", (long long)a->n_envs);
+  if (a->n_envs == 0) return PBN_OK;
+  if (!a->state) return fail(PBN_ERR_INVALID, "state is null");
+  if (injected && !a->sel) return fail(PBN_ERR_INVALID, "pbn_step_injected needs args->sel");
+  if (!injected && (a->sel || a->pert_mask)) return fail(PBN_ERR_INVALID, "pbn_step: sel/pert_mask must be null (use pbn_step_injected)");
+  if (a->env_offset < 0 || (a->env_offset & 1023)) return fail(PBN_ERR_INVALID, "env_offset=%lld must be a non-negative multiple of 1024", (long long)a->env_offset);
+  if (a->target_id && h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "target_id given but no attractor table uploaded");
+  if (a->flags & PBN_STEP_AUTORESET) {
+    if (h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "auto-reset needs pbn_update_attractors first");
+    if (!a->target_id || !a->t) return fail(PBN_ERR_INVALID, "auto-reset needs target_id and t");
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  StepParams p;
+  p.a = *a;
+  p.n = h->net;
+  p.ticket = h->d_ticket;
+  const ScalarSmemLayout L = scalar_smem_layout(h->net, h->W);
+  if (L.total > 200u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "network tables need %u B of shared memory", L.total);
+  const int block = 256;
+  const int grid = grid_for(h, a->n_envs, block, 8);
+  const bool wide = h->net.max_arity > 4;
+#define PBN_LAUNCH_SCALAR(WW, MA)                                                                          \
+  do {                                                                                                     \
+    if (L.total > 48u * 1024u && !h->scalar_smem_opted) {                                                  \
+      PBN_CUDA(cudaFuncSetAttribute(step_scalar_kernel<WW, MA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total)); \
+    }                                                                                                      \
+    step_scalar_kernel<WW, MA><<<grid, block, L.total, stream>>>(p, L);                                    \
+  } while (0)
+  if (h->W == 1) {
+    if (wide) PBN_LAUNCH_SCALAR(1, 6); else PBN_LAUNCH_SCALAR(1, 4);
+  } else {
+    if (wide) PBN_LAUNCH_SCALAR(2, 6); else PBN_LAUNCH_SCALAR(2, 4);
+  }
+#undef PBN_LAUNCH_SCALAR
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_step(pbn_handle* h, const pbn_step_args* a, void* stream) { return step_common(h, a, stream, false); }
+int pbn_step_injected(pbn_handle* h, const pbn_step_args* a, void* stream) { return step_common(h, a, stream, true); }
+
+int pbn_reset(pbn_handle* h, uint64_t* state, int32_t* target_id, int32_t* source_id, uint16_t* t,
+              const uint8_t* done_mask, uint64_t step_ctr, int64_t env_offset, int64_t n_envs, void* stream_) {
+  if (!h) return fail(PBN_ERR_INVALID, "null handle");
+  if (n_envs < 0 || !state) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  if (h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "pbn_reset needs pbn_update_attractors first");
+  if (env_offset < 0 || (env_offset & 1023)) return fail(PBN_ERR_INVALID, "env_offset must be a non-negative multiple of 1024");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, n_envs, 256, 8);
+  if (h->W == 1)
+    reset_kernel<1><<<grid, 256, 0, stream>>>(h->net, state, target_id, source_id, t, done_mask, step_ctr, env_offset, n_envs);
+  else
+    reset_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, target_id, source_id, t, done_mask, step_ctr, env_offset, n_envs);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_unpack(pbn_handle* h, const uint64_t* state, void* out, int32_t out_kind, int64_t n_envs, void* stream_) {
+  if (!h || !state || !out || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, n_envs * h->net.n_genes, 256, 8);
+  if (out_kind == PBN_UNPACK_U8)
+    unpack_kernel<uint8_t><<<grid, 256, 0, stream>>>(state, static_cast<uint8_t*>(out), h->net.n_genes, h->W, n_envs);
+  else if (out_kind == PBN_UNPACK_F32)
+    unpack_kernel<float><<<grid, 256, 0, stream>>>(state, static_cast<float*>(out), h->net.n_genes, h->W, n_envs);
+  else
+    return fail(PBN_ERR_INVALID, "out_kind=%d unknown", out_kind);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_pack(pbn_handle* h, const uint8_t* bits, uint64_t* state, int64_t n_envs, void* stream_) {
+  if (!h || !state || !bits || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, n_envs * h->W, 256, 8);
+  pack_kernel<<<grid, 256, 0, stream>>>(bits, state, h->net.n_genes, h->W, n_envs);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_attractor_id(pbn_handle* h, const uint64_t* state, int32_t* attr_id, int64_t n_envs, void* stream_) {
+  if (!h || !state || !attr_id || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, n_envs, 256, 8);
+  if (h->W == 1)
+    attractor_id_kernel<1><<<grid, 256, 0, stream>>>(h->net, state, attr_id, n_envs);
+  else
+    attractor_id_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, attr_id, n_envs);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+}  // extern "C"

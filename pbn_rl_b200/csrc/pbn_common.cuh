@@ -1,0 +1,129 @@
+// Shared device-side definitions: kernel parameter block, table views, small helpers.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "../../include/pbn_b200.h"
+#include "philox.cuh"
+
+namespace pbn {
+
+// One predictor function, 16 bytes: 64-bit truth table (replicated over unused inputs, so a
+// fixed-arity gather is branch-free) + 8 input gene indices.
+struct __align__(16) FuncDesc {
+  uint32_t lut_lo, lut_hi;
+  uint32_t in03;  // inputs 0..3, one byte each
+  uint32_t in47;  // inputs 4..7
+};
+
+// Everything a kernel needs besides the per-call arrays.  Passed by value (__grid_constant__).
+struct NetParams {
+  const int32_t* func_offset;   // [N+1]
+  const FuncDesc* funcs;        // [F]
+  const uint32_t* func_cum;     // [F]
+  const uint32_t* survival;     // [N+1]
+  const int32_t* attr_offset;   // [A+1]
+  const uint64_t* attr_care;    // [S*W]
+  const uint64_t* attr_val;     // [S*W]
+  const uint32_t* pair_cum;     // [A*A] or nullptr
+  int32_t n_genes, n_funcs, bins, horizon, pert_mode;
+  int32_t n_attr, n_attr_states, pair_last;
+  float r_success, r_step, r_action;
+  uint32_t k0, k1;
+  uint32_t sel_block_mask;      // bit b set: SELECT block b (genes 4b..4b+3) has a gene with >1 predictor
+  uint32_t max_arity;
+  uint32_t pert_rng;             // 1: draw perturbations from the stream (perturb_p > 0)
+};
+
+struct StepParams {
+  pbn_step_args a;
+  NetParams n;
+  unsigned int* ticket;  // handle-owned; used to bump *a.step_ctr_dev once per launch
+};
+
+// Effective Philox step counter of this launch (host part + optional device-resident part).
+__device__ __forceinline__ uint64_t effective_step(const pbn_step_args& a) {
+  uint64_t step = a.step_ctr;
+  if (a.step_ctr_dev != nullptr) step += *reinterpret_cast<const volatile uint64_t*>(a.step_ctr_dev);
+  return step;
+}
+
+// Called by every thread at the very end of a step kernel: the last CTA to finish increments the
+// device-resident step counter (every CTA read it before any CTA could get here last).
+__device__ __forceinline__ void bump_device_step(const pbn_step_args& a, unsigned int* ticket) {
+  if (a.step_ctr_dev == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *ticket = 0;
+      *a.step_ctr_dev += 1;
+      __threadfence();
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// number of entries k in the non-increasing table tab[1..n] with u < tab[k]   (geometric skip)
+__device__ __forceinline__ int count_below_survival(const uint32_t* tab, int n, uint32_t u) {
+  int lo = 0, hi = n;  // invariant: u < tab[lo] (tab[0] = 2^32 conceptually), !(u < tab[hi+1])
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (u < tab[mid]) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// number of entries k in [0, n) of the non-decreasing table with tab[k] <= u
+__device__ __forceinline__ int count_le(const uint32_t* tab, int n, uint32_t u) {
+  int lo = 0, hi = n;  // answer in [lo, hi]
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (tab[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// (source, target) draw + source state for env.reset(); r = Philox block (RESET, 0) of the env.
+template <int W>
+__device__ __forceinline__ void reset_draw(const NetParams& n, const Philox4& r, uint64_t (&s)[W], int& src,
+                                           int& tgt) {
+  const int A = n.n_attr;
+  if (n.pair_cum != nullptr) {
+    int pair = count_le(n.pair_cum, A * A - 1, r.x);
+    pair = min(pair, n.pair_last);
+    src = pair / A;
+    tgt = pair - src * A;
+  } else if (A > 1) {
+    const uint32_t q = __umulhi(r.x, (uint32_t)(A * (A - 1)));
+    src = (int)(q / (uint32_t)(A - 1));
+    const int tt = (int)(q - (uint32_t)src * (uint32_t)(A - 1));
+    tgt = tt + (tt >= src ? 1 : 0);
+  } else {
+    src = 0;
+    tgt = 0;
+  }
+  const int o0 = n.attr_offset[src];
+  const int ns = n.attr_offset[src + 1] - o0;
+  const int j = o0 + (int)__umulhi(r.y, (uint32_t)ns);
+#pragma unroll
+  for (int w = 0; w < W; ++w) s[w] = n.attr_val[(size_t)j * W + w];
+}
+
+template <int W>
+__device__ __forceinline__ bool in_attractor(const int32_t* offs, const uint64_t* care, const uint64_t* val,
+                                             int a, const uint64_t (&s)[W]) {
+  bool hit = false;
+  const int e1 = offs[a + 1];
+  for (int e = offs[a]; e < e1; ++e) {
+    bool m = true;
+#pragma unroll
+    for (int w = 0; w < W; ++w) m = m && ((s[w] & care[(size_t)e * W + w]) == val[(size_t)e * W + w]);
+    hit = hit || m;
+  }
+  return hit;
+}
+
+}  // namespace pbn

@@ -1,0 +1,334 @@
+"""Batched PBN environment: E independent env instances stepped by one kernel launch.
+
+This is the batched surface of the drop-in: the per-instance gym API
+of the reference (``env.reset()`` / ``env.step(a)``, bdq_model/__init__.py:161-204) is
+served by :mod:`pbn_rl_b200.gym_env` on top of this class with ``num_envs=1``; throughput
+work uses it directly.  All tensors are torch CUDA tensors owned by Python; the extension
+only sees raw pointers and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import NetDesc, StepArgs, check
+from .attractors import AttractorSet
+from .network import PBNNetwork
+
+__all__ = ["VecPBNEnv", "survival_table", "pair_thresholds"]
+
+
+def survival_table(p: float, n_genes: int) -> np.ndarray:
+    """``S[j] = floor((1-p)^j * 2^32)`` clamped to u32 -- the geometric-skip table of the
+    perturbation stream (include/pbn_b200.h, "Random streams")."""
+    out = np.zeros(n_genes + 1, dtype=np.uint32)
+    for j in range(n_genes + 1):
+        out[j] = min(int(((1.0 - p) ** j) * 4294967296.0), 0xFFFFFFFF)
+    return out
+
+
+def pair_thresholds(weights: np.ndarray) -> np.ndarray:
+    """A x A non-negative (source, target) weights -> cumulative u32 thresholds [A*A]."""
+    w = np.asarray(weights, dtype=np.float64).reshape(-1)
+    if (w < 0).any() or w.sum() <= 0:
+        raise ValueError("pair weights must be non-negative with a positive sum")
+    cum = np.cumsum(w / w.sum())
+    thr = np.minimum(np.rint(cum * 4294967296.0), 4294967295.0).astype(np.uint64).astype(np.uint32)
+    last = int(np.nonzero(w)[0][-1])
+    thr[last:] = 0xFFFFFFFF
+    return thr
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class VecPBNEnv:
+    """``num_envs`` PBN env instances resident on one GPU.
+
+    Parameters mirror the reference's ``gym.make`` kwargs where they exist (``horizon``,
+    train_BDQ.py:50) and expose every constant the reference tree does not pin:
+    ``perturb_p`` / ``perturb_mode`` (A: Shmulevich, a perturbed step skips the update; B:
+    update then flip; C: per-gene), the reward constants and the Philox ``seed``.
+    ``env_offset`` is the global id of env 0 (a multiple of 1024): shards of one logical batch
+    on several GPUs draw exactly the randomness the single-GPU batch would.
+    ``device_counter=True`` keeps the Philox step counter in device memory (incremented by each
+    step launch), so steps captured in a CUDA graph keep advancing their random streams on
+    every replay.
+    """
+
+    def __init__(self, network: PBNNetwork, num_envs: int, attractors: Optional[AttractorSet] = None,
+                 device: Union[str, torch.device, int] = "cuda:0", seed: int = 0x5EED, horizon: int = 20,
+                 bins: int = 3, perturb_p: float = 0.0, perturb_mode: str = "A", r_success: float = 5.0,
+                 r_step: float = 0.0, r_action: float = -1.0, kernel: str = "auto", env_offset: int = 0,
+                 auto_reset: bool = False, pair_weights: Optional[np.ndarray] = None,
+                 device_counter: bool = False):
+        self._h = None
+        self.lib = _cabi.lib()  # raises if the CUDA extension is not built: no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("pbn_rl_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.device = torch.device(device if not isinstance(device, int) else "cuda:%d" % device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.network = network
+        self.num_envs = int(num_envs)
+        self.n_genes = network.n_genes
+        self.n_words = network.n_words
+        self.bins = int(bins)
+        self.horizon = int(horizon)
+        self.auto_reset = bool(auto_reset)
+        self.env_offset = int(env_offset)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.step_ctr = 0
+        self.perturb_p = float(perturb_p)
+        self.perturb_mode = perturb_mode
+
+        arr = network.descriptor_arrays()
+        self._keep = arr  # host arrays must outlive pbn_create
+        surv = survival_table(self.perturb_p, self.n_genes)
+        d = NetDesc()
+        d.n_genes = self.n_genes
+        d.n_funcs = network.n_functions
+        d.func_offset = arr["func_offset"].ctypes.data
+        d.func_arity = arr["func_arity"].ctypes.data
+        d.func_inputs = arr["func_inputs"].ctypes.data
+        d.func_lut = arr["func_lut"].ctypes.data
+        d.func_cum = arr["func_cum"].ctypes.data
+        d.survival = surv.ctypes.data
+        d.bins = self.bins
+        d.horizon = self.horizon
+        d.perturb_mode = _cabi.PERT_MODES[perturb_mode]
+        d.perturb_p = self.perturb_p
+        d.r_success, d.r_step, d.r_action = float(r_success), float(r_step), float(r_action)
+        d.seed = self.seed
+        d.device = self.device.index
+        d.kernel = _cabi.KERNEL_KINDS[kernel]
+        h = C.c_void_p()
+        check(self.lib.pbn_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self.kernel = {1: "scalar", 2: "sliced"}[self.lib.pbn_kernel_kind(self._h)]
+
+        e, w = self.num_envs, self.n_words
+        dev = self.device
+        self.state = torch.zeros((e, w), dtype=torch.int64, device=dev)
+        self.target_id = torch.full((e,), -1, dtype=torch.int32, device=dev)
+        self.source_id = torch.full((e,), -1, dtype=torch.int32, device=dev)
+        self.t = torch.zeros((e,), dtype=torch.int16, device=dev)  # uint16 payload
+        self.reward = torch.zeros((e,), dtype=torch.float32, device=dev)
+        self.terminated = torch.zeros((e,), dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros((e,), dtype=torch.uint8, device=dev)
+        self.stats_buf = torch.zeros((_cabi.N_STATS,), dtype=torch.int64, device=dev)
+        self.step_ctr_dev = torch.zeros((1,), dtype=torch.int64, device=dev) if device_counter else None
+        self._reset_ctr = 0
+        self.attractors: Optional[AttractorSet] = None
+        self._host = None
+        if attractors is not None:
+            self.set_attractors(attractors, pair_weights)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.pbn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def launches(self) -> int:
+        out = C.c_uint64()
+        check(self.lib.pbn_launch_count(self._h, C.byref(out)))
+        return out.value
+
+    # ------------------------------------------------------------------ tables
+    def set_attractors(self, attractors: AttractorSet, pair_weights: Optional[np.ndarray] = None) -> None:
+        """Upload / replace the attractor table (``env.all_attractors`` may grow during
+        training, bdq_model/__init__.py:182-184) and the (source, target) sampling weights
+        (the curriculum of ``env.rework_probas``)."""
+        if attractors.n_genes != self.n_genes:
+            raise ValueError("attractor states have %d genes, network has %d" % (attractors.n_genes, self.n_genes))
+        offs, care, val = attractors.tables()
+        care = np.ascontiguousarray(care)
+        val = np.ascontiguousarray(val)
+        thr = None
+        if pair_weights is not None:
+            pw = np.asarray(pair_weights, dtype=np.float64)
+            if pw.shape != (len(attractors), len(attractors)):
+                raise ValueError("pair_weights must be [A, A]")
+            thr = pair_thresholds(pw)
+        check(self.lib.pbn_update_attractors(
+            self._h, offs.ctypes.data, care.ctypes.data, val.ctypes.data, len(attractors),
+            None if thr is None else thr.ctypes.data, self._stream()))
+        self.attractors = attractors
+        self.pair_weights = pair_weights
+
+    # ------------------------------------------------------------------ env API
+    def reset(self, mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``env.reset()`` for every instance (or those with ``mask != 0``): returns
+        ``(state_words [E,W] int64, target_id [E] int32)``."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if self.step_ctr_dev is None:
+            ctr = self.step_ctr
+            self.step_ctr += 1
+        else:  # explicit resets draw from their own half of the 48-bit counter space
+            ctr = (1 << 47) | self._reset_ctr
+            self._reset_ctr += 1
+        check(self.lib.pbn_reset(self._h, _ptr(self.state), _ptr(self.target_id), _ptr(self.source_id),
+                                 _ptr(self.t), _ptr(mask), ctr, self.env_offset, self.num_envs,
+                                 self._stream()))
+        return self.state, self.target_id
+
+    def _args(self, actions: Optional[torch.Tensor], final_state: Optional[torch.Tensor], stats: bool) -> StepArgs:
+        a = StepArgs()
+        a.state = _ptr(self.state)
+        a.actions = _ptr(actions)
+        a.target_id = _ptr(self.target_id) if self.attractors is not None else None
+        a.source_id = _ptr(self.source_id)
+        a.t = _ptr(self.t)
+        a.reward = _ptr(self.reward)
+        a.terminated = _ptr(self.terminated)
+        a.truncated = _ptr(self.truncated)
+        a.final_state = _ptr(final_state)
+        a.stats = _ptr(self.stats_buf) if stats else None
+        a.step_ctr_dev = _ptr(self.step_ctr_dev)
+        a.step_ctr = self.step_ctr
+        a.env_offset = self.env_offset
+        a.n_envs = self.num_envs
+        a.flags = _cabi.STEP_AUTORESET if self.auto_reset else 0
+        return a
+
+    def _check_actions(self, actions: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if actions is None:
+            return None
+        if actions.dtype != torch.uint8 or actions.device != self.device or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        if actions.numel() != self.num_envs * self.bins:
+            raise ValueError("actions must hold num_envs*bins = %d bytes" % (self.num_envs * self.bins))
+        return actions
+
+    def step(self, actions: Optional[torch.Tensor], final_state: Optional[torch.Tensor] = None,
+             stats: bool = True):
+        """One ``env.step`` for every instance.  ``actions``: uint8 ``[E, bins]`` with values in
+        ``[0, N]`` (0 = no-op, k flips gene k-1), or ``None`` for an uncontrolled update
+        (``env.step([])``).  Returns ``(state, reward, terminated, truncated)`` -- views of the
+        env's own tensors, overwritten by the next call."""
+        actions = self._check_actions(actions)
+        a = self._args(actions, final_state, stats)
+        check(self.lib.pbn_step(self._h, C.byref(a), self._stream()))
+        if self.step_ctr_dev is None:
+            self.step_ctr += 1
+        return self.state, self.reward, self.terminated, self.truncated
+
+    def step_injected(self, actions: Optional[torch.Tensor], sel: torch.Tensor,
+                      pert_mask: Optional[torch.Tensor] = None, final_state: Optional[torch.Tensor] = None,
+                      stats: bool = True):
+        """The same step with injected predictor choices ``sel`` (uint8 ``[E, N]``) and
+        perturbation masks ``pert_mask`` (int64 ``[E, W]``): the deterministic core the parity
+        tests compare bit for bit with the oracle."""
+        actions = self._check_actions(actions)
+        sel = sel.to(device=self.device, dtype=torch.uint8).contiguous()
+        if sel.numel() != self.num_envs * self.n_genes:
+            raise ValueError("sel must be [E, N]")
+        if pert_mask is not None:
+            pert_mask = pert_mask.to(device=self.device, dtype=torch.int64).contiguous()
+            if pert_mask.numel() != self.num_envs * self.n_words:
+                raise ValueError("pert_mask must be [E, W]")
+        a = self._args(actions, final_state, stats)
+        a.sel = _ptr(sel)
+        a.pert_mask = _ptr(pert_mask)
+        check(self.lib.pbn_step_injected(self._h, C.byref(a), self._stream()))
+        if self.step_ctr_dev is None:
+            self.step_ctr += 1
+        return self.state, self.reward, self.terminated, self.truncated
+
+    # ------------------------------------------------------------------ host-buffer path (end-to-end API)
+    def step_host(self, actions_host: np.ndarray) -> Dict[str, np.ndarray]:
+        """``step`` with HOST buffers: copies ``actions_host`` (uint8 ``[E, bins]``) to the device,
+        steps, and copies state / reward / terminated / truncated back into pinned host
+        buffers that are returned as numpy views (valid until the next call).  This is the
+        call a user of the reference's CPU env would make per step."""
+        if self._host is None:
+            e, w = self.num_envs, self.n_words
+            pin = dict(pin_memory=True)
+            self._host = {
+                "actions": torch.empty((e, self.bins), dtype=torch.uint8, **pin),
+                "state": torch.empty((e, w), dtype=torch.int64, **pin),
+                "reward": torch.empty((e,), dtype=torch.float32, **pin),
+                "terminated": torch.empty((e,), dtype=torch.uint8, **pin),
+                "truncated": torch.empty((e,), dtype=torch.uint8, **pin),
+                "d_actions": torch.empty((e, self.bins), dtype=torch.uint8, device=self.device),
+            }
+        hb = self._host
+        hb["actions"].numpy()[...] = np.asarray(actions_host, dtype=np.uint8).reshape(self.num_envs, self.bins)
+        hb["d_actions"].copy_(hb["actions"], non_blocking=True)
+        self.step(hb["d_actions"])
+        hb["state"].copy_(self.state, non_blocking=True)
+        hb["reward"].copy_(self.reward, non_blocking=True)
+        hb["terminated"].copy_(self.terminated, non_blocking=True)
+        hb["truncated"].copy_(self.truncated, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: hb[k].numpy() for k in ("state", "reward", "terminated", "truncated")}
+
+    @property
+    def host_bytes_per_step(self) -> Tuple[int, int]:
+        """(host->device, device->host) bytes moved by one :meth:`step_host`."""
+        e = self.num_envs
+        return e * self.bins, e * (8 * self.n_words + 4 + 1 + 1)
+
+    # ------------------------------------------------------------------ state access
+    def set_state(self, state: Union[torch.Tensor, np.ndarray], packed: Optional[bool] = None) -> None:
+        """``env.graph.setState`` for all instances: ``[E, N]`` 0/1 values or packed ``[E, W]`` words."""
+        st = torch.as_tensor(state)
+        if packed is None:
+            packed = st.dtype in (torch.int64, torch.uint64) and st.shape[-1] == self.n_words and self.n_genes != self.n_words
+        if packed:
+            self.state.copy_(st.to(torch.int64).reshape(self.num_envs, self.n_words))
+        else:
+            bits = st.to(device=self.device, dtype=torch.uint8).reshape(self.num_envs, self.n_genes).contiguous()
+            check(self.lib.pbn_pack(self._h, _ptr(bits), _ptr(self.state), self.num_envs, self._stream()))
+
+    def set_target(self, target_id: Union[int, torch.Tensor, np.ndarray]) -> None:
+        if isinstance(target_id, int):
+            self.target_id.fill_(target_id)
+        else:
+            self.target_id.copy_(torch.as_tensor(target_id).to(torch.int32).reshape(self.num_envs))
+
+    def unpack(self, words: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.uint8) -> torch.Tensor:
+        """Packed words -> ``[E, N]`` uint8 or float32 (the agent's input layer, bdq_model/__init__.py:92)."""
+        words = self.state if words is None else words.to(device=self.device, dtype=torch.int64).contiguous()
+        e = words.shape[0]
+        out = torch.empty((e, self.n_genes), dtype=dtype, device=self.device)
+        kind = {torch.uint8: _cabi.UNPACK_U8, torch.float32: _cabi.UNPACK_F32}[dtype]
+        check(self.lib.pbn_unpack(self._h, _ptr(words), _ptr(out), kind, e, self._stream()))
+        return out
+
+    def attractor_ids(self, words: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Index of the attractor containing each state (-1: none): ``is_attracting_state`` /
+        ``state_attractor_id`` of the reference env."""
+        if self.attractors is None:
+            raise RuntimeError("no attractor table")
+        words = self.state if words is None else words.to(device=self.device, dtype=torch.int64).contiguous()
+        e = words.shape[0]
+        out = torch.empty((e,), dtype=torch.int32, device=self.device)
+        check(self.lib.pbn_attractor_id(self._h, _ptr(words), _ptr(out), e, self._stream()))
+        return out
+
+    def stats(self, reset: bool = False) -> Dict[str, int]:
+        """Episode statistics accumulated on the device since the last reset of the counters."""
+        vals = self.stats_buf.cpu().tolist()
+        if reset:
+            self.stats_buf.zero_()
+        return dict(zip(_cabi.STAT_NAMES[:7], vals[:7]))
