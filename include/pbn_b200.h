@@ -54,7 +54,18 @@
 #ifndef PBN_B200_H
 #define PBN_B200_H
 
+#ifdef __CUDACC_RTC__ /* NVRTC (run-time specialisation of the sliced kernel) has no libc headers */
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -110,7 +121,7 @@ typedef struct {
   int32_t bins;                 /* action bytes per env per step, 1..PBN_MAX_BINS (bdq_model/utils.py:48: 3) */
   int32_t horizon;              /* steps until truncation; 0 = never (train_BDQ.py:50: 20) */
   int32_t perturb_mode;         /* PBN_PERT_* */
-  float perturb_p;              /* per-gene perturbation probability */
+  double perturb_p;             /* per-gene perturbation probability */
   float r_success, r_step, r_action;
   uint64_t seed;                /* Philox key */
   int32_t device;               /* CUDA device ordinal */
@@ -187,6 +198,15 @@ int pbn_attractor_id(pbn_handle* h, const uint64_t* state, int32_t* attr_id, int
 int pbn_kernel_kind(const pbn_handle* h);            /* PBN_KERNEL_SCALAR or PBN_KERNEL_SLICED */
 int pbn_words_per_state(const pbn_handle* h);        /* W */
 int pbn_launch_count(const pbn_handle* h, uint64_t* out); /* kernels launched through this handle */
+
+/* Load-time specialisation.  pbn_jit_source writes the CUDA source generated for this network
+ * (the predictor functions as LOP3 trees + selection logic, net_gen.cuh / net_update.inc) into
+ * buf (NUL-terminated, truncated to len) and returns the full length, or a negative status if
+ * the network is not eligible for the sliced kernel.  pbn_jit_precompile compiles that
+ * specialisation with NVRTC for sm_100a into the on-disk cache (no GPU needed), so that a later
+ * pbn_create on the GPU box only loads the cubin. */
+int64_t pbn_jit_source(const pbn_net_desc* desc, int injected, char* buf, int64_t len);
+int pbn_jit_precompile(const pbn_net_desc* desc);
 const char* pbn_last_error(void);
 const char* pbn_version(void);
 

@@ -506,3 +506,129 @@ def stream_reset(tables, n_attr: int, env_ids: np.ndarray, step_ctr: int, seed: 
     ns = (offs[src + 1] - offs[src]).astype(np.uint64)
     j = o0 + ((u1 * ns) >> np.uint64(32)).astype(np.int64)
     return val[j], src.astype(np.int32), tgt.astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------
+# Sliced kernel streams (pbn_rl_b200/csrc/step_sliced.cuh, DESIGN.md "Sliced random stream")
+# --------------------------------------------------------------------------------------
+
+KIND_FIX = 3
+
+
+def sliced_coords(env_ids: np.ndarray):
+    """global env id -> (slice-group id, slice bit)."""
+    e = np.asarray(env_ids, dtype=np.uint64)
+    gid = ((e >> np.uint64(10)) << np.uint64(5)) | ((e >> np.uint64(2)) & np.uint64(31))
+    bit = (((e >> np.uint64(7)) & np.uint64(7)) << np.uint64(2)) | (e & np.uint64(3))
+    return gid, bit.astype(np.int64)
+
+
+def sliced_survival(p: float, n: int) -> np.ndarray:
+    slots = 32 * n
+    out = np.zeros(slots + 1, dtype=np.uint64)
+    for j in range(slots + 1):
+        out[j] = min(int(((1.0 - p) ** j) * 4294967296.0), 0xFFFFFFFF)
+    return out
+
+
+class _WordStream:
+    """Sequential 32-bit words of one (group, step, kind) stream, block by block."""
+
+    def __init__(self, gid, step_ctr, kind, k0, k1):
+        self.gid, self.step, self.kind, self.k0, self.k1 = gid, step_ctr, kind, k0, k1
+        self.next = 0
+        self.blk = None
+
+    def word(self):
+        if (self.next & 3) == 0:
+            r = philox4x32(*_ctr(np.array([self.gid], dtype=np.uint64), self.step, self.kind, self.next >> 2),
+                           self.k0, self.k1)
+            self.blk = [int(x[0]) for x in r]
+        w = self.blk[self.next & 3]
+        self.next += 1
+        return w
+
+
+def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: int, seed: int):
+    """(sel[E,N], pert[E,W]) exactly as the sliced kernel draws them for the given global env ids."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    e = env_ids.shape[0]
+    n = net.n
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    gid, bit = sliced_coords(env_ids)
+    groups, inv = np.unique(gid, return_inverse=True)
+    ng = len(groups)
+    ks = [len(ps) for ps in net.probs]
+    nw = {1: 0, 2: 1, 4: 2, 3: 6}
+    total_words = sum(nw[k] for k in ks)
+    n_blocks = (total_words + 3) // 4
+    words = np.zeros((ng, max(4 * n_blocks, 4)), dtype=np.uint64)
+    for b in range(n_blocks):
+        r = philox4x32(*_ctr(groups, step_ctr, KIND_SELECT, b), k0, k1)
+        for q in range(4):
+            words[:, 4 * b + q] = r[q]
+    s0 = np.zeros((ng, n), dtype=np.uint64)
+    s1 = np.zeros((ng, n), dtype=np.uint64)
+    rej = np.zeros((ng, n), dtype=np.uint64)
+    off = 0
+    for i, k in enumerate(ks):
+        w = [words[:, off + q] for q in range(nw[k])]
+        off += nw[k]
+        if k == 2:
+            s0[:, i] = w[0]
+        elif k == 4:
+            s0[:, i], s1[:, i] = w[0], w[1]
+        elif k == 3:
+            b0, b1 = w[0].copy(), w[1].copy()
+            r_ = b0 & b1
+            for c0, c1 in ((w[2], w[3]), (w[4], w[5])):
+                b0 = np.where(True, (b0 & ~r_) | (c0 & r_), b0)
+                b1 = (b1 & ~r_) | (c1 & r_)
+                r_ = r_ & c0 & c1
+            s0[:, i], s1[:, i], rej[:, i] = b0, b1, r_
+    for g in range(ng):  # FIX stream: sequential per group
+        if not rej[g].any():
+            continue
+        ws = _WordStream(int(groups[g]), step_ctr, KIND_FIX, k0, k1)
+        cur, left = 0, 0
+        for i in range(n):
+            r_ = int(rej[g, i])
+            while r_:
+                if left == 0:
+                    cur, left = ws.word(), 16
+                pr = cur & 3
+                cur >>= 2
+                left -= 1
+                if pr != 3:
+                    m = r_ & -r_
+                    r_ ^= m
+                    if not pr & 1:
+                        s0[g, i] = int(s0[g, i]) ^ m
+                    if not pr & 2:
+                        s1[g, i] = int(s1[g, i]) ^ m
+    sh = bit.astype(np.uint64)[:, None]
+    sel = (((s0[inv] >> sh) & np.uint64(1)) + 2 * ((s1[inv] >> sh) & np.uint64(1))).astype(np.uint8)
+    for i, k in enumerate(ks):
+        if k == 1:
+            sel[:, i] = 0
+    # perturbation events per group
+    wds = 1 if n <= 64 else 2
+    pert = np.zeros((e, wds), dtype=np.uint64)
+    if p > 0:
+        surv = sliced_survival(p, n)
+        slots = 32 * n
+        planes = np.zeros((ng, n), dtype=np.uint64)
+        for g in range(ng):
+            ws = _WordStream(int(groups[g]), step_ctr, KIND_PERTURB, k0, k1)
+            pos = -1
+            while True:
+                u = ws.word()
+                skip = int(np.searchsorted(-surv[1:].astype(np.int64), -u, side="left"))  # #{j>=1: u < S[j]}
+                pos += skip + 1
+                if pos >= slots:
+                    break
+                planes[g, pos >> 5] |= np.uint64(1) << np.uint64(pos & 31)
+        pb = ((planes[inv] >> sh) & np.uint64(1))
+        for i in range(n):
+            pert[:, i >> 6] |= pb[:, i] << np.uint64(i & 63)
+    return sel, pert

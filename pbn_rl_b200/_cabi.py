@@ -26,7 +26,7 @@ STAT_NAMES = ("steps", "episodes", "terminated", "truncated", "ep_len_sum", "fli
 EXPORTS = (
     "pbn_create", "pbn_destroy", "pbn_update_attractors", "pbn_step", "pbn_step_injected", "pbn_reset",
     "pbn_unpack", "pbn_pack", "pbn_attractor_id", "pbn_kernel_kind", "pbn_words_per_state",
-    "pbn_launch_count", "pbn_last_error", "pbn_version",
+    "pbn_launch_count", "pbn_last_error", "pbn_version", "pbn_jit_source", "pbn_jit_precompile",
 )
 
 
@@ -49,7 +49,7 @@ class NetDesc(C.Structure):
         ("bins", C.c_int32),
         ("horizon", C.c_int32),
         ("perturb_mode", C.c_int32),
-        ("perturb_p", C.c_float),
+        ("perturb_p", C.c_double),
         ("r_success", C.c_float),
         ("r_step", C.c_float),
         ("r_action", C.c_float),
@@ -122,6 +122,10 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_words_per_state.restype = C.c_int
     lib.pbn_launch_count.argtypes = [vp, C.POINTER(u64)]
     lib.pbn_launch_count.restype = C.c_int
+    lib.pbn_jit_source.argtypes = [C.POINTER(NetDesc), C.c_int, C.c_char_p, i64]
+    lib.pbn_jit_source.restype = i64
+    lib.pbn_jit_precompile.argtypes = [C.POINTER(NetDesc)]
+    lib.pbn_jit_precompile.restype = C.c_int
     lib.pbn_last_error.argtypes = []
     lib.pbn_last_error.restype = C.c_char_p
     lib.pbn_version.argtypes = []

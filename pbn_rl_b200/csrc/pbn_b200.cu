@@ -10,6 +10,7 @@
 
 #include "pbn_common.cuh"
 #include "step_scalar.cuh"
+#include "sliced_host.cuh"
 
 using namespace pbn;
 
@@ -74,9 +75,77 @@ struct pbn_handle {
   uint64_t* d_attr_val = nullptr;
   uint32_t* d_pair_cum = nullptr;
   unsigned int* d_ticket = nullptr;
+  uint32_t* d_surv_sliced = nullptr;
+  // sliced kernel: [0] = own-RNG specialisation, [1] = injected-randomness one (compiled on first use)
+  jit::GenNet gen;
+  cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
+  cudaKernel_t jit_kernel[2] = {nullptr, nullptr};
+  int sliced_threads = 128, sliced_min_blocks = 1;
   uint64_t launches = 0;
   bool scalar_smem_opted = false;
 };
+
+// Compile (or fetch from the cubin cache) and load one specialisation of the sliced kernel.
+static int load_sliced(pbn_handle* h, int injected) {
+  if (h->jit_kernel[injected]) return PBN_OK;
+  std::vector<char> cubin;
+  std::string err;
+  if (jit::compile(h->gen, injected != 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
+  PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
+  const int nw = (h->gen.n_genes + 31) / 32;
+  h->sliced_threads = 128;
+  h->sliced_min_blocks = nw == 1 ? 4 : (nw == 2 ? 2 : 1);
+  return PBN_OK;
+}
+
+static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W) {
+  SlicedSmemLayout L{};
+  uint32_t o = 0;
+  L.surv_off = o;
+  o += (uint32_t)(32 * n.n_genes + 1) * 4u;
+  o = (o + 15u) & ~15u;
+  L.rew_off = o;
+  o += 80u;
+  const uint32_t abytes = (uint32_t)(n.n_attr + 1) * 4u + (uint32_t)n.n_attr_states * W * 16u + 32u;
+  L.attractors_in_smem = (n.n_attr > 0 && abytes <= 32u * 1024u) ? 1u : 0u;
+  if (L.attractors_in_smem) {
+    L.acare_off = o;
+    o += (uint32_t)n.n_attr_states * W * 8u;
+    L.aval_off = o;
+    o += (uint32_t)n.n_attr_states * W * 8u;
+    L.aoffs_off = o;
+    o += (uint32_t)(n.n_attr + 1) * 4u;
+    o = (o + 15u) & ~15u;
+  }
+  L.total = o;
+  return L;
+}
+
+static bool aligned_to(const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream_t stream) {
+  const pbn_step_args& a = p.a;
+  if (!aligned_to(a.state, 16) || !aligned_to(a.final_state, 16) || !aligned_to(a.target_id, 16) ||
+      !aligned_to(a.reward, 16) || !aligned_to(a.t, 8) || !aligned_to(a.actions, 4) ||
+      !aligned_to(a.terminated, 4) || !aligned_to(a.truncated, 4))
+    return fail(PBN_ERR_INVALID, "sliced kernel needs 16-byte aligned state/target_id/reward, 8-byte t, 4-byte actions/flags");
+  int rc = load_sliced(h, injected ? 1 : 0);
+  if (rc != PBN_OK) return rc;
+  SlicedSmemLayout L = sliced_smem_layout(h->net, h->W);
+  if (L.total > 200u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "tables need %u B of shared memory", L.total);
+  cudaKernel_t k = h->jit_kernel[injected ? 1 : 0];
+  if (L.total > 48u * 1024u)
+    PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int wpb = h->sliced_threads / 32;
+  const int64_t tiles = (a.n_envs + 1023) / 1024;
+  int64_t grid = (tiles + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 4;
+  if (grid > cap) grid = cap;
+  void* args[] = {&p, &L};
+  PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, L.total, stream));
+  return PBN_OK;
+}
 
 extern "C" {
 
@@ -104,6 +173,9 @@ void pbn_destroy(pbn_handle* h) {
     cudaFree(h->d_attr_val);
     cudaFree(h->d_pair_cum);
     cudaFree(h->d_ticket);
+    cudaFree(h->d_surv_sliced);
+    for (int i = 0; i < 2; ++i)
+      if (h->jit_lib[i]) cudaLibraryUnload(h->jit_lib[i]);
   }
   delete h;
 }
@@ -158,8 +230,13 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
     }
   }
 
-  int kernel = d->kernel == PBN_KERNEL_AUTO ? PBN_KERNEL_SCALAR : d->kernel;
-  if (kernel != PBN_KERNEL_SCALAR) return fail(PBN_ERR_UNSUPPORTED, "kernel kind %d not available", d->kernel);
+  std::string why;
+  const bool can_slice = jit::eligible(d, &why);
+  int kernel = d->kernel;
+  if (kernel == PBN_KERNEL_AUTO) kernel = can_slice ? PBN_KERNEL_SLICED : PBN_KERNEL_SCALAR;
+  if (kernel != PBN_KERNEL_SCALAR && kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_INVALID, "kernel kind %d unknown", d->kernel);
+  if (kernel == PBN_KERNEL_SLICED && !can_slice)
+    return fail(PBN_ERR_UNSUPPORTED, "network not eligible for the sliced kernel: %s", why.c_str());
 
   int ndev = 0;
   PBN_CUDA(cudaGetDeviceCount(&ndev));
@@ -189,7 +266,16 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
       return rc;
     }
   }
+  if (kernel == PBN_KERNEL_SLICED) {
+    h->gen = jit::gen_net_from_desc(d);
+    const std::vector<uint32_t> ss = jit::sliced_survival(d->perturb_p, N);
+    if ((rc = upload(&h->d_surv_sliced, ss.data(), ss.size())) != PBN_OK || (rc = load_sliced(h, 0)) != PBN_OK) {
+      pbn_destroy(h);
+      return rc;
+    }
+  }
   NetParams& n = h->net;
+  n.surv_sliced = h->d_surv_sliced;
   n.func_offset = h->d_func_offset;
   n.funcs = h->d_funcs;
   n.func_cum = h->d_func_cum;
@@ -283,6 +369,11 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   p.a = *a;
   p.n = h->net;
   p.ticket = h->d_ticket;
+  if (h->kernel == PBN_KERNEL_SLICED) {
+    const int rc = launch_sliced(h, p, injected, stream);
+    if (rc == PBN_OK) h->launches += 1;
+    return rc;
+  }
   const ScalarSmemLayout L = scalar_smem_layout(h->net, h->W);
   if (L.total > 200u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "network tables need %u B of shared memory", L.total);
   const int block = 256;
@@ -303,6 +394,34 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
 #undef PBN_LAUNCH_SCALAR
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
+  return PBN_OK;
+}
+
+int64_t pbn_jit_source(const pbn_net_desc* d, int injected, char* buf, int64_t len) {
+  if (!d || d->n_genes < 1 || !d->func_offset) return fail(PBN_ERR_INVALID, "bad descriptor");
+  std::string why;
+  if (!jit::eligible(d, &why)) return fail(PBN_ERR_UNSUPPORTED, "not eligible for the sliced kernel: %s", why.c_str());
+  std::string gen_h, upd;
+  jit::generate(jit::gen_net_from_desc(d), injected != 0, &gen_h, &upd);
+  const std::string all = "// ---- net_gen.cuh\n" + gen_h + "// ---- net_update.inc\n" + upd;
+  if (buf && len > 0) {
+    const size_t n = all.size() < (size_t)(len - 1) ? all.size() : (size_t)(len - 1);
+    memcpy(buf, all.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)all.size();
+}
+
+int pbn_jit_precompile(const pbn_net_desc* d) {
+  if (!d || d->n_genes < 1 || !d->func_offset) return fail(PBN_ERR_INVALID, "bad descriptor");
+  std::string why;
+  if (!jit::eligible(d, &why)) return fail(PBN_ERR_UNSUPPORTED, "not eligible for the sliced kernel: %s", why.c_str());
+  const jit::GenNet g = jit::gen_net_from_desc(d);
+  for (int inj = 0; inj < 2; ++inj) {
+    std::vector<char> cubin;
+    std::string err;
+    if (jit::compile(g, inj != 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
+  }
   return PBN_OK;
 }
 

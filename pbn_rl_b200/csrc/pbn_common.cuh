@@ -1,7 +1,9 @@
 // Shared device-side definitions: kernel parameter block, table views, small helpers.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
 #include <cuda_runtime.h>
+#endif
 
 #include "../../include/pbn_b200.h"
 #include "philox.cuh"
@@ -22,6 +24,7 @@ struct NetParams {
   const FuncDesc* funcs;        // [F]
   const uint32_t* func_cum;     // [F]
   const uint32_t* survival;     // [N+1]
+  const uint32_t* surv_sliced;  // [32N+1] survival table over the slots of a lane-tile (sliced kernel)
   const int32_t* attr_offset;   // [A+1]
   const uint64_t* attr_care;    // [S*W]
   const uint64_t* attr_val;     // [S*W]
@@ -63,6 +66,12 @@ __device__ __forceinline__ void bump_device_step(const pbn_step_args& a, unsigne
     }
   }
 }
+
+// Dynamic shared-memory layout of the sliced kernel (computed by the host per launch).
+struct SlicedSmemLayout {
+  uint32_t surv_off, rew_off, aoffs_off, acare_off, aval_off, total;
+  uint32_t attractors_in_smem;
+};
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 

@@ -2,7 +2,9 @@
 // Each round is 2 IMAD.WIDE (fma pipe) + 2 three-input XORs (one LOP3 each, alu pipe);
 // the key schedule is warp-uniform and folds into immediates/uniform registers.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 namespace pbn {
 

@@ -1,0 +1,373 @@
+// Host side of the sliced kernel: eligibility, per-network code generation, NVRTC compile
+// (with an on-disk cubin cache) and module loading.  Included by pbn_b200.cu only.
+#pragma once
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pbn_common.cuh"
+
+namespace pbn {
+namespace jit {
+
+// sources embedded at build time (csrc/Makefile -> embedded_src.inc)
+#include "embedded_src.inc"
+
+struct GenFunc {
+  int arity;
+  int in[PBN_MAX_ARITY];
+  uint64_t lut;
+};
+
+struct GenNet {
+  int n_genes = 0, bins = 3, pert_mode = 0;
+  std::vector<std::vector<GenFunc>> funcs;  // per gene
+};
+
+// ---- eligibility ---------------------------------------------------------------------------
+// The sliced kernel draws uniform selections among K in {1,2,3,4} predictors per gene.
+inline bool eligible(const pbn_net_desc* d, std::string* why) {
+  if (d->n_genes > 96) {
+    if (why) *why = "more than 96 genes";
+    return false;
+  }
+  for (int i = 0; i < d->n_genes; ++i) {
+    const int f0 = d->func_offset[i], K = d->func_offset[i + 1] - f0;
+    if (K < 1 || K > 4) {
+      if (why) *why = "gene with more than 4 predictors";
+      return false;
+    }
+    for (int k = 0; k + 1 < K; ++k) {
+      const double want = std::floor((double)(k + 1) / K * 4294967296.0 + 0.5);
+      if (std::fabs((double)d->func_cum[f0 + k] - want) > 2.0) {
+        if (why) *why = "non-uniform predictor selection probabilities";
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+inline GenNet gen_net_from_desc(const pbn_net_desc* d) {
+  GenNet g;
+  g.n_genes = d->n_genes;
+  g.bins = d->bins;
+  g.pert_mode = d->perturb_mode;
+  g.funcs.resize(d->n_genes);
+  for (int i = 0; i < d->n_genes; ++i)
+    for (int f = d->func_offset[i]; f < d->func_offset[i + 1]; ++f) {
+      GenFunc gf{};
+      gf.arity = d->func_arity[f];
+      for (int j = 0; j < gf.arity; ++j) gf.in[j] = d->func_inputs[f * PBN_FUNC_INPUT_STRIDE + j];
+      gf.lut = gf.arity >= 6 ? d->func_lut[f] : (d->func_lut[f] & ((1ull << (1u << gf.arity)) - 1ull));
+      g.funcs[i].push_back(gf);
+    }
+  return g;
+}
+
+// ---- Boolean function -> LOP3 tree -----------------------------------------------------------
+struct Expr {
+  std::string s;
+  int cost;
+};
+
+inline std::string plane(int gene) {
+  char buf[48];
+  snprintf(buf, sizeof(buf), "x[%d][%d]", gene >> 5, gene & 31);
+  return buf;
+}
+
+// drop variables the table does not depend on; returns the reduced table, edits vars
+inline uint64_t reduce_support(uint64_t lut, std::vector<int>& vars) {
+  for (int j = (int)vars.size() - 1; j >= 0; --j) {
+    const int k = (int)vars.size();
+    bool depends = false;
+    for (unsigned a = 0; a < (1u << k); ++a)
+      if (!((a >> j) & 1u) && (((lut >> a) ^ (lut >> (a | (1u << j)))) & 1ull)) depends = true;
+    if (depends) continue;
+    uint64_t nl = 0;
+    unsigned na = 0;
+    for (unsigned a = 0; a < (1u << k); ++a) {
+      if ((a >> j) & 1u) continue;
+      nl |= ((lut >> a) & 1ull) << na;
+      ++na;
+    }
+    lut = nl;
+    vars.erase(vars.begin() + j);
+  }
+  return lut;
+}
+
+inline Expr synth(uint64_t lut, std::vector<int> vars) {
+  lut = reduce_support(lut, vars);
+  const int k = (int)vars.size();
+  if (k == 0) return {(lut & 1ull) ? "0xFFFFFFFFu" : "0u", 0};
+  if (k == 1) return (lut & 3ull) == 2ull ? Expr{plane(vars[0]), 0} : Expr{"(~" + plane(vars[0]) + ")", 1};
+  if (k <= 3) {
+    unsigned imm = 0;
+    for (unsigned t = 0; t < 8; ++t) {
+      const unsigned a = (t >> 2) & 1u, b = (t >> 1) & 1u, c = t & 1u;
+      const unsigned idx = a | (b << 1) | (k >= 3 ? (c << 2) : 0u);
+      imm |= (unsigned)((lut >> idx) & 1ull) << t;
+    }
+    char buf[160];
+    snprintf(buf, sizeof(buf), "lop3<0x%02X>(%s, %s, %s)", imm, plane(vars[0]).c_str(), plane(vars[1]).c_str(),
+             plane(vars[k >= 3 ? 2 : 0]).c_str());
+    return {buf, 1};
+  }
+  // Shannon expansion on the variable that gives the cheapest pair of cofactors
+  Expr best{"", 1 << 30};
+  for (int j = 0; j < k; ++j) {
+    uint64_t lo = 0, hi = 0;
+    unsigned na = 0;
+    for (unsigned a = 0; a < (1u << k); ++a) {
+      if ((a >> j) & 1u) continue;
+      lo |= ((lut >> a) & 1ull) << na;
+      hi |= ((lut >> (a | (1u << j))) & 1ull) << na;
+      ++na;
+    }
+    std::vector<int> rest(vars);
+    rest.erase(rest.begin() + j);
+    const uint64_t full = (k - 1 >= 6) ? ~0ull : ((1ull << (1u << (k - 1))) - 1ull);
+    Expr cand;
+    if ((lo ^ hi) == full) {
+      const Expr e0 = synth(lo, rest);
+      cand = {"(" + e0.s + " ^ " + plane(vars[j]) + ")", e0.cost + 1};
+    } else {
+      const Expr e0 = synth(lo, rest), e1 = synth(hi, rest);
+      cand = {"bmux(" + plane(vars[j]) + ", " + e1.s + ", " + e0.s + ")", e0.cost + e1.cost + 1};
+    }
+    if (cand.cost < best.cost) best = cand;
+  }
+  return best;
+}
+
+inline int sel_words(int K) { return K == 1 ? 0 : K == 2 ? 1 : K == 4 ? 2 : 6; }
+
+// net_gen.cuh: the constants; net_update.inc: pbn_update() -- see step_sliced.cuh
+inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::string* update_inc) {
+  const int N = g.n_genes, NW = (N + 31) / 32;
+  char buf[256];
+  std::string h;
+  h += "// generated by libpbn_b200 for one network: do not edit\n#pragma once\n";
+  snprintf(buf, sizeof(buf),
+           "#define PBN_N %d\n#define PBN_NW32 %d\n#define PBN_BINS %d\n"
+           "#define PBN_INJECTED %d\n#define PBN_THREADS %d\n#define PBN_MIN_BLOCKS %d\n",
+           N, NW, g.bins, injected ? 1 : 0, 128, NW == 1 ? 4 : (NW == 2 ? 2 : 1));
+  h += buf;
+  *gen_h = h;
+
+  std::string u;
+  u += "// generated by libpbn_b200 for one network: do not edit\nnamespace pbn {\n";
+  u += "template <class Sel>\n__device__ __forceinline__ void pbn_update(const uint32_t (&x)[kNW][32], "
+       "uint32_t (&o)[kNW][32], Sel& sel) {\n";
+  int word = 0, last_block = -1;
+  for (int i = 0; i < N; ++i) {
+    const int K = (int)g.funcs[i].size();
+    snprintf(buf, sizeof(buf), "  {  // gene %d: %d predictor(s)\n", i, K);
+    u += buf;
+    std::vector<std::string> names;
+    std::vector<std::pair<uint64_t, std::vector<int>>> seen;
+    for (int k = 0; k < K; ++k) {
+      const GenFunc& f = g.funcs[i][k];
+      std::vector<int> vars(f.in, f.in + f.arity);
+      const uint64_t red = reduce_support(f.lut, vars);
+      int same = -1;
+      for (size_t q = 0; q < seen.size(); ++q)
+        if (seen[q].first == red && seen[q].second == vars) same = (int)q;
+      seen.push_back({red, vars});
+      snprintf(buf, sizeof(buf), "f%d", k);
+      if (same >= 0) {
+        names.push_back(names[same]);
+        continue;
+      }
+      names.push_back(buf);
+      const Expr e = synth(f.lut, std::vector<int>(f.in, f.in + f.arity));
+      u += "    const uint32_t " + std::string(buf) + " = " + e.s + ";\n";
+    }
+    const std::string dst = "o[" + std::to_string(i >> 5) + "][" + std::to_string(i & 31) + "]";
+    if (K == 1) {
+      u += "    " + dst + " = " + names[0] + ";\n  }\n";
+      continue;
+    }
+    const int nw = sel_words(K);
+    std::string args;
+    for (int q = 0; q < nw; ++q) {
+      const int wq = word + q, blk = wq >> 2;
+      if (blk > last_block) {
+        snprintf(buf, sizeof(buf), "    PBN_SEL_BLOCK(B%d, %d);\n", blk, blk);
+        // declared at function scope so that the next gene can use the rest of the block
+        u.insert(u.rfind("  {  // gene"), buf + 2);
+        last_block = blk;
+      }
+      snprintf(buf, sizeof(buf), "B%d.%c, ", blk, "xyzw"[wq & 3]);
+      args += buf;
+    }
+    word += nw;
+    snprintf(buf, sizeof(buf), "    uint32_t s0, s1;\n    PBN_SEL%d(%d, %ss0, s1);\n", K, i, args.c_str());
+    u += buf;
+    if (K == 2) u += "    " + dst + " = bmux(s0, " + names[1] + ", " + names[0] + ");\n";
+    if (K == 3) u += "    " + dst + " = bmux(s1, " + names[2] + ", bmux(s0, " + names[1] + ", " + names[0] + "));\n";
+    if (K == 4)
+      u += "    " + dst + " = bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " +
+           names[0] + "));\n";
+    u += "  }\n";
+  }
+  for (int i = N; i < 32 * NW; ++i) {
+    snprintf(buf, sizeof(buf), "  o[%d][%d] = 0u;\n", i >> 5, i & 31);
+    u += buf;
+  }
+  u += "}\n}  // namespace pbn\n";
+  *update_inc = u;
+}
+
+inline std::string main_source() {
+  return "#include \"../../include/pbn_b200.h\"\n#include \"net_gen.cuh\"\n#include \"step_sliced.cuh\"\n";
+}
+
+// ---- NVRTC through dlopen (the library must load on machines without it) ------------------------
+struct Nvrtc {
+  void* so = nullptr;
+  int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(void*, size_t*) = nullptr;
+  int (*GetCUBIN)(void*, char*) = nullptr;
+  int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+  int (*GetProgramLog)(void*, char*) = nullptr;
+  int (*DestroyProgram)(void**) = nullptr;
+  int (*Version)(int*, int*) = nullptr;
+  bool ok() const { return so && CreateProgram && CompileProgram && GetCUBINSize && GetCUBIN && DestroyProgram; }
+};
+
+inline Nvrtc& nvrtc() {
+  static Nvrtc n;
+  if (n.so) return n;
+  const char* names[] = {"/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so", nullptr};
+  if (const char* env = getenv("PBN_B200_NVRTC")) n.so = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+  for (int i = 0; !n.so && names[i]; ++i) n.so = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+  if (!n.so) return n;
+#define PBN_NVRTC_SYM(field, name) n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.so, name))
+  PBN_NVRTC_SYM(CreateProgram, "nvrtcCreateProgram");
+  PBN_NVRTC_SYM(CompileProgram, "nvrtcCompileProgram");
+  PBN_NVRTC_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+  PBN_NVRTC_SYM(GetCUBIN, "nvrtcGetCUBIN");
+  PBN_NVRTC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+  PBN_NVRTC_SYM(GetProgramLog, "nvrtcGetProgramLog");
+  PBN_NVRTC_SYM(DestroyProgram, "nvrtcDestroyProgram");
+  PBN_NVRTC_SYM(Version, "nvrtcVersion");
+#undef PBN_NVRTC_SYM
+  return n;
+}
+
+inline uint64_t fnv1a(const std::string& s, uint64_t h = 0xcbf29ce484222325ull) {
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 0x100000001b3ull;
+  }
+  return h;
+}
+
+inline std::string cache_dir() {
+  if (const char* env = getenv("PBN_B200_CACHE")) return env;
+  Dl_info info;
+  std::string dir = ".";
+  if (dladdr(reinterpret_cast<void*>(&cache_dir), &info) && info.dli_fname) {
+    dir = info.dli_fname;
+    const size_t slash = dir.rfind('/');
+    dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+  }
+  return dir + "/_jit_cache";
+}
+
+inline bool read_file(const std::string& path, std::vector<char>* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out->resize(n > 0 ? n : 0);
+  const bool ok = n > 0 && fread(out->data(), 1, n, f) == (size_t)n;
+  fclose(f);
+  return ok;
+}
+
+inline void write_file_atomic(const std::string& path, const std::vector<char>& data) {
+  char tmp[64];
+  snprintf(tmp, sizeof(tmp), ".tmp.%d", (int)getpid());
+  const std::string t = path + tmp;
+  FILE* f = fopen(t.c_str(), "wb");
+  if (!f) return;  // cache is best effort
+  const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (ok) rename(t.c_str(), path.c_str());
+  else unlink(t.c_str());
+}
+
+// Compile (or fetch from the cache) the specialisation; returns 0 or PBN_ERR_JIT with *err set.
+inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std::string* err) {
+  std::string gen_h, upd;
+  generate(g, injected, &gen_h, &upd);
+  const std::string main_src = main_source();
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  std::string key = gen_h + upd + main_src + kSrc_step_sliced + kSrc_pbn_common + kSrc_philox + kSrc_pbn_b200_h;
+  for (const char* o : opts) key += o;
+  char name[64];
+  snprintf(name, sizeof(name), "/sliced_%016llx.cubin", (unsigned long long)fnv1a(key));
+  const std::string dir = cache_dir(), path = dir + name;
+  if (read_file(path, cubin)) return 0;
+
+  Nvrtc& n = nvrtc();
+  if (!n.ok()) {
+    *err = "libnvrtc.so.12 not found (set PBN_B200_NVRTC) and no cached cubin at " + path;
+    return PBN_ERR_JIT;
+  }
+  const char* hdr_src[] = {kSrc_pbn_b200_h, kSrc_philox, kSrc_pbn_common, kSrc_step_sliced, gen_h.c_str(), upd.c_str()};
+  const char* hdr_name[] = {"../../include/pbn_b200.h", "philox.cuh", "pbn_common.cuh", "step_sliced.cuh",
+                            "net_gen.cuh", "net_update.inc"};
+  void* prog = nullptr;
+  int rc = n.CreateProgram(&prog, main_src.c_str(), "pbn_sliced.cu", 6, hdr_src, hdr_name);
+  if (rc != 0) {
+    *err = "nvrtcCreateProgram failed";
+    return PBN_ERR_JIT;
+  }
+  rc = n.CompileProgram(prog, 4, opts);
+  if (rc != 0) {
+    size_t ls = 0;
+    std::string log;
+    if (n.GetProgramLogSize && n.GetProgramLogSize(prog, &ls) == 0 && ls > 1) {
+      log.resize(ls);
+      n.GetProgramLog(prog, &log[0]);
+    }
+    n.DestroyProgram(&prog);
+    *err = "nvrtcCompileProgram failed: " + log.substr(0, 1500);
+    return PBN_ERR_JIT;
+  }
+  size_t sz = 0;
+  n.GetCUBINSize(prog, &sz);
+  cubin->resize(sz);
+  n.GetCUBIN(prog, cubin->data());
+  n.DestroyProgram(&prog);
+  mkdir(dir.c_str(), 0755);
+  write_file_atomic(path, *cubin);
+  return 0;
+}
+
+inline std::vector<uint32_t> sliced_survival(double p, int n_genes) {
+  const int slots = 32 * n_genes;
+  std::vector<uint32_t> s(slots + 1);
+  for (int j = 0; j <= slots; ++j) {
+    const double v = std::pow(1.0 - p, (double)j) * 4294967296.0;
+    s[j] = v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
+  }
+  return s;
+}
+
+}  // namespace jit
+}  // namespace pbn

@@ -19,7 +19,7 @@ from ._cabi import NetDesc, StepArgs, check
 from .attractors import AttractorSet
 from .network import PBNNetwork
 
-__all__ = ["VecPBNEnv", "survival_table", "pair_thresholds"]
+__all__ = ["VecPBNEnv", "survival_table", "pair_thresholds", "make_desc", "precompile", "jit_source"]
 
 
 def survival_table(p: float, n_genes: int) -> np.ndarray:
@@ -41,6 +41,53 @@ def pair_thresholds(weights: np.ndarray) -> np.ndarray:
     last = int(np.nonzero(w)[0][-1])
     thr[last:] = 0xFFFFFFFF
     return thr
+
+
+def make_desc(network: PBNNetwork, bins: int = 3, horizon: int = 20, perturb_p: float = 0.0,
+              perturb_mode: str = "A", r_success: float = 5.0, r_step: float = 0.0, r_action: float = -1.0,
+              seed: int = 0x5EED, device: int = 0, kernel: str = "auto"):
+    """Fill a ``pbn_net_desc`` for ``network``; returns ``(desc, keepalive)`` -- the host arrays the
+    descriptor points into must outlive the C call."""
+    arr = network.descriptor_arrays()
+    d = NetDesc()
+    d.n_genes = network.n_genes
+    d.n_funcs = network.n_functions
+    d.func_offset = arr["func_offset"].ctypes.data
+    d.func_arity = arr["func_arity"].ctypes.data
+    d.func_inputs = arr["func_inputs"].ctypes.data
+    d.func_lut = arr["func_lut"].ctypes.data
+    d.func_cum = arr["func_cum"].ctypes.data
+    d.survival = None  # computed by the library from perturb_p
+    d.bins = int(bins)
+    d.horizon = int(horizon)
+    d.perturb_mode = _cabi.PERT_MODES[perturb_mode]
+    d.perturb_p = float(perturb_p)
+    d.r_success, d.r_step, d.r_action = float(r_success), float(r_step), float(r_action)
+    d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    d.device = int(device)
+    d.kernel = _cabi.KERNEL_KINDS[kernel]
+    return d, arr
+
+
+def precompile(network: PBNNetwork, bins: int = 3) -> None:
+    """Generate + NVRTC-compile the sliced-kernel specialisations of ``network`` into the on-disk
+    cubin cache (works without a GPU).  Raises PbnError if the network is not eligible."""
+    d, keep = make_desc(network, bins=bins)
+    check(_cabi.lib().pbn_jit_precompile(C.byref(d)))
+    del keep
+
+
+def jit_source(network: PBNNetwork, bins: int = 3, injected: bool = False) -> str:
+    """The CUDA source generated for ``network`` (predictor functions as LOP3 trees)."""
+    d, keep = make_desc(network, bins=bins)
+    lib = _cabi.lib()
+    n = lib.pbn_jit_source(C.byref(d), int(injected), None, 0)
+    if n < 0:
+        check(int(n))
+    buf = C.create_string_buffer(int(n) + 1)
+    lib.pbn_jit_source(C.byref(d), int(injected), buf, int(n) + 1)
+    del keep
+    return buf.value.decode()
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -89,26 +136,9 @@ class VecPBNEnv:
         self.perturb_p = float(perturb_p)
         self.perturb_mode = perturb_mode
 
-        arr = network.descriptor_arrays()
-        self._keep = arr  # host arrays must outlive pbn_create
-        surv = survival_table(self.perturb_p, self.n_genes)
-        d = NetDesc()
-        d.n_genes = self.n_genes
-        d.n_funcs = network.n_functions
-        d.func_offset = arr["func_offset"].ctypes.data
-        d.func_arity = arr["func_arity"].ctypes.data
-        d.func_inputs = arr["func_inputs"].ctypes.data
-        d.func_lut = arr["func_lut"].ctypes.data
-        d.func_cum = arr["func_cum"].ctypes.data
-        d.survival = surv.ctypes.data
-        d.bins = self.bins
-        d.horizon = self.horizon
-        d.perturb_mode = _cabi.PERT_MODES[perturb_mode]
-        d.perturb_p = self.perturb_p
-        d.r_success, d.r_step, d.r_action = float(r_success), float(r_step), float(r_action)
-        d.seed = self.seed
-        d.device = self.device.index
-        d.kernel = _cabi.KERNEL_KINDS[kernel]
+        d, self._keep = make_desc(network, bins=self.bins, horizon=self.horizon, perturb_p=self.perturb_p,
+                                  perturb_mode=perturb_mode, r_success=r_success, r_step=r_step,
+                                  r_action=r_action, seed=self.seed, device=self.device.index, kernel=kernel)
         h = C.c_void_p()
         check(self.lib.pbn_create(C.byref(d), C.byref(h)))
         self._h = h

@@ -14,6 +14,7 @@ from helpers import NETS, attractor_set, golden, k4_inputs, k4_selections, oracl
 pytestmark = pytest.mark.gpu
 
 KW = dict(horizon=20, r_success=5.0, r_step=-0.25, r_action=-1.0)
+KERNELS = ["scalar", "sliced"]
 MODES = {"none": 0, "A": 1, "B": 2, "C": 3}
 
 
@@ -53,8 +54,9 @@ def _compare(env, expect, tag):
     assert np.array_equal(env.truncated.cpu().numpy(), trunc), tag + ": truncated"
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", NETS)
-def test_k4_known_answer_on_gpu(name):
+def test_k4_known_answer_on_gpu(name, kernel):
     """Fixture K4: 4 x 4096 next states per network, sha256 over LE u64 words."""
     import torch
     net = product_net(name)
@@ -62,7 +64,8 @@ def test_k4_known_answer_on_gpu(name):
     x = k4_inputs(n)
     h = hashlib.sha256()
     from pbn_rl_b200 import VecPBNEnv
-    env = VecPBNEnv(net, 4096, None, device="cuda:0", perturb_mode="none", horizon=0)
+    env = VecPBNEnv(net, 4096, None, device="cuda:0", perturb_mode="none", horizon=0, kernel=kernel)
+    assert env.kernel == kernel
     for sel in k4_selections(n):
         env.set_state(torch.from_numpy(x.astype(np.int64)), packed=True)
         env.step_injected(None, torch.from_numpy(sel))
@@ -72,29 +75,43 @@ def test_k4_known_answer_on_gpu(name):
     assert env.launches >= 4
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", NETS)
 @pytest.mark.parametrize("mode", ["none", "A", "B", "C"])
-def test_injected_step_bit_exact(name, mode):
+def test_injected_step_bit_exact(name, mode, kernel):
     import torch
     e = 4096
     case = random_case(name, e, seed=zlib.crc32((name + mode).encode()) & 0xFFFF)
-    env = _env(name, e, mode=mode)
+    env = _env(name, e, mode=mode, kernel=kernel)
     _load(env, case)
     env.step_injected(torch.from_numpy(case["actions"]), torch.from_numpy(case["sel"]),
                       torch.from_numpy(case["pert"].astype(np.int64)))
-    _compare(env, _oracle_step(name, case, case["sel"], case["pert"], mode), f"{name}/{mode}")
+    _compare(env, _oracle_step(name, case, case["sel"], case["pert"], mode), f"{name}/{mode}/{kernel}")
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("e", [1, 31, 33, 1025, 3000])
-def test_ragged_sizes(e):
+def test_ragged_sizes(e, kernel):
     import torch
     name = "pbn28"
     case = random_case(name, e, seed=e)
-    env = _env(name, e, mode="A")
+    env = _env(name, e, mode="A", kernel=kernel)
     _load(env, case)
     env.step_injected(torch.from_numpy(case["actions"]), torch.from_numpy(case["sel"]),
                       torch.from_numpy(case["pert"].astype(np.int64)))
     _compare(env, _oracle_step(name, case, case["sel"], case["pert"], "A"), f"E={e}")
+    # own-RNG mode on the same ragged batch
+    from oracle import pbn_oracle as O
+    env2 = _env(name, e, mode="A", p=0.02, kernel=kernel)
+    _load(env2, case)
+    env2.step(torch.from_numpy(case["actions"]).cuda())
+    ids = np.arange(e, dtype=np.uint64)
+    onet = oracle_net(name)
+    if kernel == "scalar":
+        sel, pert = O.scalar_stream_selection(onet, ids, 0, 0x5EED), O.scalar_stream_perturbation(onet.n, 0.02, ids, 0, 0x5EED)
+    else:
+        sel, pert = O.sliced_stream(onet, 0.02, ids, 0, 0x5EED)
+    _compare(env2, _oracle_step(name, case, sel, pert, "A"), f"E={e}/philox")
 
 
 def test_empty_batch_is_a_noop():
@@ -103,17 +120,18 @@ def test_empty_batch_is_a_noop():
     assert env.launches == 0
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", NETS)
 @pytest.mark.parametrize("mode", ["A", "B", "C"])
-def test_philox_step_bit_exact(name, mode):
+def test_philox_step_bit_exact(name, mode, kernel):
     """Own-RNG mode: the oracle re-derives predictor choices and perturbation masks from the
     documented Philox streams and must land on the very same states."""
     import torch
     from oracle import pbn_oracle as O
     e, p = 4096, 0.02
     case = random_case(name, e, seed=7)
-    env = _env(name, e, mode=mode, p=p)
-    assert env.kernel in ("scalar", "sliced")
+    env = _env(name, e, mode=mode, p=p, kernel=kernel)
+    assert env.kernel == kernel
     onet = oracle_net(name)
     ids = np.arange(e, dtype=np.uint64)
     state = case["state"]
@@ -133,19 +151,20 @@ def test_philox_step_bit_exact(name, mode):
     assert pert.any(), "perturbation stream never fired: test is vacuous"
 
 
-def test_sharding_invariance():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_sharding_invariance(kernel):
     """Two shards with env_offset 0 / 2048 reproduce the single 4096-env batch (global env ids
     drive the Philox counters)."""
     import torch
     name, e = "pbn28", 4096
     case = random_case(name, e, seed=11)
-    full = _env(name, e, mode="A", p=0.01)
+    full = _env(name, e, mode="A", p=0.01, kernel=kernel)
     _load(full, case)
     full.step(torch.from_numpy(case["actions"]).cuda())
     ref = full.state.cpu().numpy()
     for lo in (0, 2048):
         sub = {k: v[lo:lo + 2048] for k, v in case.items()}
-        shard = _env(name, 2048, mode="A", p=0.01, env_offset=lo)
+        shard = _env(name, 2048, mode="A", p=0.01, env_offset=lo, kernel=kernel)
         _load(shard, sub)
         shard.step(torch.from_numpy(sub["actions"]).cuda())
         assert np.array_equal(shard.state.cpu().numpy(), ref[lo:lo + 2048])
@@ -171,13 +190,14 @@ def test_reset_matches_oracle(name):
     assert (env.t.cpu().numpy() == 0).all()
 
 
-def test_autoreset_equals_step_then_reset():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_autoreset_equals_step_then_reset(kernel):
     import torch
     name, e = "pbn10", 4096
     case = random_case(name, e, seed=3)
     case["t"][:] = 18
-    a = _env(name, e, mode="A", p=0.01, auto_reset=True)
-    b = _env(name, e, mode="A", p=0.01, auto_reset=False)
+    a = _env(name, e, mode="A", p=0.01, auto_reset=True, kernel=kernel)
+    b = _env(name, e, mode="A", p=0.01, auto_reset=False, kernel=kernel)
     for env in (a, b):
         _load(env, case)
     final = torch.zeros_like(a.state)
@@ -222,12 +242,13 @@ def test_attractor_membership_with_wildcards():
     assert (ids >= 0).sum() == 7  # 3 singletons + 4 wildcard states (fixture K2)
 
 
-def test_large_batch_properties():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_large_batch_properties(kernel):
     """BASELINE size (2^20 envs, Bittner-28): size-independent properties instead of a full oracle pass."""
     import torch
     name, e = "pbn28", 1 << 20
     net = product_net(name)
-    env = _env(name, e, mode="A", p=0.001, auto_reset=False)
+    env = _env(name, e, mode="A", p=0.001, auto_reset=False, kernel=kernel)
     g = torch.Generator(device="cuda").manual_seed(0)
     s0 = torch.randint(0, 1 << 28, (e, 1), generator=g, device="cuda", dtype=torch.int64)
     env.set_state(s0, packed=True)
@@ -255,7 +276,7 @@ def test_large_batch_properties():
         sel = O.scalar_stream_selection(onet, ids, 0, 0x5EED)
         pert = O.scalar_stream_perturbation(28, 0.001, ids, 0, 0x5EED)
     else:
-        sel, pert = O.sliced_stream(onet, 0.001, ids, 0, 0x5EED, lo)
+        sel, pert = O.sliced_stream(onet, 0.001, ids, 0, 0x5EED)
     case = dict(state=s0[lo:lo + 4096].cpu().numpy().astype(np.uint64), actions=acts[lo:lo + 4096].cpu().numpy(),
                 target=env.target_id[lo:lo + 4096].cpu().numpy(), t=np.zeros(4096, np.uint16))
     nxt = _oracle_step(name, case, sel, pert, "A")[0]
