@@ -524,7 +524,8 @@ def sliced_coords(env_ids: np.ndarray):
 
 
 def sliced_survival(p: float, n: int) -> np.ndarray:
-    slots = 32 * n
+    """Survival table of one (column, warp) perturbation sub-stream: 8 rows x n genes."""
+    slots = 8 * n
     out = np.zeros(slots + 1, dtype=np.uint64)
     for j in range(slots + 1):
         out[j] = min(int(((1.0 - p) ** j) * 4294967296.0), 0xFFFFFFFF)
@@ -532,17 +533,17 @@ def sliced_survival(p: float, n: int) -> np.ndarray:
 
 
 class _WordStream:
-    """Sequential 32-bit words of one (group, step, kind) stream, block by block."""
+    """Sequential 32-bit words of one (group, step, kind, sub-stream q) stream: blocks 64q + i."""
 
-    def __init__(self, gid, step_ctr, kind, k0, k1):
-        self.gid, self.step, self.kind, self.k0, self.k1 = gid, step_ctr, kind, k0, k1
+    def __init__(self, gid, step_ctr, kind, k0, k1, q=0):
+        self.gid, self.step, self.kind, self.k0, self.k1, self.q = gid, step_ctr, kind, k0, k1, q
         self.next = 0
         self.blk = None
 
     def word(self):
         if (self.next & 3) == 0:
-            r = philox4x32(*_ctr(np.array([self.gid], dtype=np.uint64), self.step, self.kind, self.next >> 2),
-                           self.k0, self.k1)
+            r = philox4x32(*_ctr(np.array([self.gid], dtype=np.uint64), self.step, self.kind,
+                                 64 * self.q + ((self.next >> 2) & 63)), self.k0, self.k1)
             self.blk = [int(x[0]) for x in r]
         w = self.blk[self.next & 3]
         self.next += 1
@@ -559,7 +560,7 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
     groups, inv = np.unique(gid, return_inverse=True)
     ng = len(groups)
     ks = [len(ps) for ps in net.probs]
-    nw = {1: 0, 2: 1, 4: 2, 3: 6}
+    nw = {1: 0, 2: 8, 4: 8, 3: 8}  # every gene with K > 1 owns a slot of two Philox blocks
     total_words = sum(nw[k] for k in ks)
     n_blocks = (total_words + 3) // 4
     words = np.zeros((ng, max(4 * n_blocks, 4)), dtype=np.uint64)
@@ -581,31 +582,38 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
         elif k == 3:
             b0, b1 = w[0].copy(), w[1].copy()
             r_ = b0 & b1
-            for c0, c1 in ((w[2], w[3]), (w[4], w[5])):
+            for c0, c1 in ((w[2], w[3]), (w[4], w[5]), (w[6], w[7])):
                 b0 = np.where(True, (b0 & ~r_) | (c0 & r_), b0)
                 b1 = (b1 & ~r_) | (c1 & r_)
                 r_ = r_ & c0 & c1
             s0[:, i], s1[:, i], rej[:, i] = b0, b1, r_
-    for g in range(ng):  # FIX stream: sequential per group
+    slot_of = {}
+    for i, k in enumerate(ks):
+        if k > 1:
+            slot_of[i] = len(slot_of)
+    for g in range(ng):  # FIX sub-streams: one per (group, q = slot mod 4), shared by the slots q, q+4, ...
         if not rej[g].any():
             continue
-        ws = _WordStream(int(groups[g]), step_ctr, KIND_FIX, k0, k1)
-        cur, left = 0, 0
-        for i in range(n):
-            r_ = int(rej[g, i])
-            while r_:
-                if left == 0:
-                    cur, left = ws.word(), 16
-                pr = cur & 3
-                cur >>= 2
-                left -= 1
-                if pr != 3:
-                    m = r_ & -r_
-                    r_ ^= m
-                    if not pr & 1:
-                        s0[g, i] = int(s0[g, i]) ^ m
-                    if not pr & 2:
-                        s1[g, i] = int(s1[g, i]) ^ m
+        for q in range(4):
+            ws = _WordStream(int(groups[g]), step_ctr, KIND_FIX, k0, k1, q)
+            cur, left = 0, 0
+            for i in range(n):
+                if i not in slot_of or slot_of[i] % 4 != q:
+                    continue
+                r_ = int(rej[g, i])
+                while r_:
+                    if left == 0:
+                        cur, left = ws.word(), 16
+                    pr = cur & 3
+                    cur >>= 2
+                    left -= 1
+                    if pr != 3:
+                        m = r_ & -r_
+                        r_ ^= m
+                        if not pr & 1:
+                            s0[g, i] = int(s0[g, i]) ^ m
+                        if not pr & 2:
+                            s1[g, i] = int(s1[g, i]) ^ m
     sh = bit.astype(np.uint64)[:, None]
     sel = (((s0[inv] >> sh) & np.uint64(1)) + 2 * ((s1[inv] >> sh) & np.uint64(1))).astype(np.uint8)
     for i, k in enumerate(ks):
@@ -616,18 +624,19 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
     pert = np.zeros((e, wds), dtype=np.uint64)
     if p > 0:
         surv = sliced_survival(p, n)
-        slots = 32 * n
+        slots = 8 * n
         planes = np.zeros((ng, n), dtype=np.uint64)
         for g in range(ng):
-            ws = _WordStream(int(groups[g]), step_ctr, KIND_PERTURB, k0, k1)
-            pos = -1
-            while True:
-                u = ws.word()
-                skip = int(np.searchsorted(-surv[1:].astype(np.int64), -u, side="left"))  # #{j>=1: u < S[j]}
-                pos += skip + 1
-                if pos >= slots:
-                    break
-                planes[g, pos >> 5] |= np.uint64(1) << np.uint64(pos & 31)
+            for q in range(4):  # sub-stream q covers slice bits 8q..8q+7
+                ws = _WordStream(int(groups[g]), step_ctr, KIND_PERTURB, k0, k1, q)
+                pos = -1
+                while True:
+                    u = ws.word()
+                    skip = int(np.searchsorted(-surv[1:].astype(np.int64), -u, side="left"))  # #{j>=1: u < S[j]}
+                    pos += skip + 1
+                    if pos >= slots:
+                        break
+                    planes[g, pos >> 3] |= np.uint64(1) << np.uint64(8 * q + (pos & 7))
         pb = ((planes[inv] >> sh) & np.uint64(1))
         for i in range(n):
             pert[:, i >> 6] |= pb[:, i] << np.uint64(i & 63)

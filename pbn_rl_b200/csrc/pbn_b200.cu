@@ -81,6 +81,7 @@ struct pbn_handle {
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
   cudaKernel_t jit_kernel[2] = {nullptr, nullptr};
   int sliced_threads = 128, sliced_min_blocks = 1;
+  uint32_t jit_smem_opt_in[2] = {48u * 1024u, 48u * 1024u};
   uint64_t launches = 0;
   bool scalar_smem_opted = false;
 };
@@ -93,17 +94,16 @@ static int load_sliced(pbn_handle* h, int injected) {
   if (jit::compile(h->gen, injected != 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
   PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
-  const int nw = (h->gen.n_genes + 31) / 32;
-  h->sliced_threads = 128;
-  h->sliced_min_blocks = nw == 1 ? 4 : (nw == 2 ? 2 : 1);
+  h->sliced_threads = jit::sliced_threads(h->gen);
+  h->sliced_min_blocks = jit::sliced_min_blocks(h->gen);
   return PBN_OK;
 }
 
-static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W) {
+static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W, int warps, int scratch_words) {
   SlicedSmemLayout L{};
   uint32_t o = 0;
   L.surv_off = o;
-  o += (uint32_t)(32 * n.n_genes + 1) * 4u;
+  o += (uint32_t)(8 * n.n_genes + 1) * 4u;
   o = (o + 15u) & ~15u;
   L.rew_off = o;
   o += 80u;
@@ -118,6 +118,9 @@ static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W) {
     o += (uint32_t)(n.n_attr + 1) * 4u;
     o = (o + 15u) & ~15u;
   }
+  L.scratch_off = o;
+  (void)warps;
+  o += (uint32_t)scratch_words * 4u;  // one scratch per CTA (= per tile)
   L.total = o;
   return L;
 }
@@ -132,15 +135,16 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
     return fail(PBN_ERR_INVALID, "sliced kernel needs 16-byte aligned state/target_id/reward, 8-byte t, 4-byte actions/flags");
   int rc = load_sliced(h, injected ? 1 : 0);
   if (rc != PBN_OK) return rc;
-  SlicedSmemLayout L = sliced_smem_layout(h->net, h->W);
-  if (L.total > 200u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "tables need %u B of shared memory", L.total);
+  SlicedSmemLayout L = sliced_smem_layout(h->net, h->W, h->sliced_threads / 32, jit::scratch_words(h->gen));
+  if (L.total > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "sliced kernel needs %u B of shared memory", L.total);
   cudaKernel_t k = h->jit_kernel[injected ? 1 : 0];
-  if (L.total > 48u * 1024u)
+  if (L.total > h->jit_smem_opt_in[injected ? 1 : 0]) {
     PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  const int wpb = h->sliced_threads / 32;
-  const int64_t tiles = (a.n_envs + 1023) / 1024;
-  int64_t grid = (tiles + wpb - 1) / wpb;
-  const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 4;
+    h->jit_smem_opt_in[injected ? 1 : 0] = L.total;
+  }
+  // one CTA per 1024-env tile; beyond a few waves the CTAs loop over tiles
+  int64_t grid = (a.n_envs + 1023) / 1024;
+  const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 8;
   if (grid > cap) grid = cap;
   void* args[] = {&p, &L};
   PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, L.total, stream));
@@ -291,6 +295,10 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
   n.r_action = d->r_action;
   n.k0 = (uint32_t)d->seed;
   n.k1 = (uint32_t)(d->seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    n.rk[2 * r] = n.k0 + (uint32_t)r * 0x9E3779B9u;
+    n.rk[2 * r + 1] = n.k1 + (uint32_t)r * 0xBB67AE85u;
+  }
   n.sel_block_mask = sel_block_mask;
   n.max_arity = max_arity;
   n.pair_last = 0;
@@ -339,6 +347,14 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
   n.n_attr = A;
   n.n_attr_states = S;
   n.pair_last = pair_last;
+  bool simple = A > 0 && S == A;
+  for (int e = 0; simple && e < S; ++e)
+    for (int w = 0; w < h->W; ++w) {
+      const int nbits = n.n_genes - 64 * w;
+      const uint64_t full = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1ull);
+      if (care[(size_t)e * h->W + w] != full) simple = false;
+    }
+  n.attr_simple = simple ? 1u : 0u;
   return PBN_OK;
 }
 

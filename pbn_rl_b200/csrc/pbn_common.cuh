@@ -24,7 +24,7 @@ struct NetParams {
   const FuncDesc* funcs;        // [F]
   const uint32_t* func_cum;     // [F]
   const uint32_t* survival;     // [N+1]
-  const uint32_t* surv_sliced;  // [32N+1] survival table over the slots of a lane-tile (sliced kernel)
+  const uint32_t* surv_sliced;  // [8N+1] survival table over the slots of one (column, warp) sub-stream
   const int32_t* attr_offset;   // [A+1]
   const uint64_t* attr_care;    // [S*W]
   const uint64_t* attr_val;     // [S*W]
@@ -36,6 +36,8 @@ struct NetParams {
   uint32_t sel_block_mask;      // bit b set: SELECT block b (genes 4b..4b+3) has a gene with >1 predictor
   uint32_t max_arity;
   uint32_t pert_rng;             // 1: draw perturbations from the stream (perturb_p > 0)
+  uint32_t attr_simple;          // 1: every attractor is a single fully specified state (no wildcards)
+  uint32_t rk[20];               // Philox round keys (k0 + r*W0, k1 + r*W1), r = 0..9: constant-bank operands
 };
 
 struct StepParams {
@@ -55,21 +57,21 @@ __device__ __forceinline__ uint64_t effective_step(const pbn_step_args& a) {
 // device-resident step counter (every CTA read it before any CTA could get here last).
 __device__ __forceinline__ void bump_device_step(const pbn_step_args& a, unsigned int* ticket) {
   if (a.step_ctr_dev == nullptr) return;
+  // No fence is needed: the counter is only consumed by later launches (ordered by the stream),
+  // and every thread of this CTA has used its copy of the counter before the barrier below.
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     const unsigned int t = atomicAdd(ticket, 1u);
     if (t == gridDim.x - 1) {
       *ticket = 0;
       *a.step_ctr_dev += 1;
-      __threadfence();
     }
   }
 }
 
 // Dynamic shared-memory layout of the sliced kernel (computed by the host per launch).
 struct SlicedSmemLayout {
-  uint32_t surv_off, rew_off, aoffs_off, acare_off, aval_off, total;
+  uint32_t surv_off, rew_off, aoffs_off, acare_off, aval_off, scratch_off, total;
   uint32_t attractors_in_smem;
 };
 
@@ -93,6 +95,25 @@ __device__ __forceinline__ int count_le(const uint32_t* tab, int n, uint32_t u) 
     if (tab[mid] <= u) lo = mid + 1; else hi = mid;
   }
   return lo;
+}
+
+// (source, target) pair of env.reset() from word 0 of the env's RESET block.
+__device__ __forceinline__ void reset_pair(const NetParams& n, const Philox4& r, int& src, int& tgt) {
+  const int A = n.n_attr;
+  if (n.pair_cum != nullptr) {
+    int pair = count_le(n.pair_cum, A * A - 1, r.x);
+    pair = min(pair, n.pair_last);
+    src = pair / A;
+    tgt = pair - src * A;
+  } else if (A > 1) {
+    const uint32_t q = __umulhi(r.x, (uint32_t)(A * (A - 1)));
+    src = (int)(q / (uint32_t)(A - 1));
+    const int tt = (int)(q - (uint32_t)src * (uint32_t)(A - 1));
+    tgt = tt + (tt >= src ? 1 : 0);
+  } else {
+    src = 0;
+    tgt = 0;
+  }
 }
 
 // (source, target) draw + source state for env.reset(); r = Philox block (RESET, 0) of the env.

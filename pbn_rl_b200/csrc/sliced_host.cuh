@@ -5,6 +5,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -78,11 +79,7 @@ struct Expr {
   int cost;
 };
 
-inline std::string plane(int gene) {
-  char buf[48];
-  snprintf(buf, sizeof(buf), "x[%d][%d]", gene >> 5, gene & 31);
-  return buf;
-}
+inline std::string plane(int gene) { return "x" + std::to_string(gene); }
 
 // drop variables the table does not depend on; returns the reduced table, edits vars
 inline uint64_t reduce_support(uint64_t lut, std::vector<int>& vars) {
@@ -149,82 +146,134 @@ inline Expr synth(uint64_t lut, std::vector<int> vars) {
   return best;
 }
 
-inline int sel_words(int K) { return K == 1 ? 0 : K == 2 ? 1 : K == 4 ? 2 : 6; }
+inline int n_sel_slots(const GenNet& g) {
+  int n = 0;
+  for (const auto& fs : g.funcs) n += fs.size() > 1 ? 1 : 0;
+  return n;
+}
 
-// net_gen.cuh: the constants; net_update.inc: pbn_update() -- see step_sliced.cuh
+inline int scratch_words(const GenNet& g) {
+  const int NW = (g.n_genes + 31) / 32;
+  return 2 * NW * 32 * 32 + 2 * n_sel_slots(g) * 32 + 8;
+}
+
+inline int sliced_threads(const GenNet&) { return 128; }  // four warps per 1024-env tile
+inline int sliced_min_blocks(const GenNet& g) { return g.n_genes <= 32 ? 7 : (g.n_genes <= 64 ? 4 : 2); }
+
+// net_gen.cuh: the constants; net_update.inc: selection tables + pbn_update_part() -- see step_sliced.cuh
 inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::string* update_inc) {
-  const int N = g.n_genes, NW = (N + 31) / 32;
-  char buf[256];
+  const int N = g.n_genes, NW = (N + 31) / 32, NSEL = n_sel_slots(g);
+  char buf[320];
   std::string h;
   h += "// generated by libpbn_b200 for one network: do not edit\n#pragma once\n";
   snprintf(buf, sizeof(buf),
-           "#define PBN_N %d\n#define PBN_NW32 %d\n#define PBN_BINS %d\n"
-           "#define PBN_INJECTED %d\n#define PBN_THREADS %d\n#define PBN_MIN_BLOCKS %d\n",
-           N, NW, g.bins, injected ? 1 : 0, 128, NW == 1 ? 4 : (NW == 2 ? 2 : 1));
+           "#define PBN_N %d\n#define PBN_NW32 %d\n#define PBN_BINS %d\n#define PBN_NSEL %d\n"
+           "#define PBN_SCRATCH_WORDS %d\n#define PBN_INJECTED %d\n#define PBN_THREADS %d\n#define PBN_MIN_BLOCKS %d\n",
+           N, NW, g.bins, NSEL, scratch_words(g), injected ? 1 : 0, sliced_threads(g), sliced_min_blocks(g));
   h += buf;
   *gen_h = h;
 
+  // gene -> warp: a gene with a selection slot r is evaluated by the warp that draws slot r (r mod 4);
+  // single-predictor genes go to the warp with the fewest functions so far
+  std::vector<int> owner(N, 0), slot_of(N, -1);
+  int load[4] = {0, 0, 0, 0};
+  std::string tg, tk;
+  int slot = 0;
+  for (int i = 0; i < N; ++i)
+    if (g.funcs[i].size() > 1) {
+      tg += std::to_string(i) + ", ";
+      tk += std::to_string((int)g.funcs[i].size()) + ", ";
+      slot_of[i] = slot;
+      owner[i] = slot & 3;
+      load[slot & 3] += (int)g.funcs[i].size();
+      ++slot;
+    }
+  for (int i = 0; i < N; ++i)
+    if (g.funcs[i].size() == 1) {
+      int best = 0;
+      for (int q = 1; q < 4; ++q)
+        if (load[q] < load[best]) best = q;
+      owner[i] = best;
+      load[best] += 1;
+    }
+  if (NSEL == 0) {
+    tg = "0";
+    tk = "1";
+  }
   std::string u;
   u += "// generated by libpbn_b200 for one network: do not edit\nnamespace pbn {\n";
-  u += "template <class Sel>\n__device__ __forceinline__ void pbn_update(const uint32_t (&x)[kNW][32], "
-       "uint32_t (&o)[kNW][32], Sel& sel) {\n";
-  int word = 0, last_block = -1;
-  for (int i = 0; i < N; ++i) {
-    const int K = (int)g.funcs[i].size();
-    snprintf(buf, sizeof(buf), "  {  // gene %d: %d predictor(s)\n", i, K);
+  u += "// slot r of the SELECT stream belongs to gene kSelGene[r], which has kSelK[r] predictors\n";
+  u += "__device__ __constant__ unsigned char kSelGene[] = {" + tg + "};\n";
+  u += "__device__ __constant__ unsigned char kSelK[] = {" + tk + "};\n\n";
+  u += "// x: input planes, o: out planes, sel0/sel1: selection planes; all [row][lane], lane folded in\n";
+  u += "__device__ __forceinline__ void pbn_update_part(uint32_t w, const uint32_t* x, uint32_t* o,\n"
+       "                                                const uint32_t* sel0, const uint32_t* sel1) {\n";
+  u += "#define X(g) x[(g) * 32]\n";
+  for (int q = 0; q < 4; ++q) {
+    snprintf(buf, sizeof(buf), "  %sif (w == %du) {\n", q ? "else " : "", q);
     u += buf;
-    std::vector<std::string> names;
-    std::vector<std::pair<uint64_t, std::vector<int>>> seen;
-    for (int k = 0; k < K; ++k) {
-      const GenFunc& f = g.funcs[i][k];
-      std::vector<int> vars(f.in, f.in + f.arity);
-      const uint64_t red = reduce_support(f.lut, vars);
-      int same = -1;
-      for (size_t q = 0; q < seen.size(); ++q)
-        if (seen[q].first == red && seen[q].second == vars) same = (int)q;
-      seen.push_back({red, vars});
-      snprintf(buf, sizeof(buf), "f%d", k);
-      if (same >= 0) {
-        names.push_back(names[same]);
+    // load each distinct input plane of this part once
+    std::vector<int> used;
+    for (int i = 0; i < N; ++i) {
+      if (owner[i] != q) continue;
+      for (const GenFunc& f : g.funcs[i]) {
+        std::vector<int> vars(f.in, f.in + f.arity);
+        reduce_support(f.lut, vars);
+        for (int v : vars)
+          if (std::find(used.begin(), used.end(), v) == used.end()) used.push_back(v);
+      }
+    }
+    std::sort(used.begin(), used.end());
+    for (int v : used) {
+      snprintf(buf, sizeof(buf), "    const uint32_t x%d = X(%d);\n", v, v);
+      u += buf;
+    }
+    for (int i = 0; i < N; ++i) {
+      if (owner[i] != q) continue;
+      const int K = (int)g.funcs[i].size();
+      snprintf(buf, sizeof(buf), "    {  // gene %d: %d predictor(s)\n", i, K);
+      u += buf;
+      std::vector<std::string> names;
+      std::vector<std::pair<uint64_t, std::vector<int>>> seen;
+      for (int k = 0; k < K; ++k) {
+        const GenFunc& f = g.funcs[i][k];
+        std::vector<int> vars(f.in, f.in + f.arity);
+        const uint64_t red = reduce_support(f.lut, vars);
+        int same = -1;
+        for (size_t z = 0; z < seen.size(); ++z)
+          if (seen[z].first == red && seen[z].second == vars) same = (int)z;
+        seen.push_back({red, vars});
+        snprintf(buf, sizeof(buf), "f%d", k);
+        if (same >= 0) {
+          names.push_back(names[same]);
+          continue;
+        }
+        names.push_back(buf);
+        const Expr e = synth(f.lut, std::vector<int>(f.in, f.in + f.arity));
+        u += "      const uint32_t " + std::string(buf) + " = " + e.s + ";\n";
+      }
+      const std::string dst = "o[" + std::to_string(i * 32) + "]";
+      if (K == 1) {
+        u += "      " + dst + " = " + names[0] + ";\n    }\n";
         continue;
       }
-      names.push_back(buf);
-      const Expr e = synth(f.lut, std::vector<int>(f.in, f.in + f.arity));
-      u += "    const uint32_t " + std::string(buf) + " = " + e.s + ";\n";
+      snprintf(buf, sizeof(buf), "      const uint32_t s0 = sel0[%d], s1 = sel1[%d];\n", slot_of[i] * 32, slot_of[i] * 32);
+      u += buf;
+      if (K == 2) u += "      (void)s1;\n      " + dst + " = bmux(s0, " + names[1] + ", " + names[0] + ");\n";
+      if (K == 3) u += "      " + dst + " = bmux(s1, " + names[2] + ", bmux(s0, " + names[1] + ", " + names[0] + "));\n";
+      if (K == 4)
+        u += "      " + dst + " = bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " +
+             names[0] + "));\n";
+      u += "    }\n";
     }
-    const std::string dst = "o[" + std::to_string(i >> 5) + "][" + std::to_string(i & 31) + "]";
-    if (K == 1) {
-      u += "    " + dst + " = " + names[0] + ";\n  }\n";
-      continue;
-    }
-    const int nw = sel_words(K);
-    std::string args;
-    for (int q = 0; q < nw; ++q) {
-      const int wq = word + q, blk = wq >> 2;
-      if (blk > last_block) {
-        snprintf(buf, sizeof(buf), "    PBN_SEL_BLOCK(B%d, %d);\n", blk, blk);
-        // declared at function scope so that the next gene can use the rest of the block
-        u.insert(u.rfind("  {  // gene"), buf + 2);
-        last_block = blk;
+    if (q == 0)
+      for (int i = N; i < 32 * NW; ++i) {
+        snprintf(buf, sizeof(buf), "    o[%d] = 0u;\n", i * 32);
+        u += buf;
       }
-      snprintf(buf, sizeof(buf), "B%d.%c, ", blk, "xyzw"[wq & 3]);
-      args += buf;
-    }
-    word += nw;
-    snprintf(buf, sizeof(buf), "    uint32_t s0, s1;\n    PBN_SEL%d(%d, %ss0, s1);\n", K, i, args.c_str());
-    u += buf;
-    if (K == 2) u += "    " + dst + " = bmux(s0, " + names[1] + ", " + names[0] + ");\n";
-    if (K == 3) u += "    " + dst + " = bmux(s1, " + names[2] + ", bmux(s0, " + names[1] + ", " + names[0] + "));\n";
-    if (K == 4)
-      u += "    " + dst + " = bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " +
-           names[0] + "));\n";
     u += "  }\n";
   }
-  for (int i = N; i < 32 * NW; ++i) {
-    snprintf(buf, sizeof(buf), "  o[%d][%d] = 0u;\n", i >> 5, i & 31);
-    u += buf;
-  }
-  u += "}\n}  // namespace pbn\n";
+  u += "#undef X\n}\n}  // namespace pbn\n";
   *update_inc = u;
 }
 
@@ -360,7 +409,7 @@ inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std
 }
 
 inline std::vector<uint32_t> sliced_survival(double p, int n_genes) {
-  const int slots = 32 * n_genes;
+  const int slots = 8 * n_genes;  // one sub-stream per (column, warp): 8 rows x N genes
   std::vector<uint32_t> s(slots + 1);
   for (int j = 0; j <= slots; ++j) {
     const double v = std::pow(1.0 - p, (double)j) * 4294967296.0;

@@ -1,25 +1,44 @@
 // Bit-sliced step kernel: the fast path, specialised per network at load time (NVRTC).
 //
 // Layout of the work
-//   A warp owns a tile of 1024 consecutive env instances.  Lane L owns the 32 envs
+//   A CTA of 4 warps owns a tile of 1024 consecutive env instances.  "Column" L (= lane id, in
+//   every warp) owns the 32 envs
 //       env(L, j, c) = tile_base + 128*j + 4*L + c,   j = 0..7, c = 0..3,   slice bit b = 4*j + c
 //   so every global access is a coalesced vector access (4 consecutive envs per lane: 32 B of
 //   state, 4*BINS action bytes, 16 B of target ids / rewards, 8 B of step counters, 4 B of flags).
-//   The lane transposes its 32 packed states into N bit-planes (plane i, bit b = gene i of env b):
-//   from then on one 32-bit logic instruction advances 32 envs at once.
+//   The column's 32 packed states are transposed into N bit-planes (plane i, bit b = gene i of
+//   env b): from then on one 32-bit logic instruction advances 32 envs at once.
 //
-// What is generated per network (net_gen.cuh, emitted by pbn_b200.cu from the truth tables)
-//   pbn_update(): for every gene, its predictor functions as LOP3 trees over the input planes --
-//   the truth tables are the LOP3 immediates -- plus the predictor-selection logic.
+//   The four warps split every phase of the tile (all exchange goes through shared memory, each
+//   thread only ever touches its own column; three block barriers per tile):
+//     A  warp w loads groups j = 2w, 2w+1 (8 envs per lane), applies the interventions, keeps the
+//        s1 rows in registers and publishes them                                   -> S1 rows
+//     B  warp w gathers byte w of all 32 rows and finishes an 8x8-block bit transpose
+//        = planes 8w..8w+7 of each 32-gene word                                    -> PL planes
+//     C1 warp w draws the selection planes of slots r = w, w+4, ... from Philox   -> SEL planes
+//     C2 warp w evaluates "its" genes: generated LOP3 trees (net_update.inc)       -> OPL planes
+//     E  warp w gathers byte w of all out planes, 8x8-block transpose = its 8 next-state rows
+//     D  sparse perturbation events of the column, applied by the warp that owns the row
+//     F  target test, counters, reward, vector stores for its 8 envs; G auto-reset
+//
+// Code shape (profiles/r01_notes.md): a first, fully unrolled one-warp-per-tile version of this
+// kernel starved for instructions (300 KB of straight-line SASS); a compact-loop one-warp version
+// was latency-bound (1.7 warps per scheduler at 2^20 envs).  Hence four warps per tile, and only
+// the predictor functions themselves (LOP3 trees whose immediates are the truth tables) are
+// generated straight-line code.
 //
 // Random streams (DESIGN.md "Sliced random stream"; CPU twin: oracle/pbn_oracle.py sliced_stream)
 //   group id = (env >> 10) * 32 + ((env >> 2) & 31)  (= tile * 32 + lane), slice bit as above.
-//   SELECT  words, in gene order: K=1 none, K=2 one word, K=4 two words (b0,b1), K=3 six words
-//           (b0,b1,c0,c1,d0,d1): pair value 3 is rejected and replaced by the next pair; slots still
-//           rejected after the third pair draw 2-bit pairs from the FIX stream (gene order, bit
-//           order, 16 pairs per word LSB first) until one is != 3.  sel = b0 + 2*b1.
-//   PERTURB words: geometric skipping over slots q = gene*32 + bit with survival table S[0..32N].
-//   RESET   per env (global env id), as in the scalar kernel.
+//   SELECT: the genes with K > 1 predictors get slots r = 0, 1, ... in gene order; slot r owns
+//           Philox blocks 2r and 2r+1 = words w0..w7.  K=2 uses w0 (s0), K=4 w0,w1 (s0,s1), K=3 four
+//           pairs (w0,w1),(w2,w3),(w4,w5),(w6,w7): pair value 3 is rejected and replaced by the next
+//           pair; slots still rejected after the fourth pair (1/256 of them) draw 2-bit pairs from
+//           FIX sub-stream q = r mod 4 (Philox blocks (FIX, 64q + i); shared by the slots r = q,
+//           q+4, ... in that order; bit order inside a slot; 16 pairs per word LSB first) until one
+//           is != 3.  sel = s0 + 2*s1.
+//   PERTURB: sub-stream q = b >> 3 (Philox blocks (PERTURB, 64q + i)) covers the 8 slice bits
+//           8q..8q+7: geometric skipping over slots gene*8 + (b & 7) with survival table S[0..8N].
+//   RESET:  per env (global env id), as in the scalar kernel.
 //
 // Algorithmic HBM bytes per env-step: 33 (N <= 64) / 49 (N <= 128), see step_scalar.cuh.
 #pragma once
@@ -33,10 +52,21 @@ namespace pbn {
 
 #define PBN_RNG_FIX 3u
 
-constexpr int kSlots = 32 * PBN_N;            // perturbation slots per lane-tile
+constexpr int kSlots = 8 * PBN_N;             // perturbation slots per (column, warp) sub-stream
 constexpr int kNW = PBN_NW32;                 // 32-bit words per state
 constexpr int kW64 = (PBN_N <= 64) ? 1 : 2;   // 64-bit words per state in HBM
 constexpr uint32_t kLastMask = (PBN_N % 32) ? ((1u << (PBN_N % 32)) - 1u) : 0xFFFFFFFFu;
+constexpr int kWarps = 4;                     // warps per tile (PBN_THREADS == 128)
+
+// per-CTA scratch, in 32-bit words; every array is [row][lane]
+constexpr int kScrRows = 0;                          // S1 rows, later OPL out planes [kNW*32][32]
+constexpr int kScrPl = kScrRows + kNW * 32 * 32;     // PL input planes              [kNW*32][32]
+constexpr int kScrSel0 = kScrPl + kNW * 32 * 32;     // selection planes s0          [PBN_NSEL][32]
+constexpr int kScrSel1 = kScrSel0 + PBN_NSEL * 32;   // selection planes s1          [PBN_NSEL][32]
+constexpr int kScrStat = kScrSel1 + PBN_NSEL * 32;   // 8 block-level statistics counters
+constexpr int kScrWords = kScrStat + 8;              // total (must equal PBN_SCRATCH_WORDS)
+static_assert(kScrWords == PBN_SCRATCH_WORDS, "host and device disagree on the scratch size");
+static_assert(PBN_THREADS == 32 * kWarps, "one tile per 4-warp CTA");
 
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
   uint32_t r;
@@ -54,378 +84,435 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 // a ? b : c, bitwise
 __device__ __forceinline__ uint32_t bmux(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xCA>(a, b, c); }
 
-// In-place 32x32 bit transpose: afterwards a[i] bit b == (old a[b]) bit i.
-__device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+// One quarter of a 32x32 bit transpose.  `src` is a [32][32-lane] scratch array holding the 32 source
+// rows of this column; the result is rows 8q..8q+7 of the transposed matrix: out[i] bit b = (source
+// row b) bit 8q+i.  The two byte-granular butterfly stages are the byte gather below (byte q of rows
+// i, i+8, i+16, i+24), the three bit-granular ones run on the 8 registers.
+__device__ __forceinline__ void transpose_quarter(const uint32_t* src, uint32_t q, uint32_t (&out)[8]) {
+  const uint8_t* sb = reinterpret_cast<const uint8_t*>(src) + q;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const uint32_t lo = a[k], hi = a[k + 16];
-    a[k] = __byte_perm(lo, hi, 0x5410);
-    a[k + 16] = __byte_perm(lo, hi, 0x7632);
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t b0 = sb[(i)*128], b1 = sb[(i + 8) * 128], b2 = sb[(i + 16) * 128], b3 = sb[(i + 24) * 128];
+    out[i] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
   }
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    if (k & 8) continue;
-    const uint32_t lo = a[k], hi = a[k + 8];
-    a[k] = __byte_perm(lo, hi, 0x6240);
-    a[k + 8] = __byte_perm(lo, hi, 0x7351);
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t lo = out[k], hi = out[k + 4];
+    out[k] = bmux(0x0F0F0F0Fu, lo, hi << 4);
+    out[k + 4] = bmux(0x0F0F0F0Fu, lo >> 4, hi);
   }
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    if (k & 4) continue;
-    const uint32_t lo = a[k], hi = a[k + 4];
-    a[k] = bmux(0x0F0F0F0Fu, lo, hi << 4);
-    a[k + 4] = bmux(0x0F0F0F0Fu, lo >> 4, hi);
-  }
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
+  for (int k = 0; k < 8; ++k) {
     if (k & 2) continue;
-    const uint32_t lo = a[k], hi = a[k + 2];
-    a[k] = bmux(0x33333333u, lo, hi << 2);
-    a[k + 2] = bmux(0x33333333u, lo >> 2, hi);
+    const uint32_t lo = out[k], hi = out[k + 2];
+    out[k] = bmux(0x33333333u, lo, hi << 2);
+    out[k + 2] = bmux(0x33333333u, lo >> 2, hi);
   }
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
+  for (int k = 0; k < 8; ++k) {
     if (k & 1) continue;
-    const uint32_t lo = a[k], hi = a[k + 1];
-    a[k] = bmux(0x55555555u, lo, hi << 1);
-    a[k + 1] = bmux(0x55555555u, lo >> 1, hi);
+    const uint32_t lo = out[k], hi = out[k + 1];
+    out[k] = bmux(0x55555555u, lo, hi << 1);
+    out[k + 1] = bmux(0x55555555u, lo >> 1, hi);
   }
 }
 
-// Per-lane random-stream context.
-struct SlicedRng {
-  uint64_t gid;    // global slice-group id
-  uint64_t step;
-  uint32_t k0, k1;
-  // FIX-stream reservoir (2-bit pairs)
-  uint32_t fix_word, fix_cnt, fix_next;
-  Philox4 fix_blk;
-  // PERTURB-stream cursor
-  uint32_t pert_next;
-  Philox4 pert_blk;
+__device__ __forceinline__ uint32_t pick4(const Philox4& b, uint32_t q) {
+  return q == 0 ? b.x : q == 1 ? b.y : q == 2 ? b.z : b.w;
+}
 
-  __device__ __forceinline__ Philox4 block(uint32_t kind, uint32_t idx) const {
-    return philox_stream(gid, step, kind, idx, k0, k1);
-  }
-  __device__ __forceinline__ static uint32_t pick(const Philox4& b, uint32_t q) {
-    return q == 0 ? b.x : q == 1 ? b.y : q == 2 ? b.z : b.w;
-  }
-  __device__ __forceinline__ uint32_t next_fix_pair() {
-    if (fix_cnt == 0) {
-      if ((fix_next & 3u) == 0u) fix_blk = block(PBN_RNG_FIX, fix_next >> 2);
-      fix_word = pick(fix_blk, fix_next & 3u);
-      ++fix_next;
-      fix_cnt = 16;
-    }
-    const uint32_t pr = fix_word & 3u;
-    fix_word >>= 2;
-    --fix_cnt;
-    return pr;
-  }
-  // Resolve the slots of a K=3 gene that are still rejected (b0 = b1 = 1 there) after the three
-  // unconditional pair draws.
-  __device__ __forceinline__ void fix3(uint32_t& b0, uint32_t& b1, uint32_t rej) {
-    while (rej) {
-      const uint32_t pr = next_fix_pair();
-      if (pr != 3u) {
-        const uint32_t m = rej & (0u - rej);
-        rej ^= m;
-        b0 ^= (pr & 1u) ? 0u : m;
-        b1 ^= (pr & 2u) ? 0u : m;
-      }
-    }
-  }
-  __device__ __forceinline__ uint32_t next_pert_word() {
-    if ((pert_next & 3u) == 0u) pert_blk = block(PBN_RNG_PERTURB, pert_next >> 2);
-    const uint32_t u = pick(pert_blk, pert_next & 3u);
-    ++pert_next;
-    return u;
-  }
+// FIX sub-stream of one (column, warp): 2-bit pairs, consumed across the warp's slots.
+struct FixStream {
+  uint32_t word, cnt, next;
+  Philox4 blk;
 };
 
-// K=3 selection planes from six words: three unconditional pair draws, then the FIX stream.
-__device__ __forceinline__ void sel3(SlicedRng& rng, uint32_t b0, uint32_t b1, uint32_t c0, uint32_t c1,
-                                     uint32_t d0, uint32_t d1, uint32_t& s0, uint32_t& s1) {
-  uint32_t rej = b0 & b1;
-  b0 = bmux(rej, c0, b0);
-  b1 = bmux(rej, c1, b1);
-  rej = rej & c0 & c1;
-  b0 = bmux(rej, d0, b0);
-  b1 = bmux(rej, d1, b1);
-  rej = rej & d0 & d1;
-  rng.fix3(b0, b1, rej);
+// Selection planes of slot r of this column from the slot's two SELECT blocks (+ the FIX sub-stream).
+__device__ __forceinline__ void sel_slot(uint64_t gid, uint64_t step, const uint32_t (&rk)[20], uint32_t r,
+                                         uint32_t K, FixStream& fx, uint32_t& s0, uint32_t& s1) {
+  const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, 2u * r, rk);
+  const Philox4 B = philox_stream_rk(gid, step, PBN_RNG_SELECT, 2u * r + 1u, rk);
+  uint32_t b0 = A.x, b1 = A.y;
+  if (K == 3u) {
+    uint32_t rej = b0 & b1;
+    b0 = bmux(rej, A.z, b0);
+    b1 = bmux(rej, A.w, b1);
+    rej = rej & A.z & A.w;
+    b0 = bmux(rej, B.x, b0);
+    b1 = bmux(rej, B.y, b1);
+    rej = rej & B.x & B.y;
+    b0 = bmux(rej, B.z, b0);
+    b1 = bmux(rej, B.w, b1);
+    rej = rej & B.z & B.w;
+    // slots still rejected (b0 = b1 = 1 there): one 2-bit pair of the FIX sub-stream per trip
+    while (rej) {
+      if (fx.cnt == 0u) {
+        if ((fx.next & 3u) == 0u)
+          fx.blk = philox_stream_rk(gid, step, PBN_RNG_FIX, 64u * (r & 3u) + ((fx.next >> 2) & 63u), rk);
+        fx.word = pick4(fx.blk, fx.next & 3u);
+        ++fx.next;
+        fx.cnt = 16u;
+      }
+      const uint32_t pr = fx.word & 3u;
+      fx.word >>= 2;
+      --fx.cnt;
+      const uint32_t m = (pr != 3u) ? (rej & (0u - rej)) : 0u;
+      rej ^= m;
+      b0 ^= (pr & 1u) ? 0u : m;
+      b1 ^= (pr & 2u) ? 0u : m;
+    }
+  } else if (K == 2u) {
+    b1 = 0u;
+  }
   s0 = b0;
   s1 = b1;
 }
 
-// Parity entry point: predictor choices arrive per (env, gene) as bytes (slow, tests only).
-struct InjectedSel {
-  const uint8_t* sel;
-  int64_t e0, E;
-  __device__ __forceinline__ void get(int gene, uint32_t K, uint32_t& s0, uint32_t& s1) const {
-    s0 = 0u;
-    s1 = 0u;
+// Next event distance of the perturbation stream.
+__device__ __noinline__ int pert_search(const uint32_t* s_surv, uint32_t u) {
+  return count_below_survival(s_surv, kSlots, u) + 1;
+}
+
+}  // namespace pbn
+
+#include "net_update.inc"  // generated: kSelGene[], kSelK[], pbn::pbn_update_part(w, PL, OPL, SEL0, SEL1)
+
+namespace pbn {
+
+// Stage the small read-only tables into shared memory (first tile of a CTA, after its global loads
+// were issued; everything staged here is first read after block barrier (1)).
+__device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSmemLayout& L, uint32_t* s_surv,
+                                             float* s_rew, int32_t* s_aoffs, uint32_t* s_aent, uint32_t* s_stat) {
+  if (n.pert_rng)
+    for (int i = threadIdx.x; i <= kSlots; i += blockDim.x) s_surv[i] = n.surv_sliced[i];
+  if (threadIdx.x < 18) {
+    const uint32_t nf = threadIdx.x % 9u;
+    const bool hit = threadIdx.x >= 9;
+    const float base = __fadd_rn(n.r_step, __fmul_rn(n.r_action, (float)nf));
+    s_rew[threadIdx.x] = __fadd_rn(base, hit ? n.r_success : 0.0f);
+  }
+  if (threadIdx.x < 8) s_stat[threadIdx.x] = 0u;
+  if (L.attractors_in_smem) {
+    for (int i = threadIdx.x; i < n.n_attr_states * kNW; i += blockDim.x) {
+      const int en = i / kNW, wd = i - en * kNW;
+      s_aent[en * 2 * kNW + wd] = (uint32_t)(n.attr_care[en * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+      s_aent[en * 2 * kNW + kNW + wd] = (uint32_t)(n.attr_val[en * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+    }
+    for (int i = threadIdx.x; i <= n.n_attr; i += blockDim.x) s_aoffs[i] = n.attr_offset[i];
+  }
+}
+
+// ---- C1. selection planes of this warp's slots (independent of the state) -------------------------
+template <bool FULL>
+__device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, const NetParams& n, uint32_t* sel0,
+                                                      uint32_t* sel1, uint64_t gid, uint64_t step_ctr, int64_t e0,
+                                                      uint32_t w) {
+#if PBN_INJECTED
+  const int64_t E = a.n_envs;
+#pragma unroll 1
+  for (int r = (int)w; r < PBN_NSEL; r += kWarps) {
+    const uint32_t g = kSelGene[r], K = kSelK[r];
+    uint32_t s0 = 0u, s1 = 0u;
     for (int b = 0; b < 32; ++b) {
       const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
-      uint32_t v = (env < E) ? sel[env * PBN_N + gene] : 0u;
+      uint32_t v = (env < E) ? a.sel[env * PBN_N + g] : 0u;
       v = v < K ? v : K - 1u;
       s0 |= (v & 1u) << b;
       s1 |= ((v >> 1) & 1u) << b;
     }
+    sel0[r * 32] = s0;
+    sel1[r * 32] = s1;
   }
-};
-
-#if PBN_INJECTED
-#define PBN_SEL_BLOCK(name, idx)
-#define PBN_SEL2(g, w0, s0, s1) sel.get(g, 2u, s0, s1)
-#define PBN_SEL3(g, w0, w1, w2, w3, w4, w5, s0, s1) sel.get(g, 3u, s0, s1)
-#define PBN_SEL4(g, w0, w1, s0, s1) sel.get(g, 4u, s0, s1)
 #else
-#define PBN_SEL_BLOCK(name, idx) const Philox4 name = sel.block(PBN_RNG_SELECT, idx)
-#define PBN_SEL2(g, w0, s0, s1) do { s0 = (w0); s1 = 0u; } while (0)
-#define PBN_SEL3(g, w0, w1, w2, w3, w4, w5, s0, s1) sel3(sel, w0, w1, w2, w3, w4, w5, s0, s1)
-#define PBN_SEL4(g, w0, w1, s0, s1) do { s0 = (w0); s1 = (w1); } while (0)
+  FixStream fx;
+  // first FIX block up front: otherwise some lane meets its first rejected slot in nearly
+  // every trip and the whole warp pays for a Philox block each time
+  fx.blk = philox_stream_rk(gid, step_ctr, PBN_RNG_FIX, 64u * w, n.rk);
+  fx.word = fx.blk.x;
+  fx.cnt = 16u;
+  fx.next = 1u;
+#pragma unroll 1
+  for (int r = (int)w; r < PBN_NSEL; r += kWarps) {
+    uint32_t s0, s1;
+    sel_slot(gid, step_ctr, n.rk, (uint32_t)r, kSelK[r], fx, s0, s1);
+    sel0[r * 32] = s0;
+    sel1[r * 32] = s1;
+  }
 #endif
-
-}  // namespace pbn
-
-#include "net_update.inc"  // generated: pbn::pbn_update(x, o, rng)
-
-namespace pbn {
-
-struct TileStats {
-  uint32_t steps, eps, term, trunc, len, flips, pert;
-};
-
-// Next event distance of the perturbation stream (cold path: one call per perturbed gene + 1).
-__device__ __noinline__ int pert_skip(SlicedRng& rng, const uint32_t* s_surv) {
-  const uint32_t u = rng.next_pert_word();
-  if (u < s_surv[kSlots]) return kSlots + 1;
-  return count_below_survival(s_surv, kSlots, u) + 1;
 }
 
 // FULL: the tile has all 1024 envs (vector loads/stores); otherwise every access is guarded.
-__device__ __forceinline__ void tile_step(const StepParams& p, const uint32_t* s_surv, const float* s_rew,
-                                          const int32_t* aoffs, const uint64_t* acare, const uint64_t* aval,
-                                          int64_t tile, uint64_t step_ctr, const bool FULL, TileStats& st) {
+// ASMEM: the attractor table was staged into shared memory (the usual case).
+template <bool FULL, bool ASMEM>
+__device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemLayout& L, uint32_t* scr,
+                                          uint32_t* s_surv, float* s_rew, int32_t* s_aoffs, uint32_t* s_aent,
+                                          int64_t tile, uint64_t step_ctr, const bool stage) {
+  constexpr bool attr_in_smem = ASMEM;
   const pbn_step_args& a = p.a;
   const NetParams& n = p.n;
   const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t w = threadIdx.x >> 5;  // warp in tile: owns groups 2w, 2w+1 = rows 8w..8w+7
   const int64_t E = a.n_envs;
   const int64_t e0 = tile * 1024 + 4 * (int64_t)lane;  // local env index of (j = 0, c = 0)
+  uint32_t* rows = scr + kScrRows + lane;   // S1 rows in phases A/B, OPL planes in C2/E
+  uint32_t* pl = scr + kScrPl + lane;
+  uint32_t* sel0 = scr + kScrSel0 + lane;
+  uint32_t* sel1 = scr + kScrSel1 + lane;
+  uint32_t* s_stat = scr + kScrStat;
 
-  uint32_t x[kNW][32];
-  uint32_t nfp[4] = {0u, 0u, 0u, 0u};  // 4-bit flip counts, env b -> nfp[b >> 3] bits 4*(b&7)..
-
-  // ---- A. load states + actions, apply the interventions ---------------------------------
+  // ---- A0. issue this warp's global loads (consumed after C1, which hides their latency) -----------
+  uint32_t r1[8][kNW];   // s1 rows of this warp's 8 envs (row index 8w + i, i = 4*g + c)
+  uint32_t nfp = 0u;     // 4-bit flip counts of the 8 envs
+  uint32_t tg[8];        // target ids (prefetched for phase F)
+  uint32_t tt[8];        // episode step counters
+  uint32_t flips = 0u;
+  uint64_t sraw[2][4][kW64];
+  uint32_t awraw[2][PBN_BINS];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int64_t e = e0 + 128 * j;
-    uint64_t s[4][kW64];
+  for (int g = 0; g < 2; ++g) {
+    const int64_t e = e0 + 128 * (2 * (int)w + g);
+#pragma unroll
+    for (int k = 0; k < PBN_BINS; ++k) awraw[g][k] = 0u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tg[4 * g + c] = 0xFFFFFFFFu;
+      tt[4 * g + c] = 0u;
+    }
     if (FULL) {
       const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(a.state + e * kW64);
 #pragma unroll
       for (int q = 0; q < 2 * kW64; ++q) {
         const ulonglong2 v = sp[q];
-        s[(2 * q) / kW64][(2 * q) % kW64] = v.x;
-        s[(2 * q + 1) / kW64][(2 * q + 1) % kW64] = v.y;
+        sraw[g][(2 * q) / kW64][(2 * q) % kW64] = v.x;
+        sraw[g][(2 * q + 1) / kW64][(2 * q + 1) % kW64] = v.y;
+      }
+      if (a.actions != nullptr) {
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(a.actions + e * PBN_BINS);
+#pragma unroll
+        for (int k = 0; k < PBN_BINS; ++k) awraw[g][k] = ap[k];
+      }
+      if (a.target_id != nullptr) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a.target_id + e);
+        tg[4 * g] = v.x; tg[4 * g + 1] = v.y; tg[4 * g + 2] = v.z; tg[4 * g + 3] = v.w;
+      }
+      if (a.t != nullptr) {
+        const uint2 v = *reinterpret_cast<const uint2*>(a.t + e);
+        tt[4 * g] = v.x & 0xFFFFu; tt[4 * g + 1] = v.x >> 16; tt[4 * g + 2] = v.y & 0xFFFFu; tt[4 * g + 3] = v.y >> 16;
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int w = 0; w < kW64; ++w) s[c][w] = (e + c < E) ? a.state[(e + c) * kW64 + w] : 0ull;
-    }
-    uint32_t aw[PBN_BINS];
-#pragma unroll
-    for (int k = 0; k < PBN_BINS; ++k) aw[k] = 0u;
-    if (a.actions != nullptr) {
-      if (FULL) {
-        const uint32_t* ap = reinterpret_cast<const uint32_t*>(a.actions + e * PBN_BINS);
-#pragma unroll
-        for (int k = 0; k < PBN_BINS; ++k) aw[k] = ap[k];
-      } else {
+        for (int wd = 0; wd < kW64; ++wd) sraw[g][c][wd] = (e + c < E) ? a.state[(e + c) * kW64 + wd] : 0ull;
+        if (a.target_id != nullptr && e + c < E) tg[4 * g + c] = (uint32_t)a.target_id[e + c];
+        if (a.t != nullptr && e + c < E) tt[4 * g + c] = a.t[e + c];
+      }
+      if (a.actions != nullptr) {
 #pragma unroll
         for (int q = 0; q < 4 * PBN_BINS; ++q) {
           const int64_t env = e + q / PBN_BINS;
           const uint32_t v = (env < E) ? a.actions[e * PBN_BINS + q] : 0u;
-          aw[q >> 2] |= v << (8 * (q & 3));
+          awraw[g][q >> 2] |= v << (8 * (q & 3));
         }
       }
     }
+  }
+
+  if (stage) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);
+  const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
+  // ---- C1 (even tiles: here, hiding the load latency; odd tiles: after B, so that neighbouring
+  //      CTAs of the single wave are in different phases and share the SM's issue slots better)
+  const bool c1_first = (tile & 1) == 0;
+  if (c1_first) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
+
+  // ---- A1. apply the interventions, publish the s1 rows -----------------------------------------------
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int64_t e = e0 + 128 * (2 * (int)w + g);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t fl[kNW];
 #pragma unroll
-      for (int w = 0; w < kNW; ++w) fl[w] = 0u;
+      for (int wd = 0; wd < kNW; ++wd) fl[wd] = 0u;
 #pragma unroll
       for (int k = 0; k < PBN_BINS; ++k) {
         const int q = c * PBN_BINS + k;
-        const uint32_t act = (aw[q >> 2] >> (8 * (q & 3))) & 0xFFu;
+        const uint32_t act = (awraw[g][q >> 2] >> (8 * (q & 3))) & 0xFFu;
 #pragma unroll
-        for (int w = 0; w < kNW; ++w) fl[w] |= shl_clamp(1u, act - 1u - 32u * w);
+        for (int wd = 0; wd < kNW; ++wd) fl[wd] |= shl_clamp(1u, act - 1u - 32u * wd);
       }
       fl[kNW - 1] &= kLastMask;
       uint32_t nf = 0;
 #pragma unroll
-      for (int w = 0; w < kNW; ++w) nf += __popc(fl[w]);
-      const int b = 4 * j + c;
-      nfp[b >> 3] |= nf << (4 * (b & 7));
+      for (int wd = 0; wd < kNW; ++wd) nf += __popc(fl[wd]);
+      const int i = 4 * g + c;
+      nfp |= nf << (4 * i);
+      if (FULL || e + c < E) flips += nf;
 #pragma unroll
-      for (int w = 0; w < kNW; ++w) {
-        const uint32_t sw = (uint32_t)(s[c][w >> 1] >> (32 * (w & 1)));
-        x[w][b] = sw ^ fl[w];
+      for (int wd = 0; wd < kNW; ++wd) {
+        const uint32_t sw = (uint32_t)(sraw[g][c][wd >> 1] >> (32 * (wd & 1)));
+        r1[i][wd] = sw ^ fl[wd];
+        rows[(wd * 32 + 8 * (int)w + i) * 32] = r1[i][wd];
       }
     }
   }
+  __syncthreads();  // (1) all 32 s1 rows of the column are in scratch
 
-  // ---- B. rows -> bit-planes --------------------------------------------------------------
+  // ---- B. rows -> bit-planes: this warp produces planes 8w..8w+7 of every word ------------------
 #pragma unroll
-  for (int w = 0; w < kNW; ++w) transpose32(x[w]);
+  for (int wd = 0; wd < kNW; ++wd) {
+    uint32_t q8[8];
+    transpose_quarter(rows + wd * 32 * 32, w, q8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pl[(wd * 32 + 8 * (int)w + i) * 32] = q8[i];
+  }
 
-  // ---- C. predictor selection + synchronous update (generated) ---------------------------
-  SlicedRng rng;
-  rng.gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
-  rng.step = step_ctr;
-  rng.k0 = n.k0;
-  rng.k1 = n.k1;
-  rng.fix_word = 0;
-  rng.fix_cnt = 0;
-  rng.fix_next = 0;
-  rng.pert_next = 0;
-  uint32_t o[kNW][32];
-#if PBN_INJECTED
-  InjectedSel isel{a.sel, e0, E};
-  pbn_update(x, o, isel);
-#else
-  pbn_update(x, o, rng);
-#endif
+  if (!c1_first) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
+  __syncthreads();  // (2) all input planes (and selection planes) are in scratch; S1 rows are dead
 
-  // ---- D. perturbation ---------------------------------------------------------------------
-  uint32_t npert = 0;
-  const int pert_mode = n.pert_mode;  // warp-uniform
+  // ---- C2. synchronous update of this warp's genes: generated LOP3 trees -> OPL planes ----------
+  pbn_update_part(w, pl, rows, sel0, sel1);
+  __syncthreads();  // (3) all out planes are in scratch
+
+  // ---- E. bit-planes -> this warp's 8 next-state rows --------------------------------------------
+  uint32_t o[8][kNW];
+#pragma unroll
+  for (int wd = 0; wd < kNW; ++wd) {
+    uint32_t q8[8];
+    transpose_quarter(rows + wd * 32 * 32, w, q8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][wd] = q8[i];
+  }
+
+  // ---- D. perturbation (row domain, sparse) ---------------------------------------------------------
+  uint32_t npert = 0u;
+  const int pert_mode = n.pert_mode;  // block-uniform
   if (pert_mode != PBN_PERT_NONE) {
-    uint32_t M = 0u;
 #if PBN_INJECTED
-    {
-      if (a.pert_mask != nullptr) {
-        // rows -> planes of the injected masks (slow path)
-        uint32_t q[kNW][32];
+    if (a.pert_mask != nullptr) {
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-          const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
+      for (int i = 0; i < 8; ++i) {
+        const int64_t env = e0 + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
+        uint32_t pm[kNW];
+        bool any = false;
 #pragma unroll
-          for (int w = 0; w < kNW; ++w) {
-            const uint64_t v = (env < E) ? a.pert_mask[env * kW64 + (w >> 1)] : 0ull;
-            q[w][b] = (uint32_t)(v >> (32 * (w & 1)));
-          }
+        for (int wd = 0; wd < kNW; ++wd) {
+          pm[wd] = (env < E) ? (uint32_t)(a.pert_mask[env * kW64 + (wd >> 1)] >> (32 * (wd & 1))) : 0u;
+          if (wd == kNW - 1) pm[wd] &= kLastMask;
+          any = any || pm[wd] != 0u;
+          npert += __popc(pm[wd]);
         }
 #pragma unroll
-        for (int w = 0; w < kNW; ++w) transpose32(q[w]);
-#pragma unroll
-        for (int w = 0; w < kNW; ++w)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (32 * w + i >= PBN_N) continue;
-            M |= q[w][i];
-            npert += __popc(q[w][i]);
-            if (pert_mode == PBN_PERT_A) x[w][i] ^= q[w][i];
-            else if (pert_mode == PBN_PERT_B) o[w][i] ^= q[w][i];
-            else o[w][i] = bmux(q[w][i], ~x[w][i], o[w][i]);
-          }
+        for (int wd = 0; wd < kNW; ++wd) {
+          if (pert_mode == PBN_PERT_A) o[i][wd] = any ? (r1[i][wd] ^ pm[wd]) : o[i][wd];
+          else if (pert_mode == PBN_PERT_B) o[i][wd] ^= pm[wd];
+          else o[i][wd] = bmux(pm[wd], ~r1[i][wd], o[i][wd]);
+        }
       }
     }
 #else
     if (n.pert_rng) {
-      int pos = -1 + pert_skip(rng, s_surv);
+      // this warp's own event sub-stream: slots gene*8 + row over its 8 rows
+      const uint32_t s_last = s_surv[kSlots];
+      uint32_t pert_next = 0u, M = 0u;
+      Philox4 pert_blk = {0u, 0u, 0u, 0u};
+      int pos = -1;
+      while (true) {
+        if ((pert_next & 3u) == 0u)
+          pert_blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
+        const uint32_t u = pick4(pert_blk, pert_next & 3u);
+        ++pert_next;
+        pos += (u < s_last) ? kSlots + 1 : pert_search(s_surv, u);
+        if (pos >= kSlots) break;
+        const uint32_t g = (uint32_t)pos >> 3, ib = (uint32_t)pos & 7u;
+        const uint32_t m = 1u << (g & 31u), gw = g >> 5;
+        const bool first = !((M >> ib) & 1u);
+        M |= 1u << ib;
+        ++npert;
 #pragma unroll
-      for (int w = 0; w < kNW; ++w)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (32 * w + i >= PBN_N) continue;
-          uint32_t q = 0u;
-          while ((pos >> 5) == 32 * w + i) {
-            q |= 1u << (pos & 31);
-            pos += pert_skip(rng, s_surv);
+          for (int wd = 0; wd < kNW; ++wd) {
+            const bool here = (uint32_t)i == ib;
+            const uint32_t mm = (here && (uint32_t)wd == gw) ? m : 0u;
+            if (pert_mode == PBN_PERT_A) {
+              if (here && first) o[i][wd] = r1[i][wd];
+              o[i][wd] ^= mm;
+            } else if (pert_mode == PBN_PERT_B) {
+              o[i][wd] ^= mm;
+            } else {
+              o[i][wd] = bmux(mm, ~r1[i][wd], o[i][wd]);
+            }
           }
-          M |= q;
-          npert += __popc(q);
-          if (pert_mode == PBN_PERT_A) x[w][i] ^= q;
-          else if (pert_mode == PBN_PERT_B) o[w][i] ^= q;
-          else o[w][i] = bmux(q, ~x[w][i], o[w][i]);
-        }
+      }
     }
 #endif
-    if (pert_mode == PBN_PERT_A) {
-      // envs with any perturbed gene keep s1 XOR pert (x already holds it), the others take f
-#pragma unroll
-      for (int w = 0; w < kNW; ++w)
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (32 * w + i < PBN_N) o[w][i] = bmux(M, x[w][i], o[w][i]);
-    }
   }
 
-  // ---- E. bit-planes -> rows ---------------------------------------------------------------
+  // ---- F. target test, counters, reward, stores ------------------------------------------------------
+  uint32_t H = 0u, TR = 0u, VALID = 0u, len_sum = 0u;
+  const uint32_t n_attr = (a.target_id != nullptr) ? (uint32_t)n.n_attr : 0u;
+  const uint32_t horizon = n.horizon > 0 ? (uint32_t)n.horizon : 0xFFFFFFFFu;
+  const bool simple = n.attr_simple != 0u;  // block-uniform
 #pragma unroll
-  for (int w = 0; w < kNW; ++w) transpose32(o[w]);
-
-  // ---- F. target test, counters, reward, stores ---------------------------------------------
-  uint32_t H = 0u, TR = 0u, VALID = 0u;
-  uint32_t len_sum = 0u, flips = 0u;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int64_t e = e0 + 128 * j;
-    int32_t tg[4] = {-1, -1, -1, -1};
-    uint32_t tt[4] = {0u, 0u, 0u, 0u};
-    if (a.target_id != nullptr) {
-      if (FULL) {
-        const int4 v = *reinterpret_cast<const int4*>(a.target_id + e);
-        tg[0] = v.x; tg[1] = v.y; tg[2] = v.z; tg[3] = v.w;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tg[c] = (e + c < E) ? a.target_id[e + c] : -1;
-      }
-    }
-    if (a.t != nullptr) {
-      if (FULL) {
-        const uint2 v = *reinterpret_cast<const uint2*>(a.t + e);
-        tt[0] = v.x & 0xFFFFu; tt[1] = v.x >> 16; tt[2] = v.y & 0xFFFFu; tt[3] = v.y >> 16;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tt[c] = (e + c < E) ? a.t[e + c] : 0u;
-      }
-    }
-    uint64_t y[4][kW64];
+  for (int g = 0; g < 2; ++g) {
+    const int64_t e = e0 + 128 * (2 * (int)w + g);
     float rw[4];
-    uint32_t hbits = 0u, tbits = 0u;
+    uint32_t hbits = 0u, tbits = 0u, vbits = 0u;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int b = 4 * j + c;
-#pragma unroll
-      for (int w = 0; w < kW64; ++w) {
-        const uint32_t lo = o[2 * w][b];
-        const uint32_t hi = (2 * w + 1 < kNW) ? o[(2 * w + 1 < kNW) ? 2 * w + 1 : 0][b] : 0u;
-        y[c][w] = ((uint64_t)hi << 32) | lo;
-      }
+      const int i = 4 * g + c;
       bool hit = false;
-      if (tg[c] >= 0 && tg[c] < n.n_attr) hit = in_attractor<kW64>(aoffs, acare, aval, tg[c], y[c]);
-      const uint32_t t1 = tt[c] < 65535u ? tt[c] + 1u : 65535u;
-      const bool trunc = !hit && n.horizon > 0 && t1 >= (uint32_t)n.horizon;
-      const uint32_t nf = (nfp[b >> 3] >> (4 * (b & 7))) & 0xFu;
+      if (tg[i] < n_attr) {  // unsigned compare: negative ids never match
+        if (attr_in_smem && simple) {
+          // one fully specified state per attractor: entry index == attractor id
+          const uint32_t* ent = s_aent + tg[i] * (2 * kNW) + kNW;
+          uint32_t diff = 0u;
+#pragma unroll
+          for (int wd = 0; wd < kNW; ++wd) diff |= o[i][wd] ^ ent[wd];
+          hit = diff == 0u;
+        } else if (attr_in_smem) {
+          int en = s_aoffs[tg[i]];
+          const int en1 = s_aoffs[tg[i] + 1];
+#pragma unroll 1
+          do {
+            const uint32_t* ent = s_aent + en * (2 * kNW);
+            uint32_t diff = 0u;
+#pragma unroll
+            for (int wd = 0; wd < kNW; ++wd) diff |= (o[i][wd] & ent[wd]) ^ ent[kNW + wd];
+            hit = hit || diff == 0u;
+          } while (++en < en1);
+        } else {
+          uint64_t y64[kW64];
+#pragma unroll
+          for (int wd = 0; wd < kW64; ++wd)
+            y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
+          hit = in_attractor<kW64>(n.attr_offset, n.attr_care, n.attr_val, (int)tg[i], y64);
+        }
+      }
+      const uint32_t t1 = min(tt[i] + 1u, 65535u);
+      const bool trunc = !hit && t1 >= horizon;
+      const uint32_t nf = (nfp >> (4 * i)) & 0xFu;
       rw[c] = s_rew[nf + (hit ? 9u : 0u)];
       const bool valid = FULL || (e + c < E);
       hbits |= (hit && valid ? 1u : 0u) << c;
       tbits |= (trunc && valid ? 1u : 0u) << c;
-      VALID |= (valid ? 1u : 0u) << b;
+      vbits |= (valid ? 1u : 0u) << c;
       if ((hit || trunc) && valid) len_sum += t1;
-      if (valid) flips += nf;
-      tt[c] = t1;
+      tt[i] = t1;
     }
-    H |= hbits << (4 * j);
-    TR |= tbits << (4 * j);
+    H |= hbits << (4 * g);
+    TR |= tbits << (4 * g);
+    VALID |= vbits << (4 * g);
     const uint32_t hbytes = (hbits * 0x00204081u) & 0x01010101u;
     const uint32_t tbytes = (tbits * 0x00204081u) & 0x01010101u;
+    uint64_t y[4][kW64];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int wd = 0; wd < kW64; ++wd)
+        y[c][wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[4 * g + c][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) |
+                   o[4 * g + c][2 * wd];
     if (FULL) {
       ulonglong2* sp = reinterpret_cast<ulonglong2*>(a.state + e * kW64);
 #pragma unroll
@@ -440,44 +527,58 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const uint32_t* s
       if (a.reward != nullptr) *reinterpret_cast<float4*>(a.reward + e) = make_float4(rw[0], rw[1], rw[2], rw[3]);
       if (a.terminated != nullptr) *reinterpret_cast<uint32_t*>(a.terminated + e) = hbytes;
       if (a.truncated != nullptr) *reinterpret_cast<uint32_t*>(a.truncated + e) = tbytes;
-      if (a.t != nullptr) *reinterpret_cast<uint2*>(a.t + e) = make_uint2(tt[0] | (tt[1] << 16), tt[2] | (tt[3] << 16));
+      if (a.t != nullptr)
+        *reinterpret_cast<uint2*>(a.t + e) =
+            make_uint2(tt[4 * g] | (tt[4 * g + 1] << 16), tt[4 * g + 2] | (tt[4 * g + 3] << 16));
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (e + c >= E) continue;
 #pragma unroll
-        for (int w = 0; w < kW64; ++w) {
-          a.state[(e + c) * kW64 + w] = y[c][w];
-          if (a.final_state != nullptr) a.final_state[(e + c) * kW64 + w] = y[c][w];
+        for (int wd = 0; wd < kW64; ++wd) {
+          a.state[(e + c) * kW64 + wd] = y[c][wd];
+          if (a.final_state != nullptr) a.final_state[(e + c) * kW64 + wd] = y[c][wd];
         }
         if (a.reward != nullptr) a.reward[e + c] = rw[c];
         if (a.terminated != nullptr) a.terminated[e + c] = (uint8_t)((hbits >> c) & 1u);
         if (a.truncated != nullptr) a.truncated[e + c] = (uint8_t)((tbits >> c) & 1u);
-        if (a.t != nullptr) a.t[e + c] = (uint16_t)tt[c];
+        if (a.t != nullptr) a.t[e + c] = (uint16_t)tt[4 * g + c];
       }
     }
   }
 
-  // ---- G. auto-reset of finished envs (sparse: scattered writes after the vector stores) ----
+  // ---- G. auto-reset of finished envs (sparse: scattered writes after the vector stores) ----------
   uint32_t D = (H | TR) & VALID;
-  st.steps += __popc(VALID);
-  st.eps += __popc(D);
-  st.term += __popc(H & VALID);
-  st.trunc += __popc(TR & VALID);
-  st.len += len_sum;
-  st.flips += flips;
-  st.pert += npert;
+  if (a.stats != nullptr) {
+    const uint32_t v[7] = {(uint32_t)__popc(VALID), (uint32_t)__popc(D), (uint32_t)__popc(H & VALID),
+                           (uint32_t)__popc(TR & VALID), len_sum, flips, npert};
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const uint32_t x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
+      if (lane == 0u && x != 0u) atomicAdd(&s_stat[q], x);
+    }
+  }
   if (a.flags & PBN_STEP_AUTORESET) {
     while (D) {
-      const int b = __ffs(D) - 1;
+      const int i = __ffs(D) - 1;
       D &= D - 1u;
-      const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
-      const Philox4 r = philox_stream((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.k0, n.k1);
+      const int64_t env = e0 + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
+      const Philox4 r = philox_stream_rk((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.rk);
       uint64_t s[kW64];
       int src, tgt;
-      reset_draw<kW64>(n, r, s, src, tgt);
+      if (attr_in_smem) {
+        reset_pair(n, r, src, tgt);
+        const int o0 = s_aoffs[src];
+        const int j = o0 + (int)__umulhi(r.y, (uint32_t)(s_aoffs[src + 1] - o0));
+        const uint32_t* ent = s_aent + j * (2 * kNW) + kNW;
 #pragma unroll
-      for (int w = 0; w < kW64; ++w) a.state[env * kW64 + w] = s[w];
+        for (int wd = 0; wd < kW64; ++wd)
+          s[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? ent[(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | ent[2 * wd];
+      } else {
+        reset_draw<kW64>(n, r, s, src, tgt);
+      }
+#pragma unroll
+      for (int wd = 0; wd < kW64; ++wd) a.state[env * kW64 + wd] = s[wd];
       a.target_id[env] = tgt;
       if (a.source_id != nullptr) a.source_id[env] = src;
       a.t[env] = 0;
@@ -492,45 +593,27 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
   const pbn_step_args& a = p.a;
   uint32_t* s_surv = reinterpret_cast<uint32_t*>(smem_raw + L.surv_off);
   float* s_rew = reinterpret_cast<float*>(smem_raw + L.rew_off);
-  uint64_t* s_acare = reinterpret_cast<uint64_t*>(smem_raw + L.acare_off);
-  uint64_t* s_aval = reinterpret_cast<uint64_t*>(smem_raw + L.aval_off);
+  uint32_t* s_aent = reinterpret_cast<uint32_t*>(smem_raw + L.acare_off);  // [entry][care words | value words]
   int32_t* s_aoffs = reinterpret_cast<int32_t*>(smem_raw + L.aoffs_off);
-
-  if (n.pert_rng)
-    for (int i = threadIdx.x; i <= kSlots; i += blockDim.x) s_surv[i] = n.surv_sliced[i];
-  if (threadIdx.x < 18) {
-    const uint32_t nf = threadIdx.x % 9u;
-    const bool hit = threadIdx.x >= 9;
-    const float base = __fadd_rn(n.r_step, __fmul_rn(n.r_action, (float)nf));
-    s_rew[threadIdx.x] = __fadd_rn(base, hit ? n.r_success : 0.0f);
-  }
-  if (L.attractors_in_smem) {
-    for (int i = threadIdx.x; i < n.n_attr_states * kW64; i += blockDim.x) {
-      s_acare[i] = n.attr_care[i];
-      s_aval[i] = n.attr_val[i];
-    }
-    for (int i = threadIdx.x; i <= n.n_attr; i += blockDim.x) s_aoffs[i] = n.attr_offset[i];
-  }
-  __syncthreads();
-  const int32_t* aoffs = L.attractors_in_smem ? s_aoffs : n.attr_offset;
-  const uint64_t* acare = L.attractors_in_smem ? s_acare : n.attr_care;
-  const uint64_t* aval = L.attractors_in_smem ? s_aval : n.attr_val;
+  uint32_t* scr = reinterpret_cast<uint32_t*>(smem_raw + L.scratch_off);
 
   const uint64_t step_ctr = effective_step(a);
   const int64_t n_tiles = (a.n_envs + 1023) >> 10;
-  const int warps_per_block = blockDim.x >> 5;
-  TileStats st = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
-  for (int64_t tile = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); tile < n_tiles;
-       tile += (int64_t)gridDim.x * warps_per_block) {
-    tile_step(p, s_surv, s_rew, aoffs, acare, aval, tile, step_ctr, (tile + 1) * 1024 <= a.n_envs, st);
-  }
-  if (a.stats != nullptr) {
-    const uint32_t v[7] = {st.steps, st.eps, st.term, st.trunc, st.len, st.flips, st.pert};
-#pragma unroll
-    for (int q = 0; q < 7; ++q) {
-      const uint32_t x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
-      if ((threadIdx.x & 31u) == 0u && x != 0u) atomicAdd(&a.stats[q], (unsigned long long)x);
+  bool stage = true;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool full = (tile + 1) * 1024 <= a.n_envs;
+    if (L.attractors_in_smem != 0u) {
+      if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage);
+      else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage);
+    } else {
+      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage);
     }
+    stage = false;
+    __syncthreads();  // scratch is reused by the next tile; statistics are complete
+  }
+  if (a.stats != nullptr && threadIdx.x < 7) {
+    const uint32_t x = scr[kScrStat + threadIdx.x];
+    if (x != 0u) atomicAdd(&a.stats[threadIdx.x], (unsigned long long)x);
   }
   bump_device_step(a, p.ticket);
 }

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Time pbn_step variants on one GPU (CUDA-graph replays, CUDA events).  Development aid."""
+import argparse
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from pbn_rl_b200 import VecPBNEnv  # noqa: E402
+
+
+def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20):
+    dev = torch.device("cuda:0")
+    es = []
+    for b in range(batches):
+        kw = dict(bench.ENV_KW)
+        kw["perturb_p"] = p
+        e = VecPBNEnv(net, envs, attrs, device=dev, env_offset=b * envs, auto_reset=auto_reset, device_counter=True,
+                      kernel=kernel, **kw)
+        g = torch.Generator(device=dev).manual_seed(b)
+        e.state[:, 0] = torch.randint(0, 1 << min(net.n_genes, 62), (envs,), generator=g, device=dev)
+        e.set_target(torch.randint(0, len(attrs), (envs,), generator=g, device=dev, dtype=torch.int32))
+        es.append(e)
+    g = torch.Generator(device=dev).manual_seed(99)
+    pool = [torch.randint(0, net.n_genes + 1, (envs, 3), generator=g, device=dev, dtype=torch.uint8) for _ in range(8)]
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for i in range(4):
+            es[i % batches].step(pool[i % 8] if actions else None, stats=stats)
+        s.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            for i in range(graph_steps):
+                es[i % batches].step(pool[i % 8] if actions else None, stats=stats)
+        gr.replay()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            gr.replay()
+        e1.record(s)
+        s.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * graph_steps)
+    for e in es:
+        e.close()
+    return us
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--net", default="pbn28")
+    ap.add_argument("--envs", type=int, default=1 << 20)
+    ap.add_argument("--kernels", default="sliced")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    net, attrs = bench.load_workload(args.net)
+    W = net.n_words
+    rows = [("full (p=1e-3, reset, stats)", 0.001, True, True, True),
+            ("no perturbation", 0.0, True, True, True),
+            ("no auto-reset", 0.001, False, True, True),
+            ("no stats", 0.001, True, False, True),
+            ("no actions", 0.001, True, True, False),
+            ("bare (p=0, no reset/stats)", 0.0, False, False, True)]
+    if args.quick:
+        rows = rows[:1]
+    for kernel in args.kernels.split(","):
+        for label, p, ar, st, act in rows:
+            us = time_config(net, attrs, args.envs, kernel, p, ar, st, act)
+            gbs = bench.BYTES_PER_STEP[W] * args.envs / us / 1e3
+            print("%-8s %-30s %9.2f us/step  %8.3e steps/s  %7.1f GB/s" % (kernel, label, us, args.envs / us * 1e6, gbs), flush=True)
+
+
+if __name__ == "__main__":
+    main()
