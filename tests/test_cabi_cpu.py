@@ -1,0 +1,158 @@
+"""The C-ABI shared library without a GPU: it loads, exports every declared symbol, fails loudly on
+compute calls, and its load-time code generator emits correct LOP3 trees (checked by compiling the
+generated source as host C++)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import NETS, product_net
+from pbn_rl_b200 import PBNNetwork, _cabi
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _lib():
+    if not _cabi.LIB_PATH.exists():
+        pytest.skip("libpbn_b200.so not built (run __graft_entry__.build())")
+    return _cabi.load_library()
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib()
+    header = (ROOT / "include" / "pbn_b200.h").read_text()
+    declared = set(re.findall(r"\b(pbn_[a-z_0-9]+)\s*\(", header)) - {"pbn_step_args", "pbn_net_desc"}
+    assert declared == set(_cabi.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.pbn_version()
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed by hand from include/pbn_b200.h on LP64
+    assert C.sizeof(_cabi.NetDesc) == 112
+    assert C.sizeof(_cabi.StepArgs) == 13 * 8 + 8 + 8 + 8 + 4 + 4
+
+
+def test_no_silent_cpu_fallback():
+    """Without a CUDA device pbn_create reports a CUDA error; nothing computes on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib()
+    from pbn_rl_b200.vec_env import make_desc
+    d, keep = make_desc(product_net("pbn7"))
+    h = C.c_void_p()
+    rc = lib.pbn_create(C.byref(d), C.byref(h))
+    assert rc == -2 and not h.value
+    assert b"cuda" in lib.pbn_last_error().lower()
+    from pbn_rl_b200 import VecPBNEnv
+    with pytest.raises(RuntimeError):
+        VecPBNEnv(product_net("pbn7"), 16)
+    del keep
+
+
+def test_descriptor_validation_errors():
+    lib = _lib()
+    from pbn_rl_b200.vec_env import make_desc
+    d, keep = make_desc(product_net("pbn7"))
+    d.n_genes = 0
+    h = C.c_void_p()
+    assert lib.pbn_create(C.byref(d), C.byref(h)) == -1
+    d, keep = make_desc(product_net("pbn7"), bins=99)
+    assert lib.pbn_create(C.byref(d), C.byref(h)) == -1
+    assert b"bins" in lib.pbn_last_error()
+    assert lib.pbn_step(None, None, None) == -1
+    del keep
+
+
+def test_sliced_eligibility():
+    from pbn_rl_b200.vec_env import jit_source
+    assert "pbn_update_part" in jit_source(product_net("pbn28"))
+    nonuniform = PBNNetwork.from_expressions(["a", "b"], [[("a | b", 0.9), ("a & b", 0.1)], ["a"]])
+    with pytest.raises(_cabi.PbnError) as ei:
+        jit_source(nonuniform)
+    assert ei.value.code == -3
+    five = PBNNetwork.from_expressions(["a", "b"], [["a", "b", "a|b", "a&b", "~a"], ["a"]])
+    with pytest.raises(_cabi.PbnError):
+        jit_source(five)
+
+
+HOST_HARNESS = r"""
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#define __device__
+#define __forceinline__ inline
+#define __constant__ const
+template <int IMM> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r = 0;
+  for (int i = 0; i < 32; ++i) {
+    const int idx = (((a >> i) & 1) << 2) | (((b >> i) & 1) << 1) | ((c >> i) & 1);
+    r |= (uint32_t)((IMM >> idx) & 1) << i;
+  }
+  return r;
+}
+static inline uint32_t bmux(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (~a & c); }
+#include "net_update.inc"
+int main(int argc, char** argv) {
+  // stdin: N NSEL, then per case: N input planes, NSEL s0 planes, NSEL s1 planes; stdout: N out planes
+  int n, nsel, cases;
+  if (scanf("%d %d %d", &n, &nsel, &cases) != 3) return 1;
+  const int nw = (n + 31) / 32;
+  static uint32_t x[128 * 32], o[128 * 32], s0[128 * 32], s1[128 * 32];
+  for (int c = 0; c < cases; ++c) {
+    for (int i = 0; i < n; ++i) if (scanf("%u", &x[i * 32]) != 1) return 1;
+    for (int i = 0; i < nsel; ++i) if (scanf("%u", &s0[i * 32]) != 1) return 1;
+    for (int i = 0; i < nsel; ++i) if (scanf("%u", &s1[i * 32]) != 1) return 1;
+    for (int i = 0; i < nw * 32; ++i) o[i * 32] = 0xDEADBEEFu;
+    for (uint32_t w = 0; w < 4; ++w) pbn::pbn_update_part(w, x, o, s0, s1);
+    for (int i = 0; i < nw * 32; ++i) printf("%u ", o[i * 32]);
+    printf("\n");
+  }
+  return 0;
+}
+"""
+
+
+@pytest.mark.parametrize("name", NETS)
+def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
+    """Compile the generated net_update.inc with g++ and evaluate it on random bit-planes."""
+    _lib()
+    from pbn_rl_b200.vec_env import jit_source
+    net = product_net(name)
+    src = jit_source(net)
+    upd = src.split("// ---- net_update.inc\n")[1]
+    (tmp_path / "net_update.inc").write_text(upd)
+    (tmp_path / "h.cpp").write_text(HOST_HARNESS)
+    exe = tmp_path / "h"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(exe), str(tmp_path / "h.cpp")], check=True)
+    n = net.n_genes
+    slots = [i for i, fs in enumerate(net.functions) if len(fs) > 1]
+    rng = np.random.default_rng(1)
+    cases = 6
+    lines = ["%d %d %d" % (n, len(slots), cases)]
+    data = []
+    for _ in range(cases):
+        x = rng.integers(0, 2**32, size=n, dtype=np.uint64)
+        sel = np.stack([rng.integers(0, len(net.functions[i]), size=32) for i in slots], axis=0) if slots else np.zeros((0, 32), int)
+        s0 = [(int(sum(int(v & 1) << b for b, v in enumerate(row)))) for row in sel]
+        s1 = [(int(sum(int((v >> 1) & 1) << b for b, v in enumerate(row)))) for row in sel]
+        lines.append(" ".join(str(int(v)) for v in x) + " " + " ".join(map(str, s0)) + " " + " ".join(map(str, s1)))
+        data.append((x, sel))
+    out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+    rows = [[int(v) for v in line.split()] for line in out.strip().splitlines()]
+    for (x, sel), got in zip(data, rows):
+        for b in range(32):
+            state = sum(((int(x[i]) >> b) & 1) << i for i in range(n))
+            choice = [0] * n
+            for k, i in enumerate(slots):
+                choice[i] = int(sel[k][b])
+            want = net.next_state_int(state, choice)
+            have = sum(((got[i] >> b) & 1) << i for i in range(n))
+            assert have == want
+        for i in range(n, len(got)):
+            assert got[i] == 0  # unused planes are cleared
