@@ -316,6 +316,15 @@ def run_gpu(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+    # DRAM traffic of the step kernel per launch, from the committed ncu capture of this command
+    traffic = None
+    tfile = ROOT / "profiles" / "traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get(args.net, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
     # end-to-end through the public API with host buffers (rank-local, every rank does it)
     import numpy as np
     e2e_env = envs[0]
@@ -326,11 +335,14 @@ def run_gpu(args):
         dist.barrier()
     torch.cuda.synchronize()
     n_e2e = args.e2e_steps
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ee0.record()
     for i in range(n_e2e):
         out = e2e_env.step_host(host_actions[i % 4])
+    ee1.record()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max(time.perf_counter() - t0, ee0.elapsed_time(ee1) * 1e-3)
     t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -355,7 +367,7 @@ def run_gpu(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": workload_config(args, world, kernel),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_env_step": bytes_per,
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": bytes_per,
                          "kernel_us": ms_per_step * 1e3},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
