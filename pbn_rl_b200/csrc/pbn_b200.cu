@@ -100,6 +100,8 @@ static int load_sliced(pbn_handle* h, int injected) {
 }
 
 static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W, int warps, int scratch_words) {
+  const uint32_t stage_state_bytes = 1024u * 8u * (uint32_t)W;
+  const uint32_t stage_act_bytes = (1024u * (uint32_t)n.bins + 127u) & ~127u;
   SlicedSmemLayout L{};
   uint32_t o = 0;
   L.surv_off = o;
@@ -121,6 +123,13 @@ static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W, int warps,
   L.scratch_off = o;
   (void)warps;
   o += (uint32_t)scratch_words * 4u;  // one scratch per CTA (= per tile)
+  o = (o + 127u) & ~127u;
+  L.stage_state_off = o;
+  o += stage_state_bytes;
+  L.stage_act_off = o;
+  o += stage_act_bytes;
+  L.mbar_off = o;
+  o += 16u;
   L.total = o;
   return L;
 }
@@ -130,9 +139,9 @@ static bool aligned_to(const void* p, size_t a) { return p == nullptr || (reinte
 static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream_t stream) {
   const pbn_step_args& a = p.a;
   if (!aligned_to(a.state, 16) || !aligned_to(a.final_state, 16) || !aligned_to(a.target_id, 16) ||
-      !aligned_to(a.reward, 16) || !aligned_to(a.t, 8) || !aligned_to(a.actions, 4) ||
+      !aligned_to(a.reward, 16) || !aligned_to(a.t, 8) || !aligned_to(a.actions, 16) ||
       !aligned_to(a.terminated, 4) || !aligned_to(a.truncated, 4))
-    return fail(PBN_ERR_INVALID, "sliced kernel needs 16-byte aligned state/target_id/reward, 8-byte t, 4-byte actions/flags");
+    return fail(PBN_ERR_INVALID, "sliced kernel needs 16-byte aligned state/actions/target_id/reward, 8-byte t, 4-byte flags");
   int rc = load_sliced(h, injected ? 1 : 0);
   if (rc != PBN_OK) return rc;
   SlicedSmemLayout L = sliced_smem_layout(h->net, h->W, h->sliced_threads / 32, jit::scratch_words(h->gen));

@@ -72,6 +72,7 @@ __device__ __forceinline__ void bump_device_step(const pbn_step_args& a, unsigne
 // Dynamic shared-memory layout of the sliced kernel (computed by the host per launch).
 struct SlicedSmemLayout {
   uint32_t surv_off, rew_off, aoffs_off, acare_off, aval_off, scratch_off, total;
+  uint32_t stage_state_off, stage_act_off, mbar_off;  // TMA staging of a tile's state / action bytes
   uint32_t attractors_in_smem;
 };
 

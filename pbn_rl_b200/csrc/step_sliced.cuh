@@ -117,6 +117,56 @@ __device__ __forceinline__ void transpose_quarter(const uint32_t* src, uint32_t 
   }
 }
 
+// ---- TMA (1-D bulk copy) staging of a tile's state and action bytes into shared memory -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PBN_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PBN_DONE;\n"
+      "bra PBN_WAIT;\n"
+      "PBN_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Development aid: with flag bit 31 set, thread 0 of CTA 0 writes %globaltimer stamps (ns) of the phase
+// boundaries into final_state[E*W .. E*W+15], and thread 0 of every CTA its start/end stamps (+ SM id in
+// the top byte) into final_state[E*W + 16 + 2*blockIdx + {0,1}]: the caller provides the extra words.
+__device__ __forceinline__ void phase_stamp(const pbn_step_args& a, int i) {
+  if ((a.flags & 0x80000000u) && blockIdx.x == 0 && threadIdx.x == 0 && a.final_state != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.final_state[a.n_envs * kW64 + i] = t;
+  }
+}
+__device__ __forceinline__ void cta_stamp(const pbn_step_args& a, int which) {
+  if ((a.flags & 0x80000000u) && threadIdx.x == 0 && a.final_state != nullptr) {
+    unsigned long long t;
+    unsigned int smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    a.final_state[a.n_envs * kW64 + 16 + 2 * blockIdx.x + which] =
+        (t & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)smid << 56);
+  }
+}
+
 __device__ __forceinline__ uint32_t pick4(const Philox4& b, uint32_t q) {
   return q == 0 ? b.x : q == 1 ? b.y : q == 2 ? b.z : b.w;
 }
@@ -246,7 +296,8 @@ __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, co
 template <bool FULL, bool ASMEM>
 __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemLayout& L, uint32_t* scr,
                                           uint32_t* s_surv, float* s_rew, int32_t* s_aoffs, uint32_t* s_aent,
-                                          int64_t tile, uint64_t step_ctr, const bool stage) {
+                                          int64_t tile, uint64_t step_ctr, const bool stage, unsigned char* st_state,
+                                          unsigned char* st_act, uint64_t* mbar, uint32_t& tma_parity) {
   constexpr bool attr_in_smem = ASMEM;
   const pbn_step_args& a = p.a;
   const NetParams& n = p.n;
@@ -260,7 +311,17 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   uint32_t* sel1 = scr + kScrSel1 + lane;
   uint32_t* s_stat = scr + kScrStat;
 
-  // ---- A0. issue this warp's global loads (consumed after C1, which hides their latency) -----------
+  phase_stamp(a, 0);
+  // ---- A0. start the tile's input traffic (consumed after C1, which hides the latency) ---------------
+  // full tiles: one thread issues two TMA bulk copies (8 KB*W of state, 1024*BINS action bytes) into the
+  // staging buffers; they complete on the CTA's mbarrier, no registers are tied up meanwhile
+  if (FULL && threadIdx.x == 0) {
+    fence_proxy_async();  // the previous tile's generic-proxy reads of the staging buffers are done
+    const uint32_t sbytes = 1024u * 8u * kW64, abytes = 1024u * PBN_BINS;
+    mbar_expect_tx(mbar, sbytes + (a.actions != nullptr ? abytes : 0u));
+    tma_load_1d(st_state, a.state + tile * 1024 * kW64, sbytes, mbar);
+    if (a.actions != nullptr) tma_load_1d(st_act, a.actions + tile * 1024 * PBN_BINS, abytes, mbar);
+  }
   uint32_t r1[8][kNW];   // s1 rows of this warp's 8 envs (row index 8w + i, i = 4*g + c)
   uint32_t nfp = 0u;     // 4-bit flip counts of the 8 envs
   uint32_t tg[8];        // target ids (prefetched for phase F)
@@ -279,18 +340,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       tt[4 * g + c] = 0u;
     }
     if (FULL) {
-      const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(a.state + e * kW64);
-#pragma unroll
-      for (int q = 0; q < 2 * kW64; ++q) {
-        const ulonglong2 v = sp[q];
-        sraw[g][(2 * q) / kW64][(2 * q) % kW64] = v.x;
-        sraw[g][(2 * q + 1) / kW64][(2 * q + 1) % kW64] = v.y;
-      }
-      if (a.actions != nullptr) {
-        const uint32_t* ap = reinterpret_cast<const uint32_t*>(a.actions + e * PBN_BINS);
-#pragma unroll
-        for (int k = 0; k < PBN_BINS; ++k) awraw[g][k] = ap[k];
-      }
+      // state + actions of the tile arrive through the TMA staging buffers (see below)
       if (a.target_id != nullptr) {
         const uint4 v = *reinterpret_cast<const uint4*>(a.target_id + e);
         tg[4 * g] = v.x; tg[4 * g + 1] = v.y; tg[4 * g + 2] = v.z; tg[4 * g + 3] = v.w;
@@ -318,13 +368,39 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     }
   }
 
-  if (stage) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);
+  phase_stamp(a, 1);
+  const bool c1_first = (tile & 1) == 0;
+  if (stage && !c1_first) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);
+  phase_stamp(a, 2);
   const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
   // ---- C1 (even tiles: here, hiding the load latency; odd tiles: after B, so that neighbouring
   //      CTAs of the single wave are in different phases and share the SM's issue slots better)
-  const bool c1_first = (tile & 1) == 0;
-  if (c1_first) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
+  if (c1_first) {
+    draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
+    if (stage) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);  // first read after barrier (1)
+  }
 
+  phase_stamp(a, 3);
+  if (FULL) {
+    mbar_wait(mbar, tma_parity);
+    tma_parity ^= 1u;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int le = 4 * (int)lane + 128 * (2 * (int)w + g);  // env index inside the tile
+      const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(st_state + (size_t)le * 8 * kW64);
+#pragma unroll
+      for (int q = 0; q < 2 * kW64; ++q) {
+        const ulonglong2 v = sp[q];
+        sraw[g][(2 * q) / kW64][(2 * q) % kW64] = v.x;
+        sraw[g][(2 * q + 1) / kW64][(2 * q + 1) % kW64] = v.y;
+      }
+      if (a.actions != nullptr) {
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(st_act + (size_t)le * PBN_BINS);
+#pragma unroll
+        for (int k = 0; k < PBN_BINS; ++k) awraw[g][k] = ap[k];
+      }
+    }
+  }
   // ---- A1. apply the interventions, publish the s1 rows -----------------------------------------------
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
@@ -356,7 +432,9 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       }
     }
   }
+  phase_stamp(a, 4);
   __syncthreads();  // (1) all 32 s1 rows of the column are in scratch
+  phase_stamp(a, 5);
 
   // ---- B. rows -> bit-planes: this warp produces planes 8w..8w+7 of every word ------------------
 #pragma unroll
@@ -367,12 +445,15 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     for (int i = 0; i < 8; ++i) pl[(wd * 32 + 8 * (int)w + i) * 32] = q8[i];
   }
 
+  phase_stamp(a, 6);
   if (!c1_first) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
   __syncthreads();  // (2) all input planes (and selection planes) are in scratch; S1 rows are dead
 
   // ---- C2. synchronous update of this warp's genes: generated LOP3 trees -> OPL planes ----------
   pbn_update_part(w, pl, rows, sel0, sel1);
+  phase_stamp(a, 7);
   __syncthreads();  // (3) all out planes are in scratch
+  phase_stamp(a, 8);
 
   // ---- E. bit-planes -> this warp's 8 next-state rows --------------------------------------------
   uint32_t o[8][kNW];
@@ -384,6 +465,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     for (int i = 0; i < 8; ++i) o[i][wd] = q8[i];
   }
 
+  phase_stamp(a, 9);
   // ---- D. perturbation (row domain, sparse) ---------------------------------------------------------
   uint32_t npert = 0u;
   const int pert_mode = n.pert_mode;  // block-uniform
@@ -449,6 +531,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
 #endif
   }
 
+  phase_stamp(a, 10);
   // ---- F. target test, counters, reward, stores ------------------------------------------------------
   uint32_t H = 0u, TR = 0u, VALID = 0u, len_sum = 0u;
   const uint32_t n_attr = (a.target_id != nullptr) ? (uint32_t)n.n_attr : 0u;
@@ -547,6 +630,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     }
   }
 
+  phase_stamp(a, 11);
   // ---- G. auto-reset of finished envs (sparse: scattered writes after the vector stores) ----------
   uint32_t D = (H | TR) & VALID;
   if (a.stats != nullptr) {
@@ -596,26 +680,37 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
   uint32_t* s_aent = reinterpret_cast<uint32_t*>(smem_raw + L.acare_off);  // [entry][care words | value words]
   int32_t* s_aoffs = reinterpret_cast<int32_t*>(smem_raw + L.aoffs_off);
   uint32_t* scr = reinterpret_cast<uint32_t*>(smem_raw + L.scratch_off);
+  unsigned char* st_state = smem_raw + L.stage_state_off;
+  unsigned char* st_act = smem_raw + L.stage_act_off;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.mbar_off);
+  if (threadIdx.x == 0) mbar_init(mbar, 1u);
+  __syncthreads();  // the mbarrier is initialised before anyone polls it
+  uint32_t tma_parity = 0u;
 
+  cta_stamp(a, 0);
   const uint64_t step_ctr = effective_step(a);
   const int64_t n_tiles = (a.n_envs + 1023) >> 10;
   bool stage = true;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const bool full = (tile + 1) * 1024 <= a.n_envs;
     if (L.attractors_in_smem != 0u) {
-      if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage);
-      else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage);
+      if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity);
+      else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity);
     } else {
-      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage);
+      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity);
     }
     stage = false;
+    phase_stamp(a, 12);
     __syncthreads();  // scratch is reused by the next tile; statistics are complete
   }
   if (a.stats != nullptr && threadIdx.x < 7) {
     const uint32_t x = scr[kScrStat + threadIdx.x];
     if (x != 0u) atomicAdd(&a.stats[threadIdx.x], (unsigned long long)x);
   }
+  phase_stamp(a, 13);
+  cta_stamp(a, 1);
   bump_device_step(a, p.ticket);
+  phase_stamp(a, 14);
 }
 
 }  // namespace pbn
