@@ -10,7 +10,9 @@ agent's gene flips, draw predictor selections + perturbations from Philox, synch
 Boolean update, target-attractor test, reward/done, auto-reset.  Prints ONE JSON line.
 
 Timing: steps are captured into a CUDA graph (the launch-bound inner loop; the Philox step
-counter lives in device memory so every replay advances the streams) and replayed; the timed
+counter lives in device memory so every replay advances the streams) and replayed; the launches use
+programmatic dependent launch, so a step draws its state-independent predictor-selection planes
+while the previous kernel drains and only then waits for it; the timed
 region is bracketed by barrier + torch.cuda.synchronize() and CUDA events on the launching
 stream; max over ranks.  The L2 (126 MB) is defeated by rotating over R independent env
 batches whose combined working set exceeds it, plus a pool of distinct action buffers.
@@ -218,7 +220,9 @@ def workload_config(args, world, kernel):
         "horizon": 20, "perturb_p": 0.001, "perturb_mode": "A", "auto_reset": True,
         "actions": "uniform in [0,N], pre-generated on device, pool of %d buffers" % args.action_pool,
         "l2": "%d rotating env batches + action pool: working set > 126 MB L2, no flush" % args.batches,
-        "graph_steps": args.graph_steps, "kernel": kernel, "parallelism": "env-sharded x%d" % world,
+        "graph_steps": args.graph_steps, "kernel": kernel,
+        "launch": "CUDA graph of %d step launches%s" % (args.graph_steps, "" if getattr(args, "no_pdl", False) else
+                                                        ", programmatic dependent launch (selection planes drawn under the previous kernel's tail)"), "parallelism": "env-sharded x%d" % world,
     }
 
 
@@ -226,7 +230,7 @@ def make_env(net, attrs, args, device, env_offset, device_counter=True):
     import torch
     from pbn_rl_b200 import VecPBNEnv
     env = VecPBNEnv(net, args.envs, attrs, device=device, env_offset=env_offset, auto_reset=True,
-                    device_counter=device_counter, kernel=args.kernel, **ENV_KW)
+                    device_counter=device_counter, pdl=not args.no_pdl, kernel=args.kernel, **ENV_KW)
     g = torch.Generator(device=device).manual_seed(env_offset + 1)
     n = net.n_genes
     for w in range(net.n_words):
@@ -273,11 +277,15 @@ def run_gpu(args):
     with torch.cuda.stream(stream):
         for i in range(Wm):
             enqueue(i)
+        for e in envs:
+            e.advance_counter()
         stream.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
             for i in range(G):
                 enqueue(i)
+            for e in envs:
+                e.advance_counter()   # PDL launches do not bump the device step counter themselves
         graph.replay()
         stream.synchronize()
         launches0 = sum(e.launches for e in envs)
@@ -396,6 +404,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="plain stream-serialised launches instead of programmatic dependent launch")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps_ref = args.steps if args.steps is not None else 20

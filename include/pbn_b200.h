@@ -88,7 +88,15 @@ typedef enum {
 enum { PBN_PERT_NONE = 0, PBN_PERT_A = 1, PBN_PERT_B = 2, PBN_PERT_C = 3 };
 enum { PBN_KERNEL_AUTO = 0, PBN_KERNEL_SCALAR = 1, PBN_KERNEL_SLICED = 2 };
 enum { PBN_RNG_SELECT = 0, PBN_RNG_PERTURB = 1, PBN_RNG_RESET = 2 };
-enum { PBN_STEP_AUTORESET = 1u };
+enum {
+  PBN_STEP_AUTORESET = 1u,
+  /* Programmatic dependent launch: the step is launched with programmatic stream serialisation, draws
+   * its (state-independent) predictor-selection planes while the previous kernel in the stream is
+   * still draining, and only then waits for it (griddepcontrol.wait).  With this flag the launch
+   * does NOT increment *step_ctr_dev: pass the position inside the captured sequence as step_ctr
+   * and call pbn_advance_counter once at the end of the sequence. */
+  PBN_STEP_PDL = 2u
+};
 enum { PBN_UNPACK_U8 = 0, PBN_UNPACK_F32 = 1 };
 
 /* episode statistics accumulated by pbn_step when args->stats != NULL (u64 counters) */
@@ -193,6 +201,9 @@ int pbn_pack(pbn_handle* h, const uint8_t* bits, uint64_t* state, int64_t n_envs
  * state, -1 if none (graph_classifier/__init__.py:129-134; bdq_model/__init__.py:180). */
 int pbn_attractor_id(pbn_handle* h, const uint64_t* state, int32_t* attr_id, int64_t n_envs,
                      void* stream);
+
+/* *step_ctr_dev += n on the stream (fully serialised): closes a sequence of PBN_STEP_PDL launches. */
+int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void* stream);
 
 /* Introspection. */
 int pbn_kernel_kind(const pbn_handle* h);            /* PBN_KERNEL_SCALAR or PBN_KERNEL_SLICED */

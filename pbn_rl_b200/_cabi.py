@@ -18,6 +18,7 @@ PBN_OK = 0
 PERT_MODES = {"none": 0, "A": 1, "B": 2, "C": 3}
 KERNEL_KINDS = {"auto": 0, "scalar": 1, "sliced": 2}
 STEP_AUTORESET = 1
+STEP_PDL = 2
 UNPACK_U8, UNPACK_F32 = 0, 1
 N_STATS = 8
 STAT_NAMES = ("steps", "episodes", "terminated", "truncated", "ep_len_sum", "flips", "perturbed", "reserved")
@@ -27,6 +28,7 @@ EXPORTS = (
     "pbn_create", "pbn_destroy", "pbn_update_attractors", "pbn_step", "pbn_step_injected", "pbn_reset",
     "pbn_unpack", "pbn_pack", "pbn_attractor_id", "pbn_kernel_kind", "pbn_words_per_state",
     "pbn_launch_count", "pbn_last_error", "pbn_version", "pbn_jit_source", "pbn_jit_precompile",
+    "pbn_advance_counter",
 )
 
 
@@ -126,6 +128,8 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_jit_source.restype = i64
     lib.pbn_jit_precompile.argtypes = [C.POINTER(NetDesc)]
     lib.pbn_jit_precompile.restype = C.c_int
+    lib.pbn_advance_counter.argtypes = [vp, vp, u64, vp]
+    lib.pbn_advance_counter.restype = C.c_int
     lib.pbn_last_error.argtypes = []
     lib.pbn_last_error.restype = C.c_char_p
     lib.pbn_version.argtypes = []

@@ -156,7 +156,21 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
   const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 8;
   if (grid > cap) grid = cap;
   void* args[] = {&p, &L};
-  PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, L.total, stream));
+  if (a.flags & PBN_STEP_PDL) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)h->sliced_threads);
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PBN_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(k), args));
+  } else {
+    PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, L.total, stream));
+  }
   return PBN_OK;
 }
 
@@ -384,6 +398,7 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   if (!injected && (a->sel || a->pert_mask)) return fail(PBN_ERR_INVALID, "pbn_step: sel/pert_mask must be null (use pbn_step_injected)");
   if (a->env_offset < 0 || (a->env_offset & 1023)) return fail(PBN_ERR_INVALID, "env_offset=%lld must be a non-negative multiple of 1024", (long long)a->env_offset);
   if (a->target_id && h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "target_id given but no attractor table uploaded");
+  if ((a->flags & PBN_STEP_PDL) && !a->step_ctr_dev) return fail(PBN_ERR_INVALID, "PBN_STEP_PDL needs step_ctr_dev");
   if (a->flags & PBN_STEP_AUTORESET) {
     if (h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "auto-reset needs pbn_update_attractors first");
     if (!a->target_id || !a->t) return fail(PBN_ERR_INVALID, "auto-reset needs target_id and t");
@@ -484,6 +499,16 @@ int pbn_unpack(pbn_handle* h, const uint64_t* state, void* out, int32_t out_kind
     unpack_kernel<float><<<grid, 256, 0, stream>>>(state, static_cast<float*>(out), h->net.n_genes, h->W, n_envs);
   else
     return fail(PBN_ERR_INVALID, "out_kind=%d unknown", out_kind);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void* stream_) {
+  if (!h || !step_ctr_dev) return fail(PBN_ERR_INVALID, "bad arguments");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  advance_counter_kernel<<<1, 1, 0, stream>>>(step_ctr_dev, n);
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
   return PBN_OK;

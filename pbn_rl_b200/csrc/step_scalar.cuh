@@ -276,6 +276,8 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ NetP
   }
 }
 
+__global__ void advance_counter_kernel(uint64_t* ctr, uint64_t n) { *ctr += n; }
+
 // [E*W] packed -> [E,N] uint8 / float32.  One thread per output element: writes are coalesced,
 // the packed word is broadcast from L1 to the N threads that share it.
 template <typename OutT>

@@ -297,7 +297,8 @@ template <bool FULL, bool ASMEM>
 __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemLayout& L, uint32_t* scr,
                                           uint32_t* s_surv, float* s_rew, int32_t* s_aoffs, uint32_t* s_aent,
                                           int64_t tile, uint64_t step_ctr, const bool stage, unsigned char* st_state,
-                                          unsigned char* st_act, uint64_t* mbar, uint32_t& tma_parity) {
+                                          unsigned char* st_act, uint64_t* mbar, uint32_t& tma_parity,
+                                          const bool pre_drawn) {
   constexpr bool attr_in_smem = ASMEM;
   const pbn_step_args& a = p.a;
   const NetParams& n = p.n;
@@ -369,7 +370,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 1);
-  const bool c1_first = (tile & 1) == 0;
+  const bool c1_first = !pre_drawn && (tile & 1) == 0;  // pre_drawn: done before griddepcontrol.wait
   if (stage && !c1_first) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);
   phase_stamp(a, 2);
   const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
@@ -446,7 +447,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 6);
-  if (!c1_first) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
+  if (!c1_first && !pre_drawn) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
   __syncthreads();  // (2) all input planes (and selection planes) are in scratch; S1 rows are dead
 
   // ---- C2. synchronous update of this warp's genes: generated LOP3 trees -> OPL planes ----------
@@ -691,15 +692,32 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
   const uint64_t step_ctr = effective_step(a);
   const int64_t n_tiles = (a.n_envs + 1023) >> 10;
   bool stage = true;
+  bool pre_drawn = false;
+  if (a.flags & PBN_STEP_PDL) {
+    // Programmatic dependent launch: let the next launch start as SM resources free up, draw this CTA's
+    // first tile's selection planes (they depend on nothing the previous launch writes; the device step
+    // counter is not bumped by PDL launches), then wait for the previous launch to complete and flush.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if ((int64_t)blockIdx.x < n_tiles) {
+      const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+      const int64_t tile = blockIdx.x;
+      const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
+      draw_selection_planes<false>(a, n, scr + kScrSel0 + lane, scr + kScrSel1 + lane, gid, step_ctr,
+                                   tile * 1024 + 4 * (int64_t)lane, w);
+      pre_drawn = true;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const bool full = (tile + 1) * 1024 <= a.n_envs;
     if (L.attractors_in_smem != 0u) {
-      if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity);
-      else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity);
+      if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn);
+      else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn);
     } else {
-      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity);
+      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn);
     }
     stage = false;
+    pre_drawn = false;
     phase_stamp(a, 12);
     __syncthreads();  // scratch is reused by the next tile; statistics are complete
   }

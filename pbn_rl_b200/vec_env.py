@@ -105,7 +105,10 @@ class VecPBNEnv:
     on several GPUs draw exactly the randomness the single-GPU batch would.
     ``device_counter=True`` keeps the Philox step counter in device memory (incremented by each
     step launch), so steps captured in a CUDA graph keep advancing their random streams on
-    every replay.
+    every replay.  ``pdl=True`` (implies ``device_counter``) launches the steps with programmatic
+    dependent launch: each step draws its state-independent selection planes under the tail of the
+    previous kernel; the device counter is then advanced explicitly with :meth:`advance_counter`
+    at the end of a captured sequence instead of by every launch.
     """
 
     def __init__(self, network: PBNNetwork, num_envs: int, attractors: Optional[AttractorSet] = None,
@@ -113,7 +116,7 @@ class VecPBNEnv:
                  bins: int = 3, perturb_p: float = 0.0, perturb_mode: str = "A", r_success: float = 5.0,
                  r_step: float = 0.0, r_action: float = -1.0, kernel: str = "auto", env_offset: int = 0,
                  auto_reset: bool = False, pair_weights: Optional[np.ndarray] = None,
-                 device_counter: bool = False):
+                 device_counter: bool = False, pdl: bool = False):
         self._h = None
         self.lib = _cabi.lib()  # raises if the CUDA extension is not built: no fallback
         if not torch.cuda.is_available():
@@ -154,7 +157,9 @@ class VecPBNEnv:
         self.terminated = torch.zeros((e,), dtype=torch.uint8, device=dev)
         self.truncated = torch.zeros((e,), dtype=torch.uint8, device=dev)
         self.stats_buf = torch.zeros((_cabi.N_STATS,), dtype=torch.int64, device=dev)
-        self.step_ctr_dev = torch.zeros((1,), dtype=torch.int64, device=dev) if device_counter else None
+        self.pdl = bool(pdl)
+        self.step_ctr_dev = torch.zeros((1,), dtype=torch.int64, device=dev) if (device_counter or pdl) else None
+        self._pos = 0  # position inside a PDL sequence (host part of the step counter)
         self._reset_ctr = 0
         self.attractors: Optional[AttractorSet] = None
         self._host = None
@@ -237,7 +242,9 @@ class VecPBNEnv:
         a.step_ctr = self.step_ctr
         a.env_offset = self.env_offset
         a.n_envs = self.num_envs
-        a.flags = _cabi.STEP_AUTORESET if self.auto_reset else 0
+        a.flags = (_cabi.STEP_AUTORESET if self.auto_reset else 0) | (_cabi.STEP_PDL if self.pdl else 0)
+        if self.pdl:
+            a.step_ctr = self._pos
         return a
 
     def _check_actions(self, actions: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -260,6 +267,8 @@ class VecPBNEnv:
         check(self.lib.pbn_step(self._h, C.byref(a), self._stream()))
         if self.step_ctr_dev is None:
             self.step_ctr += 1
+        elif self.pdl:
+            self._pos += 1
         return self.state, self.reward, self.terminated, self.truncated
 
     def step_injected(self, actions: Optional[torch.Tensor], sel: torch.Tensor,
@@ -283,6 +292,15 @@ class VecPBNEnv:
         if self.step_ctr_dev is None:
             self.step_ctr += 1
         return self.state, self.reward, self.terminated, self.truncated
+
+    def advance_counter(self) -> None:
+        """Close a sequence of ``pdl`` steps: add the number of steps taken since the last call to the
+        device step counter (one tiny serialised launch) and restart the host-side positions.  When the
+        sequence is captured in a CUDA graph, capture this call as its last node."""
+        if not self.pdl:
+            return
+        check(self.lib.pbn_advance_counter(self._h, _ptr(self.step_ctr_dev), self._pos, self._stream()))
+        self._pos = 0
 
     # ------------------------------------------------------------------ host-buffer path (end-to-end API)
     def step_host(self, actions_host: np.ndarray) -> Dict[str, np.ndarray]:

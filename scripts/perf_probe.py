@@ -13,14 +13,14 @@ import bench  # noqa: E402
 from pbn_rl_b200 import VecPBNEnv  # noqa: E402
 
 
-def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20):
+def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20, pdl=False):
     dev = torch.device("cuda:0")
     es = []
     for b in range(batches):
         kw = dict(bench.ENV_KW)
         kw["perturb_p"] = p
         e = VecPBNEnv(net, envs, attrs, device=dev, env_offset=b * envs, auto_reset=auto_reset, device_counter=True,
-                      kernel=kernel, **kw)
+                      kernel=kernel, pdl=pdl, **kw)
         g = torch.Generator(device=dev).manual_seed(b)
         e.state[:, 0] = torch.randint(0, 1 << min(net.n_genes, 62), (envs,), generator=g, device=dev)
         e.set_target(torch.randint(0, len(attrs), (envs,), generator=g, device=dev, dtype=torch.int32))
@@ -31,11 +31,15 @@ def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches
     with torch.cuda.stream(s):
         for i in range(4):
             es[i % batches].step(pool[i % 8] if actions else None, stats=stats)
+        for e in es:
+            e.advance_counter()
         s.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=s):
             for i in range(graph_steps):
                 es[i % batches].step(pool[i % 8] if actions else None, stats=stats)
+            for e in es:
+                e.advance_counter()
         gr.replay()
         s.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -56,6 +60,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--kernels", default="sliced")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--pdl", action="store_true")
     args = ap.parse_args()
     net, attrs = bench.load_workload(args.net)
     W = net.n_words
@@ -69,7 +74,7 @@ def main():
         rows = rows[:1]
     for kernel in args.kernels.split(","):
         for label, p, ar, st, act in rows:
-            us = time_config(net, attrs, args.envs, kernel, p, ar, st, act)
+            us = time_config(net, attrs, args.envs, kernel, p, ar, st, act, pdl=args.pdl)
             gbs = bench.BYTES_PER_STEP[W] * args.envs / us / 1e3
             print("%-8s %-30s %9.2f us/step  %8.3e steps/s  %7.1f GB/s" % (kernel, label, us, args.envs / us * 1e6, gbs), flush=True)
 

@@ -235,3 +235,48 @@ def test_cuda_graph_replay_advances_the_streams():
     b.step(acts)
     assert torch.equal(a.state, b.state)
     assert int(a.step_ctr_dev.item()) == 2
+
+
+def test_pdl_graph_sequence_matches_eager_steps():
+    """pdl=True: steps launched with programmatic stream serialisation (selection planes drawn before
+    griddepcontrol.wait) inside a CUDA graph give exactly the states of plain eager steps."""
+    import torch
+    from pbn_rl_b200 import VecPBNEnv
+    net, attrs = product_net("pbn28"), attractor_set("pbn28")
+    e, steps = 8192, 5
+    a = VecPBNEnv(net, e, attrs, device="cuda:0", perturb_p=0.01, pdl=True, auto_reset=True)
+    b = VecPBNEnv(net, e, attrs, device="cuda:0", perturb_p=0.01, auto_reset=True)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    s0 = torch.randint(0, 1 << 28, (e, 1), generator=g, device="cuda", dtype=torch.int64)
+    acts = [torch.randint(0, 29, (e, 3), generator=g, device="cuda", dtype=torch.uint8) for _ in range(steps)]
+    tgt = torch.randint(0, 14, (e,), generator=g, device="cuda", dtype=torch.int32)
+    for env in (a, b):
+        env.state.copy_(s0)
+        env.set_target(tgt)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        a.step(acts[0])                      # warm-up (loads the module before capture)
+        a.advance_counter()
+        stream.synchronize()
+        a.state.copy_(s0)
+        a.set_target(tgt)
+        a.t.zero_()
+        a.step_ctr_dev.zero_()
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for k in range(steps):
+                a.step(acts[k])
+            a.advance_counter()
+        a.state.copy_(s0)
+        a.set_target(tgt)
+        a.t.zero_()
+        a.step_ctr_dev.zero_()
+        graph.replay()
+        graph.replay()
+        stream.synchronize()
+    for rep in range(2):
+        for k in range(steps):
+            b.step(acts[k])
+    assert torch.equal(a.state, b.state) and torch.equal(a.target_id, b.target_id) and torch.equal(a.t, b.t)
+    assert int(a.step_ctr_dev.item()) == 2 * steps
