@@ -105,7 +105,7 @@ static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W, int warps,
   SlicedSmemLayout L{};
   uint32_t o = 0;
   L.surv_off = o;
-  o += (uint32_t)(8 * n.n_genes + 1) * 4u;
+  o += 16u;  // (the survival table stays in global memory)
   o = (o + 15u) & ~15u;
   L.rew_off = o;
   o += 80u;

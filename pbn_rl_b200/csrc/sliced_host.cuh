@@ -160,7 +160,7 @@ inline int scratch_words(const GenNet& g) {
 inline int sliced_threads(const GenNet&) { return 128; }  // four warps per 1024-env tile
 inline int sliced_min_blocks(const GenNet& g) {
   if (const char* env = getenv("PBN_B200_MIN_BLOCKS")) return atoi(env);  // tuning experiments
-  return g.n_genes <= 32 ? 7 : (g.n_genes <= 64 ? 4 : 2);
+  return g.n_genes <= 32 ? 8 : (g.n_genes <= 64 ? 4 : 2);
 }
 
 // net_gen.cuh: the constants; net_update.inc: selection tables + pbn_update_part() -- see step_sliced.cuh

@@ -59,7 +59,7 @@ constexpr uint32_t kLastMask = (PBN_N % 32) ? ((1u << (PBN_N % 32)) - 1u) : 0xFF
 constexpr int kWarps = 4;                     // warps per tile (PBN_THREADS == 128)
 
 // per-CTA scratch, in 32-bit words; every array is [row][lane]
-constexpr int kScrRows = 0;                          // S1 rows, later OPL out planes [kNW*32][32]
+constexpr int kScrRows = 0;                          // s1 rows                      [kNW*32][32]
 constexpr int kScrPl = kScrRows + kNW * 32 * 32;     // PL input planes              [kNW*32][32]
 constexpr int kScrSel0 = kScrPl + kNW * 32 * 32;     // selection planes s0          [PBN_NSEL][32]
 constexpr int kScrSel1 = kScrSel0 + PBN_NSEL * 32;   // selection planes s1          [PBN_NSEL][32]
@@ -219,8 +219,14 @@ __device__ __forceinline__ void sel_slot(uint64_t gid, uint64_t step, const uint
 }
 
 // Next event distance of the perturbation stream.
-__device__ __noinline__ int pert_search(const uint32_t* s_surv, uint32_t u) {
-  return count_below_survival(s_surv, kSlots, u) + 1;
+// (cold path; the table stays in global memory / L1: it is touched by a few lanes per tile only)
+__device__ __noinline__ int pert_search(const uint32_t* __restrict__ surv, uint32_t u) {
+  int lo = 0, hi = kSlots;  // invariant: u < surv[lo] (surv[0] = 2^32 conceptually)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (u < __ldg(surv + mid)) lo = mid; else hi = mid - 1;
+  }
+  return lo + 1;
 }
 
 }  // namespace pbn
@@ -233,8 +239,7 @@ namespace pbn {
 // were issued; everything staged here is first read after block barrier (1)).
 __device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSmemLayout& L, uint32_t* s_surv,
                                              float* s_rew, int32_t* s_aoffs, uint32_t* s_aent, uint32_t* s_stat) {
-  if (n.pert_rng)
-    for (int i = threadIdx.x; i <= kSlots; i += blockDim.x) s_surv[i] = n.surv_sliced[i];
+  (void)s_surv;  // the survival table is read through the read-only path where needed
   if (threadIdx.x < 18) {
     const uint32_t nf = threadIdx.x % 9u;
     const bool hit = threadIdx.x >= 9;
@@ -306,7 +311,8 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   const uint32_t w = threadIdx.x >> 5;  // warp in tile: owns groups 2w, 2w+1 = rows 8w..8w+7
   const int64_t E = a.n_envs;
   const int64_t e0 = tile * 1024 + 4 * (int64_t)lane;  // local env index of (j = 0, c = 0)
-  uint32_t* rows = scr + kScrRows + lane;   // S1 rows in phases A/B, OPL planes in C2/E
+  uint32_t* rows = scr + kScrRows + lane;   // s1 rows (kept for the perturbation phase)
+  uint32_t* opl = reinterpret_cast<uint32_t*>(st_state) + lane;  // out planes: the TMA staging buffer is dead after A1
   uint32_t* pl = scr + kScrPl + lane;
   uint32_t* sel0 = scr + kScrSel0 + lane;
   uint32_t* sel1 = scr + kScrSel1 + lane;
@@ -323,10 +329,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     tma_load_1d(st_state, a.state + tile * 1024 * kW64, sbytes, mbar);
     if (a.actions != nullptr) tma_load_1d(st_act, a.actions + tile * 1024 * PBN_BINS, abytes, mbar);
   }
-  uint32_t r1[8][kNW];   // s1 rows of this warp's 8 envs (row index 8w + i, i = 4*g + c)
   uint32_t nfp = 0u;     // 4-bit flip counts of the 8 envs
-  uint32_t tg[8];        // target ids (prefetched for phase F)
-  uint32_t tt[8];        // episode step counters
   uint32_t flips = 0u;
   uint64_t sraw[2][4][kW64];
   uint32_t awraw[2][PBN_BINS];
@@ -335,28 +338,13 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     const int64_t e = e0 + 128 * (2 * (int)w + g);
 #pragma unroll
     for (int k = 0; k < PBN_BINS; ++k) awraw[g][k] = 0u;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      tg[4 * g + c] = 0xFFFFFFFFu;
-      tt[4 * g + c] = 0u;
-    }
     if (FULL) {
-      // state + actions of the tile arrive through the TMA staging buffers (see below)
-      if (a.target_id != nullptr) {
-        const uint4 v = *reinterpret_cast<const uint4*>(a.target_id + e);
-        tg[4 * g] = v.x; tg[4 * g + 1] = v.y; tg[4 * g + 2] = v.z; tg[4 * g + 3] = v.w;
-      }
-      if (a.t != nullptr) {
-        const uint2 v = *reinterpret_cast<const uint2*>(a.t + e);
-        tt[4 * g] = v.x & 0xFFFFu; tt[4 * g + 1] = v.x >> 16; tt[4 * g + 2] = v.y & 0xFFFFu; tt[4 * g + 3] = v.y >> 16;
-      }
+      // state + actions of the tile arrive through the TMA staging buffers (see above)
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int wd = 0; wd < kW64; ++wd) sraw[g][c][wd] = (e + c < E) ? a.state[(e + c) * kW64 + wd] : 0ull;
-        if (a.target_id != nullptr && e + c < E) tg[4 * g + c] = (uint32_t)a.target_id[e + c];
-        if (a.t != nullptr && e + c < E) tt[4 * g + c] = a.t[e + c];
       }
       if (a.actions != nullptr) {
 #pragma unroll
@@ -428,8 +416,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
 #pragma unroll
       for (int wd = 0; wd < kNW; ++wd) {
         const uint32_t sw = (uint32_t)(sraw[g][c][wd >> 1] >> (32 * (wd & 1)));
-        r1[i][wd] = sw ^ fl[wd];
-        rows[(wd * 32 + 8 * (int)w + i) * 32] = r1[i][wd];
+        rows[(wd * 32 + 8 * (int)w + i) * 32] = sw ^ fl[wd];  // row 8w + i of the column
       }
     }
   }
@@ -451,17 +438,46 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   __syncthreads();  // (2) all input planes (and selection planes) are in scratch; S1 rows are dead
 
   // ---- C2. synchronous update of this warp's genes: generated LOP3 trees -> OPL planes ----------
-  pbn_update_part(w, pl, rows, sel0, sel1);
+  pbn_update_part(w, pl, opl, sel0, sel1);
   phase_stamp(a, 7);
   __syncthreads();  // (3) all out planes are in scratch
   phase_stamp(a, 8);
+
+  // target ids and episode counters of this warp's 8 envs: issued here, consumed in F (E and D hide them)
+  uint32_t tg[8];
+  uint32_t tt[8];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int64_t e = e0 + 128 * (2 * (int)w + g);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      tg[4 * g + c] = 0xFFFFFFFFu;
+      tt[4 * g + c] = 0u;
+    }
+    if (FULL) {
+      if (a.target_id != nullptr) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a.target_id + e);
+        tg[4 * g] = v.x; tg[4 * g + 1] = v.y; tg[4 * g + 2] = v.z; tg[4 * g + 3] = v.w;
+      }
+      if (a.t != nullptr) {
+        const uint2 v = *reinterpret_cast<const uint2*>(a.t + e);
+        tt[4 * g] = v.x & 0xFFFFu; tt[4 * g + 1] = v.x >> 16; tt[4 * g + 2] = v.y & 0xFFFFu; tt[4 * g + 3] = v.y >> 16;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (a.target_id != nullptr && e + c < E) tg[4 * g + c] = (uint32_t)a.target_id[e + c];
+        if (a.t != nullptr && e + c < E) tt[4 * g + c] = a.t[e + c];
+      }
+    }
+  }
 
   // ---- E. bit-planes -> this warp's 8 next-state rows --------------------------------------------
   uint32_t o[8][kNW];
 #pragma unroll
   for (int wd = 0; wd < kNW; ++wd) {
     uint32_t q8[8];
-    transpose_quarter(rows + wd * 32 * 32, w, q8);
+    transpose_quarter(opl + wd * 32 * 32, w, q8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i][wd] = q8[i];
   }
@@ -487,16 +503,17 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
         }
 #pragma unroll
         for (int wd = 0; wd < kNW; ++wd) {
-          if (pert_mode == PBN_PERT_A) o[i][wd] = any ? (r1[i][wd] ^ pm[wd]) : o[i][wd];
+          const uint32_t s1w = rows[(wd * 32 + 8 * (int)w + i) * 32];
+          if (pert_mode == PBN_PERT_A) o[i][wd] = any ? (s1w ^ pm[wd]) : o[i][wd];
           else if (pert_mode == PBN_PERT_B) o[i][wd] ^= pm[wd];
-          else o[i][wd] = bmux(pm[wd], ~r1[i][wd], o[i][wd]);
+          else o[i][wd] = bmux(pm[wd], ~s1w, o[i][wd]);
         }
       }
     }
 #else
     if (n.pert_rng) {
       // this warp's own event sub-stream: slots gene*8 + row over its 8 rows
-      const uint32_t s_last = s_surv[kSlots];
+      const uint32_t s_last = __ldg(n.surv_sliced + kSlots);
       uint32_t pert_next = 0u, M = 0u;
       Philox4 pert_blk = {0u, 0u, 0u, 0u};
       int pos = -1;
@@ -505,7 +522,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
           pert_blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
         const uint32_t u = pick4(pert_blk, pert_next & 3u);
         ++pert_next;
-        pos += (u < s_last) ? kSlots + 1 : pert_search(s_surv, u);
+        pos += (u < s_last) ? kSlots + 1 : pert_search(n.surv_sliced, u);
         if (pos >= kSlots) break;
         const uint32_t g = (uint32_t)pos >> 3, ib = (uint32_t)pos & 7u;
         const uint32_t m = 1u << (g & 31u), gw = g >> 5;
@@ -519,12 +536,12 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
             const bool here = (uint32_t)i == ib;
             const uint32_t mm = (here && (uint32_t)wd == gw) ? m : 0u;
             if (pert_mode == PBN_PERT_A) {
-              if (here && first) o[i][wd] = r1[i][wd];
+              if (here && first) o[i][wd] = rows[(wd * 32 + 8 * (int)w + i) * 32];
               o[i][wd] ^= mm;
             } else if (pert_mode == PBN_PERT_B) {
               o[i][wd] ^= mm;
-            } else {
-              o[i][wd] = bmux(mm, ~r1[i][wd], o[i][wd]);
+            } else if (here) {
+              o[i][wd] = bmux(mm, ~rows[(wd * 32 + 8 * (int)w + i) * 32], o[i][wd]);
             }
           }
       }
