@@ -200,7 +200,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": K, "warmup": Wm, "ms_per_step": 1e3 * busy / max(K, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, 1, None),
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1")), None),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -336,27 +336,46 @@ def run_gpu(args):
     # end-to-end through the public API with host buffers (rank-local, every rank does it)
     import numpy as np
     e2e_env = envs[0]
-    host_actions = [p.cpu().numpy() for p in pool[:4]]
-    for i in range(3):
-        e2e_env.step_host(host_actions[i % 4])
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    host_actions = []
+    for p in pool[:4]:  # the step's inputs live in pinned host memory, as the contract asks
+        pa = e2e_env.pinned_actions()
+        pa.copy_(p)
+        host_actions.append(pa)
     n_e2e = args.e2e_steps
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    ee0.record()
-    for i in range(n_e2e):
-        out = e2e_env.step_host(host_actions[i % 4])
-    ee1.record()
-    torch.cuda.synchronize()
-    e2e_s = max(time.perf_counter() - t0, ee0.elapsed_time(ee1) * 1e-3)
-    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = args.envs * world * n_e2e / float(t_e2e.item())
-    h2d, d2h = e2e_env.host_bytes_per_step
-    assert out["reward"].shape[0] == args.envs
+
+    def time_e2e(compact):
+        for i in range(3):
+            e2e_env.step_host(host_actions[i % 4], compact=compact)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ee0.record()
+        for i in range(n_e2e):
+            out = e2e_env.step_host(host_actions[i % 4], compact=compact)
+        ee1.record()
+        torch.cuda.synchronize()
+        secs = max(time.perf_counter() - t0, ee0.elapsed_time(ee1) * 1e-3)
+        t_e2e = torch.tensor([secs], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        assert out["reward"].shape[0] == args.envs
+        return args.envs * world * n_e2e / float(t_e2e.item())
+
+    # full-width results (int64 state words, fp32 reward, terminated, truncated) and, for N <= 32, the
+    # compact form of the same results (uint32 state, fp32 reward, done byte): fewer PCIe bytes per env-step
+    e2e_full = time_e2e(False)
+    compact_ok = net.n_genes <= 32
+    e2e_value = time_e2e(True) if compact_ok else e2e_full
+    h2d, d2h = e2e_env.host_bytes_per_step_compact if compact_ok else e2e_env.host_bytes_per_step
+    e2e_note = {
+        "results": "uint32 state + fp32 reward + done byte per env (step_host(compact=True))" if compact_ok
+        else "int64 state words + fp32 reward + terminated + truncated per env",
+        "full_width_value": e2e_full, "full_width_d2h_bytes_per_step": e2e_env.host_bytes_per_step[1],
+        "transfer": "pbn_step_host: actions uploaded from pinned memory by the copy engine, results written "
+                    "by an export kernel straight into pinned host memory (zero-copy over PCIe), 2 chunks pipelined",
+    }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -378,8 +397,8 @@ def run_gpu(args):
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_env_step": bytes_per,
                          "kernel_us": ms_per_step * 1e3},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": n_e2e},
+            "e2e": dict({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "steps": n_e2e}, **e2e_note),
             "gpu_launches": K,
             "clocks": clocks,
             "episode_stats": stats,

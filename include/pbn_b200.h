@@ -95,7 +95,10 @@ enum {
    * still draining, and only then waits for it (griddepcontrol.wait).  With this flag the launch
    * does NOT increment *step_ctr_dev: pass the position inside the captured sequence as step_ctr
    * and call pbn_advance_counter once at the end of the sequence. */
-  PBN_STEP_PDL = 2u
+  PBN_STEP_PDL = 2u,
+  /* Do not increment *step_ctr_dev when the launch completes (several launches that belong to the same
+   * logical step, e.g. the chunks of pbn_step_host, share one counter value). */
+  PBN_STEP_NO_COUNT = 4u
 };
 enum { PBN_UNPACK_U8 = 0, PBN_UNPACK_F32 = 1 };
 
@@ -177,6 +180,34 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
 /* env.step(action) for every instance (bdq_model/__init__.py:177; ddqn_per/__init__.py:354),
  * randomness from the handle's Philox stream.  args->sel and args->pert_mask must be NULL. */
 int pbn_step(pbn_handle* h, const pbn_step_args* args, void* stream);
+
+/* Host buffers of pbn_step_host: what a caller of the reference's CPU env holds per step -- the
+ * action it passes to env.step (bdq_model/__init__.py:176-177) and the tuple it gets back
+ * (state, reward, terminated, truncated).  HOST pointers (page-locked memory for the copies to
+ * overlap; pageable memory works but serialises); any output may be NULL = not wanted. */
+typedef struct {
+  const uint8_t* actions;   /* HOST [E*bins] in; NULL = no interventions */
+  uint8_t* actions_dev;     /* DEVICE [E*bins] staging buffer, caller-owned (required with actions) */
+  uint64_t* state;          /* HOST [E*W] out: args->state after the step (after auto-reset, if enabled) */
+  float* reward;            /* HOST [E] out */
+  uint8_t* terminated;      /* HOST [E] out */
+  uint8_t* truncated;       /* HOST [E] out */
+  int32_t n_chunks;         /* pipeline depth; 0 = library default */
+  int32_t reserved;
+  /* Compact forms of the same results (fewer PCIe bytes per env-step); page-locked memory only. */
+  uint32_t* state32;        /* HOST [E] out: the state word narrowed to 32 bits; networks with N <= 32 only */
+  uint8_t* done;            /* HOST [E] out: terminated | truncated << 1 */
+} pbn_host_io;
+
+/* env.step(action) with HOST buffers, end to end: copies the actions to the device, steps all
+ * n_envs instances (exactly as pbn_step with args->actions = io->actions_dev) and copies the
+ * results back.  The batch is cut into n_chunks ranges of whole 1024-env tiles; the action
+ * upload of chunk c+1, the step kernel of chunk c and the result download of chunk c-1 run
+ * concurrently on two library-owned copy streams and the caller's stream (envs are independent,
+ * so the result does not depend on n_chunks).  Unlike the device entry points this call BLOCKS
+ * until the host outputs are complete (like the reference's env.step it returns values); it waits
+ * on its own streams only, never on the whole device. */
+int pbn_step_host(pbn_handle* h, const pbn_step_args* args, const pbn_host_io* io, void* stream);
 
 /* The same step with injected predictor choices / perturbation masks: the parity entry point
  * (deterministic core T of SURVEY.md 8a-4).  args->sel must be non-NULL. */

@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-__all__ = ["lib", "load_library", "PbnError", "NetDesc", "StepArgs", "check", "LIB_PATH", "EXPORTS"]
+__all__ = ["lib", "load_library", "PbnError", "NetDesc", "StepArgs", "HostIO", "check", "LIB_PATH", "EXPORTS"]
 
 LIB_PATH = Path(__file__).resolve().parent / "libpbn_b200.so"
 
@@ -19,6 +19,7 @@ PERT_MODES = {"none": 0, "A": 1, "B": 2, "C": 3}
 KERNEL_KINDS = {"auto": 0, "scalar": 1, "sliced": 2}
 STEP_AUTORESET = 1
 STEP_PDL = 2
+STEP_NO_COUNT = 4
 UNPACK_U8, UNPACK_F32 = 0, 1
 N_STATS = 8
 STAT_NAMES = ("steps", "episodes", "terminated", "truncated", "ep_len_sum", "flips", "perturbed", "reserved")
@@ -28,7 +29,7 @@ EXPORTS = (
     "pbn_create", "pbn_destroy", "pbn_update_attractors", "pbn_step", "pbn_step_injected", "pbn_reset",
     "pbn_unpack", "pbn_pack", "pbn_attractor_id", "pbn_kernel_kind", "pbn_words_per_state",
     "pbn_launch_count", "pbn_last_error", "pbn_version", "pbn_jit_source", "pbn_jit_precompile",
-    "pbn_advance_counter",
+    "pbn_advance_counter", "pbn_step_host",
 )
 
 
@@ -84,6 +85,21 @@ class StepArgs(C.Structure):
     ]
 
 
+class HostIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p),
+        ("actions_dev", C.c_void_p),
+        ("state", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("terminated", C.c_void_p),
+        ("truncated", C.c_void_p),
+        ("n_chunks", C.c_int32),
+        ("reserved", C.c_int32),
+        ("state32", C.c_void_p),
+        ("done", C.c_void_p),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -108,6 +124,8 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_update_attractors.restype = C.c_int
     lib.pbn_step.argtypes = [vp, C.POINTER(StepArgs), vp]
     lib.pbn_step.restype = C.c_int
+    lib.pbn_step_host.argtypes = [vp, C.POINTER(StepArgs), C.POINTER(HostIO), vp]
+    lib.pbn_step_host.restype = C.c_int
     lib.pbn_step_injected.argtypes = [vp, C.POINTER(StepArgs), vp]
     lib.pbn_step_injected.restype = C.c_int
     lib.pbn_reset.argtypes = [vp, vp, vp, vp, vp, vp, u64, i64, i64, vp]

@@ -84,6 +84,10 @@ struct pbn_handle {
   uint32_t jit_smem_opt_in[2] = {48u * 1024u, 48u * 1024u};
   uint64_t launches = 0;
   bool scalar_smem_opted = false;
+  // pbn_step_host: two copy streams + per-chunk events (created on first use)
+  static constexpr int kMaxChunks = 16;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_entry = nullptr, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
 };
 
 // Compile (or fetch from the cubin cache) and load one specialisation of the sliced kernel.
@@ -203,6 +207,13 @@ void pbn_destroy(pbn_handle* h) {
     cudaFree(h->d_surv_sliced);
     for (int i = 0; i < 2; ++i)
       if (h->jit_lib[i]) cudaLibraryUnload(h->jit_lib[i]);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->ev_entry) cudaEventDestroy(h->ev_entry);
+    for (int i = 0; i < pbn_handle::kMaxChunks; ++i) {
+      if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+      if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+    }
   }
   delete h;
 }
@@ -466,6 +477,123 @@ int pbn_jit_precompile(const pbn_net_desc* d) {
 }
 
 int pbn_step(pbn_handle* h, const pbn_step_args* a, void* stream) { return step_common(h, a, stream, false); }
+
+int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, void* stream_) {
+  if (!h || !a || !io) return fail(PBN_ERR_INVALID, "null argument");
+  if (a->n_envs < 0) return fail(PBN_ERR_INVALID, "n_envs=%lld", (long long)a->n_envs);
+  if (a->n_envs == 0) return PBN_OK;
+  if (io->actions && !io->actions_dev) return fail(PBN_ERR_INVALID, "pbn_step_host: actions given without actions_dev staging buffer");
+  if ((io->reward && !a->reward) || (io->terminated && !a->terminated) || (io->truncated && !a->truncated) || !a->state)
+    return fail(PBN_ERR_INVALID, "pbn_step_host: a host output is requested whose device array is null");
+  if (a->sel || a->pert_mask) return fail(PBN_ERR_INVALID, "pbn_step_host: sel/pert_mask must be null");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  if (!h->s_h2d) {
+    PBN_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    PBN_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    PBN_CUDA(cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming));
+    for (int i = 0; i < pbn_handle::kMaxChunks; ++i) {
+      PBN_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      PBN_CUDA(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+    }
+  }
+  // Outputs in page-locked host memory are written by an export kernel straight over PCIe (one launch
+  // per chunk); pageable outputs go through the copy engine (one cudaMemcpyAsync per array and chunk).
+  uint8_t* zc[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool zero_copy = true;
+  {
+    void* hp[4] = {io->state, io->reward, io->terminated, io->truncated};
+    for (int k = 0; k < 4 && zero_copy; ++k) {
+      if (!hp[k]) continue;
+      void* dp = nullptr;
+      if (cudaHostGetDevicePointer(&dp, hp[k], 0) != cudaSuccess || !dp) {
+        cudaGetLastError();  // not page-locked: clear the sticky-less error and fall back to the copy engine
+        zero_copy = false;
+      }
+      zc[k] = static_cast<uint8_t*>(dp);
+    }
+  }
+  uint32_t* zc_state32 = nullptr;
+  uint8_t* zc_done = nullptr;
+  if (io->state32 || io->done) {
+    if (io->state32 && h->net.n_genes > 32) return fail(PBN_ERR_INVALID, "pbn_step_host: state32 needs a network with N <= 32 (N=%d)", h->net.n_genes);
+    if (io->done && (!a->terminated || !a->truncated)) return fail(PBN_ERR_INVALID, "pbn_step_host: done needs the terminated and truncated device arrays");
+    void* dp = nullptr;
+    if (!zero_copy || (io->state32 && (cudaHostGetDevicePointer(&dp, io->state32, 0) != cudaSuccess || !(zc_state32 = static_cast<uint32_t*>(dp)))) ||
+        (io->done && (cudaHostGetDevicePointer(&dp, io->done, 0) != cudaSuccess || !(zc_done = static_cast<uint8_t*>(dp))))) {
+      cudaGetLastError();
+      return fail(PBN_ERR_INVALID, "pbn_step_host: state32/done need page-locked host memory for every output");
+    }
+  }
+  const int64_t E = a->n_envs, tiles = (E + 1023) / 1024;
+  int64_t nc = io->n_chunks > 0 ? io->n_chunks : (E >= (1 << 18) ? 2 : 1);  // measured best on B200 / PCIe Gen5 (scripts/host_path_probe.py)
+  if (nc > pbn_handle::kMaxChunks) nc = pbn_handle::kMaxChunks;
+  if (nc > tiles) nc = tiles;
+  const int64_t chunk = ((tiles + nc - 1) / nc) * 1024;  // envs per chunk: whole tiles
+  const int W = h->W, bins = h->net.bins;
+  // the staging buffer / device outputs may still be in use by earlier work on the caller's stream
+  PBN_CUDA(cudaEventRecord(h->ev_entry, stream));
+  PBN_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_entry, 0));
+  int c = 0;
+  for (int64_t e0 = 0; e0 < E; e0 += chunk, ++c) {
+    const int64_t n = (E - e0 < chunk) ? (E - e0) : chunk;
+    const bool last = e0 + chunk >= E;
+    if (io->actions) {
+      PBN_CUDA(cudaMemcpyAsync(io->actions_dev + e0 * bins, io->actions + e0 * bins, (size_t)n * bins, cudaMemcpyHostToDevice, h->s_h2d));
+      PBN_CUDA(cudaEventRecord(h->ev_in[c], h->s_h2d));
+      PBN_CUDA(cudaStreamWaitEvent(stream, h->ev_in[c], 0));
+    }
+    pbn_step_args s = *a;
+    s.state = a->state + e0 * W;
+    s.actions = io->actions ? io->actions_dev + e0 * bins : nullptr;
+    if (a->target_id) s.target_id = a->target_id + e0;
+    if (a->source_id) s.source_id = a->source_id + e0;
+    if (a->t) s.t = a->t + e0;
+    if (a->reward) s.reward = a->reward + e0;
+    if (a->terminated) s.terminated = a->terminated + e0;
+    if (a->truncated) s.truncated = a->truncated + e0;
+    if (a->final_state) s.final_state = a->final_state + e0 * W;
+    s.env_offset = a->env_offset + e0;
+    s.n_envs = n;
+    // the chunks are one logical step: one counter value; PDL only orders kernels, which the event waits already do
+    s.flags = (a->flags & ~PBN_STEP_PDL) | ((last && !(a->flags & PBN_STEP_PDL)) ? 0u : PBN_STEP_NO_COUNT);
+    const int rc = step_common(h, &s, stream_, false);
+    if (rc != PBN_OK) return rc;
+    PBN_CUDA(cudaEventRecord(h->ev_k[c], stream));
+    PBN_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_k[c], 0));
+    if (zero_copy) {
+      ExportArgs x{};
+      x.src[0] = reinterpret_cast<const uint8_t*>(a->state + e0 * W);
+      x.dst[0] = zc[0] ? zc[0] + (size_t)e0 * W * 8 : nullptr;
+      x.bytes[0] = (unsigned long long)n * W * 8;
+      x.src[1] = reinterpret_cast<const uint8_t*>(a->reward + e0);
+      x.dst[1] = zc[1] ? zc[1] + (size_t)e0 * 4 : nullptr;
+      x.bytes[1] = (unsigned long long)n * 4;
+      x.src[2] = a->terminated + e0;
+      x.dst[2] = zc[2] ? zc[2] + e0 : nullptr;
+      x.bytes[2] = (unsigned long long)n;
+      x.src[3] = a->truncated + e0;
+      x.dst[3] = zc[3] ? zc[3] + e0 : nullptr;
+      x.bytes[3] = (unsigned long long)n;
+      x.state64 = a->state + e0;
+      x.state32 = zc_state32 ? zc_state32 + e0 : nullptr;
+      x.term = a->terminated ? a->terminated + e0 : nullptr;
+      x.trunc = a->truncated ? a->truncated + e0 : nullptr;
+      x.done = zc_done ? zc_done + e0 : nullptr;
+      x.n_envs = n;
+      export_kernel<<<16, 256, 0, h->s_d2h>>>(x);
+      PBN_CUDA(cudaGetLastError());
+      h->launches += 1;
+      continue;
+    }
+    if (io->state) PBN_CUDA(cudaMemcpyAsync(io->state + e0 * W, a->state + e0 * W, (size_t)n * W * 8, cudaMemcpyDeviceToHost, h->s_d2h));
+    if (io->reward) PBN_CUDA(cudaMemcpyAsync(io->reward + e0, a->reward + e0, (size_t)n * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+    if (io->terminated) PBN_CUDA(cudaMemcpyAsync(io->terminated + e0, a->terminated + e0, (size_t)n, cudaMemcpyDeviceToHost, h->s_d2h));
+    if (io->truncated) PBN_CUDA(cudaMemcpyAsync(io->truncated + e0, a->truncated + e0, (size_t)n, cudaMemcpyDeviceToHost, h->s_d2h));
+  }
+  PBN_CUDA(cudaStreamSynchronize(h->s_d2h));
+  return PBN_OK;
+}
 int pbn_step_injected(pbn_handle* h, const pbn_step_args* a, void* stream) { return step_common(h, a, stream, true); }
 
 int pbn_reset(pbn_handle* h, uint64_t* state, int32_t* target_id, int32_t* source_id, uint16_t* t,

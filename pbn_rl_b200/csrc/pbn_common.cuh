@@ -56,7 +56,7 @@ __device__ __forceinline__ uint64_t effective_step(const pbn_step_args& a) {
 // Called by every thread at the very end of a step kernel: the last CTA to finish increments the
 // device-resident step counter (every CTA read it before any CTA could get here last).
 __device__ __forceinline__ void bump_device_step(const pbn_step_args& a, unsigned int* ticket) {
-  if (a.step_ctr_dev == nullptr || (a.flags & PBN_STEP_PDL)) return;
+  if (a.step_ctr_dev == nullptr || (a.flags & (PBN_STEP_PDL | PBN_STEP_NO_COUNT))) return;
   // No fence is needed: the counter is only consumed by later launches (ordered by the stream),
   // and every thread of this CTA has used its copy of the counter before the barrier below.
   __syncthreads();

@@ -278,6 +278,63 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ NetP
 
 __global__ void advance_counter_kernel(uint64_t* ctr, uint64_t n) { *ctr += n; }
 
+// pbn_step_host: stream one chunk's results from the device arrays into page-locked host memory that
+// is mapped into the device address space (zero-copy posted writes over PCIe, 16 B per thread).
+// A few CTAs saturate the link (scripts/micro/zerocopy_rate.cu); the grid is kept small so that the
+// step kernel of the next chunk finds free SMs.
+struct ExportArgs {
+  const uint8_t* src[4];
+  uint8_t* dst[4];
+  unsigned long long bytes[4];
+  // compact outputs (optional): state narrowed to 32 bits (N <= 32), done = terminated | truncated << 1
+  const uint64_t* state64;
+  uint32_t* state32;
+  const uint8_t* term;
+  const uint8_t* trunc;
+  uint8_t* done;
+  long long n_envs;
+};
+
+__global__ void __launch_bounds__(256) export_kernel(ExportArgs x) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint8_t* __restrict__ src = x.src[k];
+    uint8_t* __restrict__ dst = x.dst[k];
+    const size_t nb = x.bytes[k];
+    if (dst == nullptr || nb == 0) continue;
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) != 0) {
+      for (size_t i = tid; i < nb; i += nth) dst[i] = src[i];
+      continue;
+    }
+    const size_t nv = nb >> 4;
+    for (size_t i = tid; i < nv; i += nth) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = (nv << 4) + tid; i < nb; i += nth) dst[i] = src[i];
+  }
+  // compact forms, four envs per thread and iteration: one 16 B / one 4 B posted write each
+  const size_t n4 = (size_t)x.n_envs >> 2;
+  if (x.state32 != nullptr) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(x.state64) | reinterpret_cast<uintptr_t>(x.state32)) & 15u) == 0;
+    if (vec) {
+      for (size_t i = tid; i < n4; i += nth) {
+        const uint4 a = reinterpret_cast<const uint4*>(x.state64)[2 * i], b = reinterpret_cast<const uint4*>(x.state64)[2 * i + 1];
+        reinterpret_cast<uint4*>(x.state32)[i] = make_uint4(a.x, a.z, b.x, b.z);
+      }
+    }
+    for (size_t e = (vec ? (n4 << 2) : 0) + tid; e < (size_t)x.n_envs; e += nth) x.state32[e] = (uint32_t)x.state64[e];
+  }
+  if (x.done != nullptr) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(x.term) | reinterpret_cast<uintptr_t>(x.trunc) | reinterpret_cast<uintptr_t>(x.done)) & 3u) == 0;
+    if (vec) {
+      for (size_t i = tid; i < n4; i += nth)
+        reinterpret_cast<uint32_t*>(x.done)[i] = (reinterpret_cast<const uint32_t*>(x.term)[i] & 0x01010101u) |
+                                                 ((reinterpret_cast<const uint32_t*>(x.trunc)[i] & 0x01010101u) << 1);
+    }
+    for (size_t e = (vec ? (n4 << 2) : 0) + tid; e < (size_t)x.n_envs; e += nth)
+      x.done[e] = (uint8_t)((x.term[e] & 1u) | ((x.trunc[e] & 1u) << 1));
+  }
+}
+
 // [E*W] packed -> [E,N] uint8 / float32.  One thread per output element: writes are coalesced,
 // the packed word is broadcast from L1 to the N threads that share it.
 template <typename OutT>

@@ -208,6 +208,8 @@ class VecPBNEnv:
             None if thr is None else thr.ctypes.data, self._stream()))
         self.attractors = attractors
         self.pair_weights = pair_weights
+        if self._host is not None:
+            self._host.pop("args", None)  # cached step_host arguments depend on the table's presence
 
     # ------------------------------------------------------------------ env API
     def reset(self, mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -303,11 +305,7 @@ class VecPBNEnv:
         self._pos = 0
 
     # ------------------------------------------------------------------ host-buffer path (end-to-end API)
-    def step_host(self, actions_host: np.ndarray) -> Dict[str, np.ndarray]:
-        """``step`` with HOST buffers: copies ``actions_host`` (uint8 ``[E, bins]``) to the device,
-        steps, and copies state / reward / terminated / truncated back into pinned host
-        buffers that are returned as numpy views (valid until the next call).  This is the
-        call a user of the reference's CPU env would make per step."""
+    def _host_buffers(self) -> Dict[str, torch.Tensor]:
         if self._host is None:
             e, w = self.num_envs, self.n_words
             pin = dict(pin_memory=True)
@@ -319,22 +317,76 @@ class VecPBNEnv:
                 "truncated": torch.empty((e,), dtype=torch.uint8, **pin),
                 "d_actions": torch.empty((e, self.bins), dtype=torch.uint8, device=self.device),
             }
-        hb = self._host
-        hb["actions"].numpy()[...] = np.asarray(actions_host, dtype=np.uint8).reshape(self.num_envs, self.bins)
-        hb["d_actions"].copy_(hb["actions"], non_blocking=True)
-        self.step(hb["d_actions"])
-        hb["state"].copy_(self.state, non_blocking=True)
-        hb["reward"].copy_(self.reward, non_blocking=True)
-        hb["terminated"].copy_(self.terminated, non_blocking=True)
-        hb["truncated"].copy_(self.truncated, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return {k: hb[k].numpy() for k in ("state", "reward", "terminated", "truncated")}
+        return self._host
+
+    def pinned_actions(self) -> torch.Tensor:
+        """A page-locked uint8 ``[E, bins]`` host tensor: actions written here (or into any other pinned
+        tensor of that shape) go to the device without an intermediate host copy in :meth:`step_host`."""
+        return torch.empty((self.num_envs, self.bins), dtype=torch.uint8, pin_memory=True)
+
+    def step_host(self, actions_host, chunks: int = 0, compact: bool = False) -> Dict[str, np.ndarray]:
+        """``step`` with HOST buffers, the call a user of the reference's CPU env makes per step
+        (``pbn_step_host``): uploads ``actions_host`` (uint8 ``[E, bins]``: a pinned torch tensor is used
+        in place, anything else is first copied into a pinned buffer; ``None`` = no interventions), steps,
+        and streams state / reward / terminated / truncated into pinned host buffers returned as
+        numpy views (valid until the next call).  ``compact=True`` returns the same information in
+        fewer PCIe bytes: ``state32`` (uint32, networks with N <= 32), ``reward`` and ``done``
+        (``terminated | truncated << 1``).  The batch is processed in ``chunks`` ranges so that upload,
+        kernel and download overlap (0 = library default); blocks until the results are there."""
+        hb = self._host_buffers()
+        key = "io_compact" if compact else "io"
+        if key not in hb:
+            io = _cabi.HostIO()
+            io.actions_dev = hb["d_actions"].data_ptr()
+            io.reward = hb["reward"].data_ptr()
+            if compact:
+                if self.n_genes > 32:
+                    raise ValueError("compact host results need N <= 32 (state32)")
+                hb["state32"] = torch.empty((self.num_envs,), dtype=torch.int32, pin_memory=True)
+                hb["done"] = torch.empty((self.num_envs,), dtype=torch.uint8, pin_memory=True)
+                io.state32 = hb["state32"].data_ptr()
+                io.done = hb["done"].data_ptr()
+                hb["views_compact"] = {"state32": hb["state32"].numpy().view(np.uint32), "reward": hb["reward"].numpy(),
+                                       "done": hb["done"].numpy()}
+            else:
+                io.state = hb["state"].data_ptr()
+                io.terminated = hb["terminated"].data_ptr()
+                io.truncated = hb["truncated"].data_ptr()
+                hb["views"] = {k: hb[k].numpy() for k in ("state", "reward", "terminated", "truncated")}
+            hb[key] = io
+        io = hb[key]
+        if actions_host is None:
+            io.actions = None
+        elif isinstance(actions_host, torch.Tensor) and actions_host.is_pinned() and actions_host.dtype == torch.uint8 \
+                and actions_host.is_contiguous() and actions_host.numel() == self.num_envs * self.bins:
+            io.actions = actions_host.data_ptr()
+        else:
+            src = hb["actions"]
+            src.numpy()[...] = np.asarray(actions_host, dtype=np.uint8).reshape(self.num_envs, self.bins)
+            io.actions = src.data_ptr()
+        io.n_chunks = int(chunks)
+        a = hb.get("args")
+        if a is None:
+            a = hb["args"] = self._args(None, None, True)
+        a.step_ctr = self._pos if self.pdl else self.step_ctr
+        check(self.lib.pbn_step_host(self._h, C.byref(a), C.byref(io), self._stream()))
+        if self.step_ctr_dev is None:
+            self.step_ctr += 1
+        elif self.pdl:
+            self._pos += 1
+        return hb["views_compact" if compact else "views"]
 
     @property
     def host_bytes_per_step(self) -> Tuple[int, int]:
         """(host->device, device->host) bytes moved by one :meth:`step_host`."""
         e = self.num_envs
         return e * self.bins, e * (8 * self.n_words + 4 + 1 + 1)
+
+    @property
+    def host_bytes_per_step_compact(self) -> Tuple[int, int]:
+        """The same for ``step_host(..., compact=True)``: uint32 state + fp32 reward + done byte."""
+        e = self.num_envs
+        return e * self.bins, e * (4 + 4 + 1)
 
     # ------------------------------------------------------------------ state access
     def set_state(self, state: Union[torch.Tensor, np.ndarray], packed: Optional[bool] = None) -> None:

@@ -1,0 +1,149 @@
+"""GPU: pbn_step_host (host buffers, chunk-pipelined upload / kernel / download) against pbn_step on the
+same inputs -- the result must not depend on the number of chunks, the counter mode or the kernel."""
+import numpy as np
+import pytest
+
+from helpers import attractor_set, product_net
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(horizon=6, bins=3, perturb_p=0.01, perturb_mode="A", seed=77)
+
+
+def _mk(name, e, **kw):
+    from pbn_rl_b200 import VecPBNEnv
+    args = dict(KW)
+    args.update(kw)
+    return VecPBNEnv(product_net(name), e, attractor_set(name), device="cuda:0", **args)
+
+
+def _seed_env(env, name, e, seed):
+    import torch
+    net = product_net(name)
+    rng = np.random.default_rng(seed)
+    masks = np.array(net.state_mask(), dtype=np.uint64)
+    st = (rng.integers(0, 2**63, size=(e, net.n_words), dtype=np.int64).astype(np.uint64) * np.uint64(2)) & masks
+    env.set_state(torch.from_numpy(st.astype(np.int64)), packed=True)
+    env.set_target(torch.from_numpy(rng.integers(0, len(attractor_set(name)), size=e, dtype=np.int32)))
+
+
+@pytest.mark.parametrize("name,e", [("pbn28", 5000), ("pbn28", 8192), ("pbn70", 3000), ("pbn10", 1)])
+@pytest.mark.parametrize("kernel", ["auto", "scalar"])
+@pytest.mark.parametrize("chunks", [0, 1, 3, 16])
+def test_step_host_equals_step(name, e, kernel, chunks):
+    import torch
+    ref = _mk(name, e, kernel=kernel, auto_reset=True)
+    dut = _mk(name, e, kernel=kernel, auto_reset=True)
+    _seed_env(ref, name, e, 5)
+    _seed_env(dut, name, e, 5)
+    rng = np.random.default_rng(9)
+    n = product_net(name).n_genes
+    for step in range(8):
+        act = rng.integers(0, n + 1, size=(e, 3), dtype=np.uint8)
+        ref.step(torch.from_numpy(act).cuda())
+        if step % 2:
+            pinned = dut.pinned_actions()
+            pinned.numpy()[...] = act
+            out = dut.step_host(pinned, chunks=chunks)   # pinned tensor: used in place
+        else:
+            out = dut.step_host(act, chunks=chunks)      # pageable numpy array: copied into a pinned buffer
+        torch.cuda.synchronize()
+        assert np.array_equal(out["state"], ref.state.cpu().numpy())
+        assert np.array_equal(out["reward"], ref.reward.cpu().numpy())
+        assert np.array_equal(out["terminated"], ref.terminated.cpu().numpy())
+        assert np.array_equal(out["truncated"], ref.truncated.cpu().numpy())
+        assert np.array_equal(dut.t.cpu().numpy(), ref.t.cpu().numpy())
+        assert np.array_equal(dut.target_id.cpu().numpy(), ref.target_id.cpu().numpy())
+    assert ref.stats() == dut.stats()
+    ref.close()
+    dut.close()
+
+
+@pytest.mark.parametrize("mode", ["device_counter", "pdl"])
+def test_step_host_counter_modes(mode):
+    """Chunk launches of one logical step share one Philox step counter, whichever side keeps it."""
+    import torch
+    e, name = 6 * 1024 + 17, "pbn28"
+    ref = _mk(name, e)                                    # host-side counter
+    dut = _mk(name, e, device_counter=True, pdl=(mode == "pdl"))
+    _seed_env(ref, name, e, 3)
+    _seed_env(dut, name, e, 3)
+    rng = np.random.default_rng(4)
+    for step in range(5):
+        act = rng.integers(0, 29, size=(e, 3), dtype=np.uint8)
+        ref.step(torch.from_numpy(act).cuda())
+        out = dut.step_host(act, chunks=4)
+        assert np.array_equal(out["state"], ref.state.cpu().numpy()), step
+    if mode == "device_counter":
+        assert int(dut.step_ctr_dev.item()) == 5
+    ref.close()
+    dut.close()
+
+
+def test_step_host_no_actions():
+    import torch
+    e, name = 2048, "pbn10"
+    ref, dut = _mk(name, e), _mk(name, e)
+    _seed_env(ref, name, e, 1)
+    _seed_env(dut, name, e, 1)
+    ref.step(None)
+    out = dut.step_host(None)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["state"], ref.state.cpu().numpy())
+    ref.close()
+    dut.close()
+
+
+def test_step_host_pageable_buffers_use_copy_engine():
+    """The C entry point also takes pageable host memory (plain numpy arrays): same results."""
+    import ctypes as C
+    import torch
+    from pbn_rl_b200 import _cabi
+    e, name = 3 * 1024 + 5, "pbn28"
+    ref, dut = _mk(name, e), _mk(name, e)
+    _seed_env(ref, name, e, 8)
+    _seed_env(dut, name, e, 8)
+    act = np.random.default_rng(2).integers(0, 29, size=(e, 3), dtype=np.uint8)
+    ref.step(torch.from_numpy(act).cuda())
+    out = {k: np.zeros(e, dt) for k, dt in (("state", np.int64), ("reward", np.float32), ("terminated", np.uint8),
+                                            ("truncated", np.uint8))}
+    d_act = torch.empty((e, 3), dtype=torch.uint8, device="cuda:0")
+    io = _cabi.HostIO()
+    io.actions, io.actions_dev = act.ctypes.data, d_act.data_ptr()
+    io.state, io.reward = out["state"].ctypes.data, out["reward"].ctypes.data
+    io.terminated, io.truncated = out["terminated"].ctypes.data, out["truncated"].ctypes.data
+    io.n_chunks = 2
+    a = dut._args(None, None, True)
+    _cabi.check(dut.lib.pbn_step_host(dut._h, C.byref(a), C.byref(io), dut._stream()))
+    assert np.array_equal(out["state"], ref.state.cpu().numpy()[:, 0])
+    assert np.array_equal(out["reward"], ref.reward.cpu().numpy())
+    assert np.array_equal(out["terminated"], ref.terminated.cpu().numpy())
+    # compact outputs are refused for pageable memory, loudly
+    done = np.zeros(e, np.uint8)
+    io.done = done.ctypes.data
+    with pytest.raises(_cabi.PbnError):
+        _cabi.check(dut.lib.pbn_step_host(dut._h, C.byref(a), C.byref(io), dut._stream()))
+    ref.close()
+    dut.close()
+
+
+@pytest.mark.parametrize("e", [1, 1023, 4099, 65536 + 3])
+def test_step_host_compact_results(e):
+    """compact=True: uint32 state + reward + done byte carry the same information."""
+    import torch
+    name = "pbn28"
+    ref, dut = _mk(name, e, auto_reset=True), _mk(name, e, auto_reset=True)
+    _seed_env(ref, name, e, 11)
+    _seed_env(dut, name, e, 11)
+    rng = np.random.default_rng(12)
+    for step in range(7):
+        act = rng.integers(0, 29, size=(e, 3), dtype=np.uint8)
+        ref.step(torch.from_numpy(act).cuda())
+        out = dut.step_host(act, compact=True, chunks=(0, 3)[step & 1])
+        assert np.array_equal(out["state32"].astype(np.int64), ref.state.cpu().numpy()[:, 0])
+        assert np.array_equal(out["reward"], ref.reward.cpu().numpy())
+        assert np.array_equal(out["done"], ref.terminated.cpu().numpy() | (ref.truncated.cpu().numpy() << 1))
+    with pytest.raises(ValueError):
+        _mk("pbn70", 1024).step_host(None, compact=True)
+    ref.close()
+    dut.close()
