@@ -233,6 +233,39 @@ int pbn_pack(pbn_handle* h, const uint8_t* bits, uint64_t* state, int64_t n_envs
 int pbn_attractor_id(pbn_handle* h, const uint64_t* state, int32_t* attr_id, int64_t n_envs,
                      void* stream);
 
+/* ---- Device-resident replay ring + fused observation unpack (the callers' side of the path) ----------
+ * Replaces the python-list ExperienceReplay (bdq_model/memory.py:22-70: store / sample) and the tuple ->
+ * float-tensor rebuilds of predict() and update_policy() (bdq_model/__init__.py:92-93,100-109).
+ * Transitions stay packed; all arrays are caller-owned DEVICE memory holding `capacity` transitions. */
+typedef struct {
+  uint64_t* state;       /* [capacity*W] state the action was chosen in */
+  uint64_t* next_state;  /* [capacity*W] state after the step (before any auto-reset) */
+  int32_t* target_id;    /* [capacity]   target attractor of the episode */
+  uint8_t* actions;      /* [capacity*bins] */
+  float* reward;         /* [capacity] */
+  uint8_t* done;         /* [capacity]   terminated | truncated << 1 */
+  int64_t capacity;
+} pbn_replay;
+
+/* memory.store(), first half, BEFORE the step: ring slot (head + e) mod capacity <- (state[e], target_id[e]). */
+int pbn_replay_observe(pbn_handle* h, const pbn_replay* r, int64_t head, const uint64_t* state,
+                       const int32_t* target_id, int64_t n_envs, void* stream);
+/* memory.store(), second half, AFTER the step: the same slots <- (actions, reward, done flags, next_state);
+ * pass the step's final_state as next_state when auto-reset is on.  actions/truncated may be NULL. */
+int pbn_replay_commit(pbn_handle* h, const pbn_replay* r, int64_t head, const uint8_t* actions, const float* reward,
+                      const uint8_t* terminated, const uint8_t* truncated, const uint64_t* next_state,
+                      int64_t n_envs, void* stream);
+/* memory.sample() + the tensor building of update_policy(): for ring slots index[0..B) (DEVICE int64) write
+ * obs [2,B,N] = (state bits, target-state bits), next_obs [2,B,N] = (next-state bits, target-state bits) as
+ * float32, actions [B,bins] int64, reward [B], done [B] float32 (1.0 if terminated or truncated).  Any output
+ * may be NULL.  The target state is the first state of the attractor with '*' -> 0 (env.reset()'s `target`). */
+int pbn_replay_sample(pbn_handle* h, const pbn_replay* r, const int64_t* index, int64_t batch, float* obs,
+                      float* next_obs, int64_t* actions, float* reward, float* done, void* stream);
+/* The agent's network input for the live envs (predict(), bdq_model/__init__.py:92-93):
+ * obs [2,E,N] float32 = (state bits, target-state bits). */
+int pbn_observe(pbn_handle* h, const uint64_t* state, const int32_t* target_id, float* obs, int64_t n_envs,
+                void* stream);
+
 /* *step_ctr_dev += n on the stream (fully serialised): closes a sequence of PBN_STEP_PDL launches. */
 int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void* stream);
 

@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 from typing import Optional
 
-__all__ = ["lib", "load_library", "PbnError", "NetDesc", "StepArgs", "HostIO", "check", "LIB_PATH", "EXPORTS"]
+__all__ = ["lib", "load_library", "PbnError", "NetDesc", "StepArgs", "HostIO", "Replay", "check", "LIB_PATH", "EXPORTS"]
 
 LIB_PATH = Path(__file__).resolve().parent / "libpbn_b200.so"
 
@@ -29,7 +29,8 @@ EXPORTS = (
     "pbn_create", "pbn_destroy", "pbn_update_attractors", "pbn_step", "pbn_step_injected", "pbn_reset",
     "pbn_unpack", "pbn_pack", "pbn_attractor_id", "pbn_kernel_kind", "pbn_words_per_state",
     "pbn_launch_count", "pbn_last_error", "pbn_version", "pbn_jit_source", "pbn_jit_precompile",
-    "pbn_advance_counter", "pbn_step_host",
+    "pbn_advance_counter", "pbn_step_host", "pbn_replay_observe", "pbn_replay_commit", "pbn_replay_sample",
+    "pbn_observe",
 )
 
 
@@ -100,6 +101,18 @@ class HostIO(C.Structure):
     ]
 
 
+class Replay(C.Structure):
+    _fields_ = [
+        ("state", C.c_void_p),
+        ("next_state", C.c_void_p),
+        ("target_id", C.c_void_p),
+        ("actions", C.c_void_p),
+        ("reward", C.c_void_p),
+        ("done", C.c_void_p),
+        ("capacity", C.c_int64),
+    ]
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -126,6 +139,14 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_step.restype = C.c_int
     lib.pbn_step_host.argtypes = [vp, C.POINTER(StepArgs), C.POINTER(HostIO), vp]
     lib.pbn_step_host.restype = C.c_int
+    lib.pbn_replay_observe.argtypes = [vp, C.POINTER(Replay), i64, vp, vp, i64, vp]
+    lib.pbn_replay_observe.restype = C.c_int
+    lib.pbn_replay_commit.argtypes = [vp, C.POINTER(Replay), i64, vp, vp, vp, vp, vp, i64, vp]
+    lib.pbn_replay_commit.restype = C.c_int
+    lib.pbn_replay_sample.argtypes = [vp, C.POINTER(Replay), vp, i64, vp, vp, vp, vp, vp, vp]
+    lib.pbn_replay_sample.restype = C.c_int
+    lib.pbn_observe.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.pbn_observe.restype = C.c_int
     lib.pbn_step_injected.argtypes = [vp, C.POINTER(StepArgs), vp]
     lib.pbn_step_injected.restype = C.c_int
     lib.pbn_reset.argtypes = [vp, vp, vp, vp, vp, vp, u64, i64, i64, vp]

@@ -11,6 +11,7 @@
 #include "pbn_common.cuh"
 #include "step_scalar.cuh"
 #include "sliced_host.cuh"
+#include "replay.cuh"
 
 using namespace pbn;
 
@@ -637,6 +638,78 @@ int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DeviceGuard guard(h->device);
   advance_counter_kernel<<<1, 1, 0, stream>>>(step_ctr_dev, n);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+static int check_replay(const pbn_replay* r) {
+  if (!r || r->capacity < 1 || !r->state || !r->next_state || !r->target_id || !r->actions || !r->reward || !r->done)
+    return fail(PBN_ERR_INVALID, "replay ring: null array or capacity < 1");
+  return PBN_OK;
+}
+
+int pbn_replay_observe(pbn_handle* h, const pbn_replay* r, int64_t head, const uint64_t* state, const int32_t* target_id,
+                       int64_t n_envs, void* stream_) {
+  if (!h || !state || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  int rc = check_replay(r);
+  if (rc != PBN_OK) return rc;
+  if (head < 0 || head >= r->capacity || n_envs > r->capacity) return fail(PBN_ERR_INVALID, "replay push: head=%lld, n=%lld, capacity=%lld", (long long)head, (long long)n_envs, (long long)r->capacity);
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  replay_observe_kernel<<<grid_for(h, n_envs * h->W, 256, 8), 256, 0, stream>>>(*r, head, state, target_id, h->W, n_envs);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_replay_commit(pbn_handle* h, const pbn_replay* r, int64_t head, const uint8_t* actions, const float* reward,
+                      const uint8_t* terminated, const uint8_t* truncated, const uint64_t* next_state, int64_t n_envs,
+                      void* stream_) {
+  if (!h || !reward || !terminated || !next_state || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  int rc = check_replay(r);
+  if (rc != PBN_OK) return rc;
+  if (head < 0 || head >= r->capacity || n_envs > r->capacity) return fail(PBN_ERR_INVALID, "replay push: head=%lld, n=%lld, capacity=%lld", (long long)head, (long long)n_envs, (long long)r->capacity);
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  replay_commit_kernel<<<grid_for(h, n_envs * h->net.bins, 256, 8), 256, 0, stream>>>(*r, head, actions, reward, terminated, truncated,
+                                                                                 next_state, h->W, h->net.bins, n_envs);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_replay_sample(pbn_handle* h, const pbn_replay* r, const int64_t* index, int64_t batch, float* obs, float* next_obs,
+                      int64_t* actions, float* reward, float* done, void* stream_) {
+  if (!h || !index || batch < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  int rc = check_replay(r);
+  if (rc != PBN_OK) return rc;
+  if (batch == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  if (obs || next_obs) {
+    gather_unpack_kernel<<<grid_for(h, batch * h->net.n_genes, 256, 8), 256, 0, stream>>>(h->net, r->state, r->next_state, r->target_id, index,
+                                                                                      h->W, batch, obs, next_obs);
+    PBN_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (actions || reward || done) {
+    gather_scalars_kernel<<<grid_for(h, batch * h->net.bins, 256, 8), 256, 0, stream>>>(*r, index, h->net.bins, batch, actions, reward, done);
+    PBN_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  return PBN_OK;
+}
+
+int pbn_observe(pbn_handle* h, const uint64_t* state, const int32_t* target_id, float* obs, int64_t n_envs, void* stream_) {
+  if (!h || !state || !obs || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  gather_unpack_kernel<<<grid_for(h, n_envs * h->net.n_genes, 256, 8), 256, 0, stream>>>(h->net, state, nullptr, target_id, nullptr, h->W,
+                                                                                     n_envs, obs, nullptr);
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
   return PBN_OK;

@@ -415,6 +415,16 @@ class VecPBNEnv:
         check(self.lib.pbn_unpack(self._h, _ptr(words), _ptr(out), kind, e, self._stream()))
         return out
 
+    def observe(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The agent's network input for all instances in one kernel: float32 ``[2, E, N]`` =
+        (state bits, bits of the target attractor's first state with ``'*'`` -> 0) -- what
+        ``predict`` builds per instance with ``np.stack((state, target))`` (bdq_model/__init__.py:92-93)."""
+        if out is None:
+            out = torch.empty((2, self.num_envs, self.n_genes), dtype=torch.float32, device=self.device)
+        check(self.lib.pbn_observe(self._h, _ptr(self.state), _ptr(self.target_id) if self.attractors is not None else None,
+                                   _ptr(out), self.num_envs, self._stream()))
+        return out
+
     def attractor_ids(self, words: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Index of the attractor containing each state (-1: none): ``is_attracting_state`` /
         ``state_attractor_id`` of the reference env."""
