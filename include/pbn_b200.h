@@ -266,6 +266,39 @@ int pbn_replay_sample(pbn_handle* h, const pbn_replay* r, const int64_t* index, 
 int pbn_observe(pbn_handle* h, const uint64_t* state, const int32_t* target_id, float* obs, int64_t n_envs,
                 void* stream);
 
+/* ---- Batched all-pairs evaluation (model_tester.py:584-658) -------------------------------------------
+ * E rollouts (run x source attractor x target attractor) are stepped together with pbn_step; these entry
+ * points do the reference loop's bookkeeping on the device. */
+/* env.in_target(state) for every instance (model_tester.py:616): out[e] = 1 iff state[e] is in attractor
+ * target_id[e]. */
+int pbn_in_target(pbn_handle* h, const uint64_t* state, const int32_t* target_id, uint8_t* out, int64_t n_envs,
+                  void* stream);
+/* After a step, for rollouts with active[e] != 0: count[e] += 1; if count[e] > max_steps the rollout has failed
+ * (model_tester.py:627-636 books max_steps + 1 = 101) and stops; else if terminated[e] it stops with count[e]
+ * steps.  n_active (DEVICE, may be NULL) is incremented by the number of rollouts still running. */
+int pbn_rollout_track(pbn_handle* h, const uint8_t* terminated, uint8_t* active, int32_t* count,
+                      int32_t max_steps, int64_t n_envs, unsigned int* n_active, void* stream);
+/* result_matrix[pair] += count, data[count] += 1 (model_tester.py:645-652): matrix [n_pairs] and
+ * hist [max_steps + 2] are DEVICE u64 accumulators; pair_id[e] = source * A + target. */
+int pbn_rollout_reduce(pbn_handle* h, const int32_t* count, const int32_t* pair_id, int64_t n_envs,
+                       int32_t n_pairs, int32_t max_steps, unsigned long long* matrix,
+                       unsigned long long* hist, void* stream);
+
+/* ---- Attractor discovery / steady-state statistics (print_graph.py:15-34, train_pbn_28.py:257) -------
+ * Visit-count hash table in DEVICE memory: tags[capacity] (0 = empty slot), slot_state[capacity*W],
+ * counts[capacity], capacity a power of two, all zero-initialised by the caller.  For every instance with
+ * mask[e] != 0 (all if mask is NULL) counts[slot of state[e]] += 1; *overflow (DEVICE) counts states
+ * that found no slot (table too full).  The tag of a state is the splitmix64-based fingerprint
+ * documented in csrc/discover.cuh; distinct states with equal tags (probability 2^-64 per pair) merge. */
+int pbn_visit_count(pbn_handle* h, const uint64_t* state, const uint8_t* mask, int64_t n_envs,
+                    unsigned long long* tags, uint64_t* slot_state, unsigned long long* counts,
+                    int64_t capacity, unsigned int* overflow, void* stream);
+/* Successor descriptor of the perturbation-free state-transition graph (graph.genSTG(), print_graph.py:15-21)
+ * for a list of states: bit i of can1[e] / can0[e] = some predictor of gene i yields 1 / 0 in state[e].
+ * The successors of state[e] are {t : t_i = 1 where only can1, 0 where only can0, free where both}. */
+int pbn_successor_sets(pbn_handle* h, const uint64_t* state, int64_t n_states, uint64_t* can1, uint64_t* can0,
+                       void* stream);
+
 /* *step_ctr_dev += n on the stream (fully serialised): closes a sequence of PBN_STEP_PDL launches. */
 int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void* stream);
 

@@ -30,7 +30,8 @@ EXPORTS = (
     "pbn_unpack", "pbn_pack", "pbn_attractor_id", "pbn_kernel_kind", "pbn_words_per_state",
     "pbn_launch_count", "pbn_last_error", "pbn_version", "pbn_jit_source", "pbn_jit_precompile",
     "pbn_advance_counter", "pbn_step_host", "pbn_replay_observe", "pbn_replay_commit", "pbn_replay_sample",
-    "pbn_observe",
+    "pbn_observe", "pbn_in_target", "pbn_rollout_track", "pbn_rollout_reduce",
+    "pbn_visit_count", "pbn_successor_sets",
 )
 
 
@@ -147,6 +148,16 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_replay_sample.restype = C.c_int
     lib.pbn_observe.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.pbn_observe.restype = C.c_int
+    lib.pbn_in_target.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.pbn_in_target.restype = C.c_int
+    lib.pbn_rollout_track.argtypes = [vp, vp, vp, vp, i32, i64, vp, vp]
+    lib.pbn_rollout_track.restype = C.c_int
+    lib.pbn_rollout_reduce.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.pbn_rollout_reduce.restype = C.c_int
+    lib.pbn_visit_count.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, vp, vp]
+    lib.pbn_visit_count.restype = C.c_int
+    lib.pbn_successor_sets.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.pbn_successor_sets.restype = C.c_int
     lib.pbn_step_injected.argtypes = [vp, C.POINTER(StepArgs), vp]
     lib.pbn_step_injected.restype = C.c_int
     lib.pbn_reset.argtypes = [vp, vp, vp, vp, vp, vp, u64, i64, i64, vp]

@@ -12,6 +12,8 @@
 #include "step_scalar.cuh"
 #include "sliced_host.cuh"
 #include "replay.cuh"
+#include "evaluate.cuh"
+#include "discover.cuh"
 
 using namespace pbn;
 
@@ -710,6 +712,72 @@ int pbn_observe(pbn_handle* h, const uint64_t* state, const int32_t* target_id, 
   DeviceGuard guard(h->device);
   gather_unpack_kernel<<<grid_for(h, n_envs * h->net.n_genes, 256, 8), 256, 0, stream>>>(h->net, state, nullptr, target_id, nullptr, h->W,
                                                                                      n_envs, obs, nullptr);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_in_target(pbn_handle* h, const uint64_t* state, const int32_t* target_id, uint8_t* out, int64_t n_envs, void* stream_) {
+  if (!h || !state || !target_id || !out || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, n_envs, 256, 8);
+  if (h->W == 1) in_target_kernel<1><<<grid, 256, 0, stream>>>(h->net, state, target_id, out, n_envs);
+  else in_target_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, target_id, out, n_envs);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_rollout_track(pbn_handle* h, const uint8_t* terminated, uint8_t* active, int32_t* count, int32_t max_steps,
+                      int64_t n_envs, unsigned int* n_active, void* stream_) {
+  if (!h || !terminated || !active || !count || n_envs < 0 || max_steps < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  rollout_track_kernel<<<grid_for(h, n_envs, 256, 8), 256, 0, stream>>>(terminated, active, count, max_steps, n_envs, n_active);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_rollout_reduce(pbn_handle* h, const int32_t* count, const int32_t* pair_id, int64_t n_envs, int32_t n_pairs,
+                       int32_t max_steps, unsigned long long* matrix, unsigned long long* hist, void* stream_) {
+  if (!h || !count || !pair_id || !matrix || !hist || n_envs < 0 || n_pairs < 1 || max_steps < 0)
+    return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  rollout_reduce_kernel<<<grid_for(h, n_envs, 256, 8), 256, 0, stream>>>(count, pair_id, n_envs, n_pairs, max_steps, matrix, hist);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_visit_count(pbn_handle* h, const uint64_t* state, const uint8_t* mask, int64_t n_envs, unsigned long long* tags,
+                    uint64_t* slot_state, unsigned long long* counts, int64_t capacity, unsigned int* overflow, void* stream_) {
+  if (!h || !state || !tags || !slot_state || !counts || !overflow || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (capacity < 2 || (capacity & (capacity - 1))) return fail(PBN_ERR_INVALID, "capacity=%lld must be a power of two >= 2", (long long)capacity);
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, n_envs, 256, 8);
+  if (h->W == 1) visit_count_kernel<1><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, overflow);
+  else visit_count_kernel<2><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, overflow);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_successor_sets(pbn_handle* h, const uint64_t* state, int64_t n_states, uint64_t* can1, uint64_t* can0, void* stream_) {
+  if (!h || !state || !can1 || !can0 || n_states < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_states == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, n_states, 256, 8);
+  if (h->W == 1) successor_sets_kernel<1><<<grid, 256, 0, stream>>>(h->net, state, n_states, can1, can0);
+  else successor_sets_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, n_states, can1, can0);
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
   return PBN_OK;
