@@ -299,6 +299,22 @@ int pbn_visit_count(pbn_handle* h, const uint64_t* state, const uint8_t* mask, i
 int pbn_successor_sets(pbn_handle* h, const uint64_t* state, int64_t n_states, uint64_t* can1, uint64_t* can0,
                        void* stream);
 
+/* Exact attractors of large networks: forward closure of a candidate state and backward reachability, on
+ * the device.  `list` [list_cap*W] holds the closure in discovery order (the caller writes the seed into
+ * list[0], sets *list_count = 1 and registers it in the table with index 1); the hash table is the
+ * visit-count table above with its counts column reused as slot_index = list index + 1.
+ * pbn_closure_expand appends every successor of list[begin, end) that is not in the table yet;
+ * *status (DEVICE int) becomes 1 if a state has more than max_free free genes (2^max_free successors),
+ * 2 if the list is full, 3 if the table is full.  pbn_closure_reach does one sweep of "flags[i] = 1 if a
+ * successor of list[i] has flag 1" and sets *changed (DEVICE int) if any flag changed. */
+int pbn_closure_expand(pbn_handle* h, uint64_t* list, int64_t begin, int64_t end, int64_t list_cap,
+                       unsigned long long* list_count, unsigned long long* tags, uint64_t* slot_state,
+                       unsigned long long* slot_index, int64_t capacity, int32_t max_free, int32_t* status,
+                       void* stream);
+int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_t* flags,
+                      const unsigned long long* tags, const unsigned long long* slot_index, int64_t capacity,
+                      int32_t* changed, void* stream);
+
 /* *step_ctr_dev += n on the stream (fully serialised): closes a sequence of PBN_STEP_PDL launches. */
 int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void* stream);
 

@@ -31,7 +31,7 @@ EXPORTS = (
     "pbn_launch_count", "pbn_last_error", "pbn_version", "pbn_jit_source", "pbn_jit_precompile",
     "pbn_advance_counter", "pbn_step_host", "pbn_replay_observe", "pbn_replay_commit", "pbn_replay_sample",
     "pbn_observe", "pbn_in_target", "pbn_rollout_track", "pbn_rollout_reduce",
-    "pbn_visit_count", "pbn_successor_sets",
+    "pbn_visit_count", "pbn_successor_sets", "pbn_closure_expand", "pbn_closure_reach",
 )
 
 
@@ -158,6 +158,10 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_visit_count.restype = C.c_int
     lib.pbn_successor_sets.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.pbn_successor_sets.restype = C.c_int
+    lib.pbn_closure_expand.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, i64, i32, vp, vp]
+    lib.pbn_closure_expand.restype = C.c_int
+    lib.pbn_closure_reach.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, vp]
+    lib.pbn_closure_reach.restype = C.c_int
     lib.pbn_step_injected.argtypes = [vp, C.POINTER(StepArgs), vp]
     lib.pbn_step_injected.restype = C.c_int
     lib.pbn_reset.argtypes = [vp, vp, vp, vp, vp, vp, u64, i64, i64, vp]

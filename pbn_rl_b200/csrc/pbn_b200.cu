@@ -783,6 +783,39 @@ int pbn_successor_sets(pbn_handle* h, const uint64_t* state, int64_t n_states, u
   return PBN_OK;
 }
 
+int pbn_closure_expand(pbn_handle* h, uint64_t* list, int64_t begin, int64_t end, int64_t list_cap, unsigned long long* list_count,
+                       unsigned long long* tags, uint64_t* slot_state, unsigned long long* slot_index, int64_t capacity,
+                       int32_t max_free, int32_t* status, void* stream_) {
+  if (!h || !list || !list_count || !tags || !slot_state || !slot_index || !status || begin < 0 || end < begin || end > list_cap)
+    return fail(PBN_ERR_INVALID, "bad arguments");
+  if (capacity < 2 || (capacity & (capacity - 1))) return fail(PBN_ERR_INVALID, "capacity=%lld must be a power of two >= 2", (long long)capacity);
+  if (max_free < 0 || max_free > kClosureMaxFree) return fail(PBN_ERR_INVALID, "max_free=%d outside 0..%d", max_free, kClosureMaxFree);
+  if (end == begin) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, (end - begin) * 128, 128, 16);
+  if (h->W == 1) closure_expand_kernel<1><<<grid, 128, 0, stream>>>(h->net, list, begin, end, list_cap, list_count, tags, slot_state, slot_index, (uint64_t)capacity - 1, max_free, status);
+  else closure_expand_kernel<2><<<grid, 128, 0, stream>>>(h->net, list, begin, end, list_cap, list_count, tags, slot_state, slot_index, (uint64_t)capacity - 1, max_free, status);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_t* flags, const unsigned long long* tags,
+                      const unsigned long long* slot_index, int64_t capacity, int32_t* changed, void* stream_) {
+  if (!h || !list || !flags || !tags || !slot_index || !changed || count < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (capacity < 2 || (capacity & (capacity - 1))) return fail(PBN_ERR_INVALID, "capacity=%lld must be a power of two >= 2", (long long)capacity);
+  if (count == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, count * 128, 128, 16);
+  if (h->W == 1) closure_reach_kernel<1><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_index, (uint64_t)capacity - 1, changed);
+  else closure_reach_kernel<2><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_index, (uint64_t)capacity - 1, changed);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
 int pbn_pack(pbn_handle* h, const uint8_t* bits, uint64_t* state, int64_t n_envs, void* stream_) {
   if (!h || !state || !bits || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
   if (n_envs == 0) return PBN_OK;

@@ -1,0 +1,131 @@
+"""GPU: attractor discovery by massive rollouts + device visit-count hash (pbn_rl_b200/discover.py)
+against the known answers K2/K5 (tests/golden/k5_stg.json: sink SCCs of pbn7/pbn10 by brute force) and,
+for the large networks, against closure/connectivity checks done with the oracle's evaluator."""
+import numpy as np
+import pytest
+
+from helpers import golden, oracle_net, product_net
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_descriptor(onet, s):
+    """(can1, can0) of state s from the oracle: OR over 'every gene uses its predictor min(k, K_i - 1)'."""
+    can1 = can0 = 0
+    full = (1 << onet.n) - 1
+    nf = [len(row) for row in onet.py_code]
+    for k in range(max(nf)):
+        t = onet.transition(s, 0, [min(k, nf[i] - 1) for i in range(onet.n)], 0)
+        can1 |= t
+        can0 |= ~t & full
+    return can1, can0
+
+
+def _successors(can1, can0):
+    free = can1 & can0
+    out = [can1 & ~free]
+    b = free
+    while b:
+        low = b & -b
+        out += [t | low for t in out]
+        b ^= low
+    return out
+
+
+@pytest.mark.parametrize("method", ["device", "host"])
+@pytest.mark.parametrize("name", ["pbn7", "pbn10"])
+def test_rollout_finder_reproduces_brute_force_sink_sccs(name, method):
+    from pbn_rl_b200.discover import find_attractors_rollout
+    attrs, info = find_attractors_rollout(product_net(name), n_rollouts=4096, burn_in=200, method=method)
+    want = golden("k5_stg.json")[name]["sink_sccs"]
+    assert info["states"] == [sorted(m) for m in sorted(want, key=lambda m: min(m))]
+    assert abs(sum(info["basin_fraction"]) - 1.0) < 1e-9 and not info["unresolved"]
+    assert len(attrs) == len(want)
+
+
+@pytest.mark.parametrize("name,kernel", [("pbn7", "auto"), ("pbn10", "scalar")])
+def test_successor_sets_match_host_enumeration(name, kernel):
+    import torch
+    from pbn_rl_b200 import VecPBNEnv
+    from pbn_rl_b200.attractors import _successor_sets
+    from pbn_rl_b200.discover import successor_descriptors
+    net = product_net(name)
+    env = VecPBNEnv(net, 1024, None, device="cuda:0", kernel=kernel)
+    can1, can0 = _successor_sets(net)
+    got = successor_descriptors(env, list(range(1 << net.n_genes)))
+    assert [g[0] for g in got] == can1.tolist() and [g[1] for g in got] == can0.tolist()
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["pbn28", "pbn70"])
+def test_large_network_attractors_are_closed_and_strongly_connected(name):
+    from pbn_rl_b200.discover import find_attractors_rollout
+    onet = oracle_net(name)
+    attrs, info = find_attractors_rollout(product_net(name), n_rollouts=1 << 14, burn_in=300, max_candidates=64)
+    if name == "pbn28":   # the host closure + Tarjan path finds the very same attractors
+        _, info_host = find_attractors_rollout(product_net(name), n_rollouts=1 << 14, burn_in=300, max_candidates=64,
+                                               method="host")
+        assert info_host["states"] == info["states"]
+    assert len(attrs) >= 1 and sum(info["basin_fraction"]) > 0.5
+    for members in info["states"][:12]:
+        mset = set(members)
+        succ = {}
+        for s in members[:64]:
+            succ[s] = _successors(*_oracle_descriptor(onet, s))
+            assert set(succ[s]) <= mset, "attractor is not closed under the oracle's transition relation"
+        if len(members) <= 64:           # strongly connected: everything reaches the first member and back
+            reach = {members[0]}
+            todo = [members[0]]
+            while todo:
+                for t in succ[todo.pop()]:
+                    if t not in reach:
+                        reach.add(t)
+                        todo.append(t)
+            assert reach == mset
+
+
+@pytest.mark.parametrize("name,e", [("pbn10", 5000), ("pbn70", 3000)])
+def test_visit_count_equals_numpy_unique(name, e):
+    import torch
+    from pbn_rl_b200 import VecPBNEnv
+    from pbn_rl_b200.discover import VisitCounter
+    net = product_net(name)
+    env = VecPBNEnv(net, e, None, device="cuda:0")
+    rng = np.random.default_rng(3)
+    table = VisitCounter(env, 1 << 12)
+    ref = {}
+    for rnd in range(3):
+        st = rng.integers(0, 40, size=(e, net.n_words), dtype=np.int64)     # many duplicates
+        if net.n_words == 2:
+            st[:, 1] = rng.integers(0, 3, size=e)
+        mask = (rng.random(e) < 0.7).astype(np.uint8) if rnd else None
+        table.add(torch.from_numpy(st), None if mask is None else torch.from_numpy(mask))
+        for k in range(e):
+            if mask is None or mask[k]:
+                key = tuple(int(x) for x in st[k])
+                ref[key] = ref.get(key, 0) + 1
+    states, counts = table.items()
+    got = {tuple(int(x) for x in states[k]): int(counts[k]) for k in range(len(counts))}
+    assert got == ref
+    small = VisitCounter(env, 16)                                            # too small: overflow is reported
+    small.add(torch.arange(e, dtype=torch.int64).reshape(e, 1).repeat(1, net.n_words))
+    with pytest.raises(RuntimeError):
+        small.items()
+    env.close()
+
+
+def test_steady_state_histogram_mass():
+    import torch
+    from helpers import attractor_set
+    from pbn_rl_b200 import VecPBNEnv
+    from pbn_rl_b200.discover import steady_state_histogram
+    net = product_net("pbn7")
+    env = VecPBNEnv(net, 2048, None, device="cuda:0", perturb_p=0.0)
+    env.state.random_(0, 128)
+    hist = steady_state_histogram(env, steps=20, burn_in=200)
+    assert sum(hist.values()) == 20 * 2048
+    sinks = {s for m in golden("k5_stg.json")["pbn7"]["sink_sccs"] for s in m}
+    assert set(hist) <= sinks                    # without perturbation all mass sits on the attractors
+    proj = steady_state_histogram(env, steps=5, genes=[0, 6])
+    assert sum(proj.values()) == 5 * 2048 and set(proj) <= {0, 1, 2, 3}
+    env.close()
