@@ -72,7 +72,8 @@ extern "C" {
 #endif
 
 #define PBN_MAX_GENES 128
-#define PBN_MAX_ARITY 6
+#define PBN_MAX_ARITY 6        /* predictors with a 64-bit truth table (func_lut) */
+#define PBN_MAX_WIDE_ARITY 16  /* "wide" predictors: multi-word truth tables (wide_lut), scalar kernel only */
 #define PBN_MAX_BINS 8
 #define PBN_FUNC_INPUT_STRIDE 8
 
@@ -137,6 +138,15 @@ typedef struct {
   uint64_t seed;                /* Philox key */
   int32_t device;               /* CUDA device ordinal */
   int32_t kernel;               /* PBN_KERNEL_* */
+  /* Wide predictors (arity 7..PBN_MAX_WIDE_ARITY), e.g. the inline logic_functions of model_tester.py:97-341
+   * and train_control_gbdq.py:45-72.  Function f is wide iff func_arity[f] > PBN_MAX_ARITY; then
+   * func_lut[f] holds its index v into these tables and func_inputs[f*8..] is ignored.  n_wide = 0 and
+   * NULL pointers when the network has none. */
+  int32_t n_wide;
+  int32_t reserved0;
+  const uint8_t* wide_inputs;       /* [n_wide*16] gene index feeding bit j of the truth-table index */
+  const int32_t* wide_lut_offset;   /* [n_wide+1] offsets into wide_lut, in 64-bit words */
+  const uint64_t* wide_lut;         /* truth tables: bit a of table v = wide_lut[off[v] + a/64] >> (a%64) */
 } pbn_net_desc;
 
 /* Arguments of one step over n_envs instances (device pointers). */

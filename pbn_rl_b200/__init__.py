@@ -21,7 +21,7 @@ def __getattr__(name):
     if name == "VecPBNEnv":
         from .vec_env import VecPBNEnv
         return VecPBNEnv
-    if name in ("PBNEnv", "make", "register_gym_ids"):
+    if name in ("PBNEnv", "ControlPBNEnv", "make", "register_gym_ids"):
         from . import gym_env
         return getattr(gym_env, name)
     raise AttributeError(name)

@@ -61,6 +61,11 @@ class NetDesc(C.Structure):
         ("seed", C.c_uint64),
         ("device", C.c_int32),
         ("kernel", C.c_int32),
+        ("n_wide", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("wide_inputs", C.c_void_p),
+        ("wide_lut_offset", C.c_void_p),
+        ("wide_lut", C.c_void_p),
     ]
 
 

@@ -91,14 +91,19 @@ __device__ __forceinline__ void successor_descriptor(const NetParams& n, const u
   for (int g = 0; g < n.n_genes; ++g) {
     for (int f = n.func_offset[g]; f < n.func_offset[g + 1]; ++f) {
       const FuncDesc d = n.funcs[f];
-      uint32_t idx = 0;
+      uint64_t v;
+      if (d.in47 == kWideMarker) {
+        v = eval_wide<W>(n, d.lut_lo, s);
+      } else {
+        uint32_t idx = 0;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const uint32_t in = ((j < 4 ? d.in03 >> (8 * j) : d.in47 >> (8 * (j - 4))) & 0xFFu);
-        idx |= (uint32_t)((s[in >> 6] >> (in & 63u)) & 1ull) << j;
+        for (int j = 0; j < 6; ++j) {
+          const uint32_t in = ((j < 4 ? d.in03 >> (8 * j) : d.in47 >> (8 * (j - 4))) & 0xFFu);
+          idx |= (uint32_t)((s[W == 1 ? 0 : (in >> 6)] >> (in & 63u)) & 1ull) << j;
+        }
+        const uint64_t lut = ((uint64_t)d.lut_hi << 32) | d.lut_lo;   // replicated over unused inputs
+        v = (lut >> idx) & 1ull;
       }
-      const uint64_t lut = ((uint64_t)d.lut_hi << 32) | d.lut_lo;   // replicated over unused inputs
-      const uint64_t v = (lut >> idx) & 1ull;
       c1[g >> 6] |= v << (g & 63);
       c0[g >> 6] |= (v ^ 1ull) << (g & 63);
     }

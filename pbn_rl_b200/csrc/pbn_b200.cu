@@ -79,6 +79,8 @@ struct pbn_handle {
   uint32_t* d_pair_cum = nullptr;
   unsigned int* d_ticket = nullptr;
   uint32_t* d_surv_sliced = nullptr;
+  WideDesc* d_wide = nullptr;
+  uint64_t* d_wide_lut = nullptr;
   // sliced kernel: [0] = own-RNG specialisation, [1] = injected-randomness one (compiled on first use)
   jit::GenNet gen;
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
@@ -208,6 +210,8 @@ void pbn_destroy(pbn_handle* h) {
     cudaFree(h->d_pair_cum);
     cudaFree(h->d_ticket);
     cudaFree(h->d_surv_sliced);
+    cudaFree(h->d_wide);
+    cudaFree(h->d_wide_lut);
     for (int i = 0; i < 2; ++i)
       if (h->jit_lib[i]) cudaLibraryUnload(h->jit_lib[i]);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -237,6 +241,9 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
   if (N > 4 * 32) return fail(PBN_ERR_INVALID, "too many genes");
 
   std::vector<FuncDesc> funcs(F);
+  std::vector<WideDesc> wides((size_t)(d->n_wide > 0 ? d->n_wide : 0));
+  if (d->n_wide < 0 || (d->n_wide > 0 && (!d->wide_inputs || !d->wide_lut_offset || !d->wide_lut)))
+    return fail(PBN_ERR_INVALID, "n_wide=%d but wide tables missing", d->n_wide);
   uint32_t sel_block_mask = 0, max_arity = 0;
   for (int i = 0; i < N; ++i) {
     const int f0 = d->func_offset[i], f1 = d->func_offset[i + 1];
@@ -244,8 +251,27 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
     if (f1 - f0 > 1) sel_block_mask |= 1u << (i >> 2);
     for (int f = f0; f < f1; ++f) {
       const int k = d->func_arity[f];
-      if (k > PBN_MAX_ARITY) return fail(PBN_ERR_UNSUPPORTED, "function %d has arity %d > %d", f, k, PBN_MAX_ARITY);
+      if (k > PBN_MAX_WIDE_ARITY) return fail(PBN_ERR_UNSUPPORTED, "function %d has arity %d > %d", f, k, PBN_MAX_WIDE_ARITY);
       max_arity = k > (int)max_arity ? (uint32_t)k : max_arity;
+      if (k > PBN_MAX_ARITY) {  // wide predictor: multi-word truth table
+        const uint64_t v = d->func_lut[f];
+        if (v >= (uint64_t)d->n_wide) return fail(PBN_ERR_INVALID, "function %d: wide index %llu out of range", f, (unsigned long long)v);
+        const int64_t words = (int64_t)d->wide_lut_offset[v + 1] - d->wide_lut_offset[v];
+        if (d->wide_lut_offset[v] < 0 || words != (1ll << (k - 6))) return fail(PBN_ERR_INVALID, "function %d: wide truth table has %lld words, arity %d needs %lld", f, (long long)words, k, 1ll << (k - 6));
+        WideDesc& wd = wides[v];
+        memset(&wd, 0, sizeof(wd));
+        for (int j = 0; j < k; ++j) {
+          wd.in[j] = d->wide_inputs[v * 16 + j];
+          if (wd.in[j] >= N) return fail(PBN_ERR_INVALID, "function %d input %d out of range", f, j);
+        }
+        wd.lut_off = (uint32_t)d->wide_lut_offset[v];
+        wd.arity = (uint32_t)k;
+        funcs[f].lut_lo = (uint32_t)v;
+        funcs[f].lut_hi = 0;
+        funcs[f].in03 = 0;
+        funcs[f].in47 = kWideMarker;
+        continue;
+      }
       uint8_t in[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int j = 0; j < k; ++j) {
         in[j] = d->func_inputs[f * PBN_FUNC_INPUT_STRIDE + j];
@@ -272,7 +298,11 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
   }
 
   std::string why;
-  const bool can_slice = jit::eligible(d, &why);
+  bool can_slice = jit::eligible(d, &why);
+  if (max_arity > PBN_MAX_ARITY) {
+    can_slice = false;
+    why = "predictor with more than 6 inputs";
+  }
   int kernel = d->kernel;
   if (kernel == PBN_KERNEL_AUTO) kernel = can_slice ? PBN_KERNEL_SLICED : PBN_KERNEL_SCALAR;
   if (kernel != PBN_KERNEL_SCALAR && kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_INVALID, "kernel kind %d unknown", d->kernel);
@@ -300,6 +330,13 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
     pbn_destroy(h);
     return rc;
   }
+  if (d->n_wide > 0) {
+    if ((rc = upload(&h->d_wide, wides.data(), wides.size())) != PBN_OK ||
+        (rc = upload(&h->d_wide_lut, d->wide_lut, (size_t)d->wide_lut_offset[d->n_wide])) != PBN_OK) {
+      pbn_destroy(h);
+      return rc;
+    }
+  }
   {
     const unsigned int zero = 0;
     if ((rc = upload(&h->d_ticket, &zero, 1)) != PBN_OK) {
@@ -317,6 +354,8 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
   }
   NetParams& n = h->net;
   n.surv_sliced = h->d_surv_sliced;
+  n.wide = h->d_wide;
+  n.wide_lut = h->d_wide_lut;
   n.func_offset = h->d_func_offset;
   n.funcs = h->d_funcs;
   n.func_cum = h->d_func_cum;
@@ -433,6 +472,7 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   const int block = 256;
   const int grid = grid_for(h, a->n_envs, block, 8);
   const bool wide = h->net.max_arity > 4;
+  const bool xwide = h->net.max_arity > PBN_MAX_ARITY;
 #define PBN_LAUNCH_SCALAR(WW, MA)                                                                          \
   do {                                                                                                     \
     if (L.total > 48u * 1024u && !h->scalar_smem_opted) {                                                  \
@@ -441,9 +481,9 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
     step_scalar_kernel<WW, MA><<<grid, block, L.total, stream>>>(p, L);                                    \
   } while (0)
   if (h->W == 1) {
-    if (wide) PBN_LAUNCH_SCALAR(1, 6); else PBN_LAUNCH_SCALAR(1, 4);
+    if (xwide) PBN_LAUNCH_SCALAR(1, 16); else if (wide) PBN_LAUNCH_SCALAR(1, 6); else PBN_LAUNCH_SCALAR(1, 4);
   } else {
-    if (wide) PBN_LAUNCH_SCALAR(2, 6); else PBN_LAUNCH_SCALAR(2, 4);
+    if (xwide) PBN_LAUNCH_SCALAR(2, 16); else if (wide) PBN_LAUNCH_SCALAR(2, 6); else PBN_LAUNCH_SCALAR(2, 4);
   }
 #undef PBN_LAUNCH_SCALAR
   PBN_CUDA(cudaGetLastError());

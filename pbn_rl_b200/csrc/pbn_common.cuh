@@ -18,6 +18,16 @@ struct __align__(16) FuncDesc {
   uint32_t in47;  // inputs 4..7
 };
 
+// A wide predictor (arity 7..16): 16 input gene indices + where its truth table starts in wide_lut.
+// Its FuncDesc carries in47 = kWideMarker (0xFF is never a gene index) and lut_lo = index into this table.
+struct __align__(16) WideDesc {
+  uint8_t in[16];
+  uint32_t lut_off;   // in 64-bit words
+  uint32_t arity;
+  uint32_t pad[2];
+};
+constexpr uint32_t kWideMarker = 0xFFFFFFFFu;
+
 // Everything a kernel needs besides the per-call arrays.  Passed by value (__grid_constant__).
 struct NetParams {
   const int32_t* func_offset;   // [N+1]
@@ -38,7 +48,21 @@ struct NetParams {
   uint32_t pert_rng;             // 1: draw perturbations from the stream (perturb_p > 0)
   uint32_t attr_simple;          // 1: every attractor is a single fully specified state (no wildcards)
   uint32_t rk[20];               // Philox round keys (k0 + r*W0, k1 + r*W1), r = 0..9: constant-bank operands
+  const WideDesc* wide;          // [n_wide] or nullptr
+  const uint64_t* wide_lut;      // multi-word truth tables of the wide predictors
 };
+
+// Value of a wide predictor in state s (gather up to 16 state bits, look the bit up in global memory / L1).
+template <int W>
+__device__ __forceinline__ uint32_t eval_wide(const NetParams& n, uint32_t v, const uint64_t (&s)[W]) {
+  const WideDesc wd = n.wide[v];
+  uint32_t idx = 0;
+  for (uint32_t j = 0; j < wd.arity; ++j) {
+    const uint32_t g = wd.in[j];
+    idx |= (uint32_t)((s[W == 1 ? 0 : (g >> 6)] >> (g & 63u)) & 1ull) << j;
+  }
+  return (uint32_t)(n.wide_lut[wd.lut_off + (idx >> 6)] >> (idx & 63u)) & 1u;
+}
 
 struct StepParams {
   pbn_step_args a;

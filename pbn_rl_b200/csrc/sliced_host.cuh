@@ -45,6 +45,11 @@ inline bool eligible(const pbn_net_desc* d, std::string* why) {
       if (why) *why = "gene with more than 4 predictors";
       return false;
     }
+    for (int k = 0; k < K; ++k)
+      if (d->func_arity[f0 + k] > PBN_MAX_ARITY) {
+        if (why) *why = "predictor with more than 6 inputs";
+        return false;
+      }
     for (int k = 0; k + 1 < K; ++k) {
       const double want = std::floor((double)(k + 1) / K * 4294967296.0 + 0.5);
       if (std::fabs((double)d->func_cum[f0 + k] - want) > 2.0) {

@@ -48,7 +48,8 @@ __device__ __forceinline__ uint32_t state_bit(const uint64_t (&s)[W], uint32_t g
   }
 }
 
-// MAXA = 4: truth tables are 16-bit (replicated), 4 gathers per gene; MAXA = 6: 64-bit, 6 gathers.
+// MAXA = 4: truth tables are 16-bit (replicated), 4 gathers per gene; MAXA = 6: 64-bit, 6 gathers;
+// MAXA = 16: as 6, plus wide predictors (multi-word tables in global memory).
 template <int W, int MAXA>
 __global__ void __launch_bounds__(256) step_scalar_kernel(const __grid_constant__ StepParams p,
                                                          const ScalarSmemLayout L) {
@@ -138,9 +139,15 @@ __global__ void __launch_bounds__(256) step_scalar_kernel(const __grid_constant_
       }
       const FuncDesc fd = s_funcs[fo + k];
       uint32_t idx = 0;
+      uint32_t bit;
+      if (MAXA > 6 && fd.in47 == kWideMarker) {
+        bit = eval_wide<W>(n, fd.lut_lo, s);
+        if constexpr (W == 1) f[0] |= (uint64_t)bit << i;
+        else f[i >> 6] |= (uint64_t)bit << (i & 63);
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) idx |= state_bit<W>(s, (fd.in03 >> (8 * j)) & 0xFFu) << j;
-      uint32_t bit;
       if constexpr (MAXA == 4) {
         bit = (fd.lut_lo >> idx) & 1u;
       } else {

@@ -30,7 +30,7 @@ import numpy as np
 from .attractors import AttractorSet, find_attractors_stg, load_attractor_pickle, sorted_id_permutation
 from .network import PBNNetwork
 
-__all__ = ["PBNEnv", "make", "register_gym_ids", "Graph", "Node", "Discrete", "Box", "ENV_IDS"]
+__all__ = ["PBNEnv", "ControlPBNEnv", "make", "register_gym_ids", "Graph", "Node", "Discrete", "Box", "ENV_IDS"]
 
 MAX_ACTIONS = 8  # PBN_MAX_BINS
 
@@ -333,6 +333,33 @@ class PBNEnv:
         self.vec.close()
 
 
+class ControlPBNEnv(PBNEnv):
+    """``gym.make("gym-PBN/ControlPBNEnv", ..., control_nodes=[...])`` (train_control_gbdq.py:45-72): only
+    the listed genes can be intervened on.  The control agent has one *binary* branch per control node
+    (``GraphBranchingQNetwork(observation, 2, len(env.control_nodes))``, control_gbdq_model/__init__.py:35-38)
+    and passes the length-``len(control_nodes)`` 0/1 vector to ``env.step`` (:66-86,169): entry ``i`` = 1 flips
+    gene ``control_nodes[i]``.  Indices are 0-based positions in ``genes``; entries outside ``[0, N)`` (the
+    reference's own example lists node 14 for a 14-gene network) are kept in ``control_nodes`` so the
+    agent's branch count matches, but are inert."""
+
+    def __init__(self, *args, control_nodes: Sequence[int] = (), **kwargs):
+        super().__init__(*args, **kwargs)
+        self.control_nodes = [int(c) for c in control_nodes]
+        if sum(1 for c in self.control_nodes if 0 <= c < self.N) > MAX_ACTIONS:
+            raise ValueError("at most %d controllable genes are supported" % MAX_ACTIONS)
+        self.action_space = Box(0, 1, (len(self.control_nodes),), np.int8)
+        self.discrete_action_space = Discrete(2)
+
+    def step(self, action):
+        bits = _as_int_list(action)
+        if len(bits) != len(self.control_nodes):
+            raise ValueError("control action has %d entries, env has %d control nodes" % (len(bits), len(self.control_nodes)))
+        if any(b not in (0, 1) for b in bits):
+            raise ValueError("control actions are 0/1 per control node")
+        flips = [c + 1 for b, c in zip(bits, self.control_nodes) if b and 0 <= c < self.N]
+        return super().step(flips)
+
+
 # --------------------------------------------------------------------------------------
 # gym.make-style construction
 # --------------------------------------------------------------------------------------
@@ -385,8 +412,7 @@ def make(env_id: str, root: Union[str, Path, None] = None, **kwargs) -> PBNEnv:
     if short in ("PBNEnv", "PBN"):
         return PBNEnv(**kwargs)
     if short == "ControlPBNEnv":
-        kwargs.pop("control_nodes", None)  # restricted control sets: accepted, not yet enforced
-        return PBNEnv(**kwargs)
+        return ControlPBNEnv(**kwargs)
     raise ValueError("unknown env id %r (known: %s)" % (env_id, ", ".join(ENV_IDS)))
 
 

@@ -22,7 +22,8 @@ from .ispl import BoolFunction, IsplError, compile_expression, parse_ispl, rende
 __all__ = ["PBNNetwork", "MAX_GENES", "MAX_ARITY", "pack_states", "unpack_states", "words_for"]
 
 MAX_GENES = 128  # two 64-bit words per state
-MAX_ARITY = 6  # 64-bit truth tables in the device descriptors
+MAX_ARITY = 16  # PBN_MAX_WIDE_ARITY: up to 6 inputs use a 64-bit truth table, 7..16 a multi-word one (scalar kernel)
+NARROW_ARITY = 6  # PBN_MAX_ARITY
 
 
 def words_for(n_genes: int) -> int:
@@ -186,14 +187,22 @@ class PBNNetwork:
         n = self.n_genes
         offs = np.zeros(n + 1, dtype=np.int32)
         arity, inputs, luts, cum = [], [], [], []
+        wide_inputs, wide_offs, wide_words = [], [0], []
         for i, (fs, ps) in enumerate(zip(self.functions, self.probabilities)):
             offs[i + 1] = offs[i] + len(fs)
             acc = 0.0
             for k, (f, p) in enumerate(zip(fs, ps)):
                 arity.append(f.arity)
-                row = list(f.inputs) + [0] * (8 - f.arity)
-                inputs.append(row)
-                luts.append(f.lut)
+                if f.arity > NARROW_ARITY:      # wide predictor: multi-word truth table, func_lut = its index
+                    inputs.append([0] * 8)
+                    luts.append(len(wide_inputs))
+                    wide_inputs.append(list(f.inputs) + [0] * (16 - f.arity))
+                    nw = 1 << (f.arity - 6)
+                    wide_words += [(f.lut >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(nw)]
+                    wide_offs.append(wide_offs[-1] + nw)
+                else:
+                    inputs.append(list(f.inputs) + [0] * (8 - f.arity))
+                    luts.append(f.lut)
                 acc += p
                 # cumulative threshold in 2^-32 units; the last one is pinned to 2^32-1 (inclusive top)
                 thr = 0xFFFFFFFF if k == len(fs) - 1 else min(int(round(acc * 4294967296.0)), 0xFFFFFFFF)
@@ -204,6 +213,9 @@ class PBNNetwork:
             "func_inputs": np.asarray(inputs, dtype=np.uint8).reshape(-1, 8),
             "func_lut": np.asarray(luts, dtype=np.uint64),
             "func_cum": np.asarray(cum, dtype=np.uint32),
+            "wide_inputs": np.asarray(wide_inputs, dtype=np.uint8).reshape(-1, 16),
+            "wide_lut_offset": np.asarray(wide_offs, dtype=np.int32),
+            "wide_lut": np.asarray(wide_words, dtype=np.uint64),
         }
 
     # ---------------------------------------------------------------- writers

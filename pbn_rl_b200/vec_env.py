@@ -66,6 +66,11 @@ def make_desc(network: PBNNetwork, bins: int = 3, horizon: int = 20, perturb_p: 
     d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.device = int(device)
     d.kernel = _cabi.KERNEL_KINDS[kernel]
+    d.n_wide = int(arr["wide_inputs"].shape[0])
+    if d.n_wide:
+        d.wide_inputs = arr["wide_inputs"].ctypes.data
+        d.wide_lut_offset = arr["wide_lut_offset"].ctypes.data
+        d.wide_lut = arr["wide_lut"].ctypes.data
     return d, arr
 
 

@@ -31,10 +31,29 @@ def test_library_exports_every_header_symbol():
     assert b"sm_100a" in lib.pbn_version()
 
 
-def test_struct_layouts_match_the_header():
-    # sizes computed by hand from include/pbn_b200.h on LP64
-    assert C.sizeof(_cabi.NetDesc) == 112
-    assert C.sizeof(_cabi.StepArgs) == 13 * 8 + 8 + 8 + 8 + 4 + 4
+def test_struct_layouts_match_the_header(tmp_path):
+    """gcc compiles include/pbn_b200.h (it is plain C) and prints sizeof/offsetof of every struct and field;
+    the ctypes mirrors in pbn_rl_b200/_cabi.py must agree field by field."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    structs = {"pbn_net_desc": _cabi.NetDesc, "pbn_step_args": _cabi.StepArgs, "pbn_host_io": _cabi.HostIO,
+               "pbn_replay": _cabi.Replay}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "pbn_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", str(root / "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_no_silent_cpu_fallback():
