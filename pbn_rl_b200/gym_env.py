@@ -177,7 +177,15 @@ class PBNEnv:
         self.network = network
         self.N = network.n_genes
         if attractors is None:
-            attractors, _ = find_attractors_stg(network)  # exhaustive sink-SCC search (N <= 20)
+            if network.n_genes <= 16:
+                attractors, _ = find_attractors_stg(network)  # exhaustive sink-SCC search on the host
+            else:
+                # large networks: massive GPU rollouts + device closure search (exact attractors with a
+                # sampled basin; pbn_rl_b200/discover.py), most visited first, capped like the fork's tables
+                from .discover import find_attractors_rollout
+                attractors, info = find_attractors_rollout(network, n_rollouts=1 << 16, burn_in=256, device=device,
+                                                           seed=0x5EED if seed is None else int(seed))
+                self.attractor_search = info
         if min_attractors is not None and len(attractors) < int(min_attractors):
             raise ValueError("found %d attractors, min_attractors=%s" % (len(attractors), min_attractors))
         self.horizon = int(horizon)

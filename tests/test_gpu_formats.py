@@ -116,3 +116,25 @@ def test_control_env_protocol():
     with pytest.raises(ValueError):
         env.step([1, 0, 0])
     env.close()
+
+
+def test_pbnenv_from_reference_parser_output_finds_attractors_on_the_gpu():
+    """train_assa_BQN.py:121-124: gym.make("gym-PBN/PBNEnv", N=, genes=, logic_functions=) with what the
+    reference's ISPL parser produced for models/bb33/bb33.ispl.  N = 33: the attractor table comes from
+    GPU rollouts + the device closure search; every attractor must be closed under the network's update."""
+    import torch
+    from pbn_rl_b200 import make
+    want = _golden("bb33_expected.json")
+    env = make("gym-PBN/PBNEnv", N=33, genes=want["genes"], logic_functions=[[(e, 1.0)] for e in want["python_exprs"]],
+               min_attractors=1)
+    assert len(env.all_attractors) >= 1 and sum(env.attractor_search["basin_fraction"]) > 0.9
+    net = env.network
+    for members in env.attractor_search["states"]:
+        mset = set(members)
+        for s in members[:64]:             # a Boolean network: exactly one successor per state
+            assert net.next_state_int(s, [0] * 33) in mset
+    (state, target), _ = env.reset()
+    assert env.is_attracting_state(state) and len(target) == 33
+    s, r, term, trunc, _ = env.step(torch.tensor([0, 0, 0]))
+    assert env.is_attracting_state(s)      # no intervention: the state stays inside its attractor
+    env.close()
