@@ -220,8 +220,8 @@ def workload_config(args, world, kernel):
         "horizon": 20, "perturb_p": 0.001, "perturb_mode": "A", "auto_reset": True,
         "actions": "uniform in [0,N], pre-generated on device, pool of %d buffers" % args.action_pool,
         "l2": "%d rotating env batches + action pool: working set > 126 MB L2, no flush" % args.batches,
-        "graph_steps": args.graph_steps, "kernel": kernel,
-        "launch": "CUDA graph of %d step launches%s" % (args.graph_steps, "" if getattr(args, "no_pdl", False) else
+        "graph_steps": min(args.graph_steps, max(1, args.steps or 1)), "kernel": kernel,
+        "launch": "CUDA graph of %d step launches%s" % (min(args.graph_steps, max(1, args.steps or 1)), "" if getattr(args, "no_pdl", False) else
                                                         ", programmatic dependent launch (selection planes drawn under the previous kernel's tail)"), "parallelism": "env-sharded x%d" % world,
     }
 
@@ -265,8 +265,9 @@ def run_gpu(args):
             for _ in range(args.action_pool)]
     kernel = envs[0].kernel
 
-    G = args.graph_steps
-    K = max(G, (args.steps // G) * G)
+    K = max(1, args.steps)                     # EXACTLY K timed steps: K // G replays of a G-step graph + one tail graph
+    G = min(args.graph_steps, K)
+    tail_steps = K % G
     Wm = max(3, args.warmup)
     stream = torch.cuda.Stream(device)
     stats_total = torch.zeros(8, dtype=torch.int64, device=device)
@@ -287,8 +288,16 @@ def run_gpu(args):
             for e in envs:
                 e.advance_counter()   # PDL launches do not bump the device step counter themselves
         graph.replay()
+        tail = None
+        if tail_steps:
+            tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(tail, stream=stream):
+                for i in range(tail_steps):
+                    enqueue(i)
+                for e in envs:
+                    e.advance_counter()
+            tail.replay()
         stream.synchronize()
-        launches0 = sum(e.launches for e in envs)
 
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -299,6 +308,8 @@ def run_gpu(args):
         ev0.record(stream)
         for _ in range(K // G):
             graph.replay()
+        if tail is not None:
+            tail.replay()
         ev1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
