@@ -171,6 +171,8 @@ typedef struct {
   int64_t n_envs;               /* E */
   uint32_t flags;               /* PBN_STEP_* */
   uint32_t reserved;
+  const uint32_t* sel_planes;   /* [pbn_planes_words()] predictor-selection planes of THIS step drawn earlier by
+                                   pbn_predraw (sliced kernel only), or NULL: the step draws them itself */
 } pbn_step_args;
 
 /* gym.make(...) construction: upload truth tables and constants, pick the kernel. */
@@ -218,6 +220,16 @@ typedef struct {
  * until the host outputs are complete (like the reference's env.step it returns values); it waits
  * on its own streams only, never on the whole device. */
 int pbn_step_host(pbn_handle* h, const pbn_step_args* args, const pbn_host_io* io, void* stream);
+
+/* Split launch (sliced kernel): the predictor-selection planes of a step depend only on (seed, env ids,
+ * step counter), never on the state, so they can be drawn ahead of time -- pbn_predraw for step k+1 on a
+ * second stream runs concurrently with pbn_step for step k (its Philox multiplies use the FMA pipe, the
+ * step's logic the ALU pipe).  pbn_predraw reads args->step_ctr / step_ctr_dev / env_offset / n_envs exactly
+ * as the pbn_step call that will consume the planes (same values => bit-identical results to the fused
+ * step); planes: DEVICE buffer of pbn_planes_words(h, n_envs) 32-bit words, passed to that pbn_step as
+ * args->sel_planes.  Returns PBN_ERR_UNSUPPORTED for handles running the scalar kernel. */
+int pbn_predraw(pbn_handle* h, const pbn_step_args* args, uint32_t* planes, void* stream);
+int64_t pbn_planes_words(const pbn_handle* h, int64_t n_envs);
 
 /* The same step with injected predictor choices / perturbation masks: the parity entry point
  * (deterministic core T of SURVEY.md 8a-4).  args->sel must be non-NULL. */

@@ -85,6 +85,8 @@ struct pbn_handle {
   jit::GenNet gen;
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
   cudaKernel_t jit_kernel[2] = {nullptr, nullptr};
+  cudaKernel_t predraw_kernel = nullptr;  // pbn_predraw_sliced of the own-RNG specialisation
+  std::vector<uint32_t> surv_sliced_host;  // copied into every loaded specialisation's constant memory
   int sliced_threads = 128, sliced_min_blocks = 1;
   uint32_t jit_smem_opt_in[2] = {48u * 1024u, 48u * 1024u};
   uint64_t launches = 0;
@@ -103,6 +105,14 @@ static int load_sliced(pbn_handle* h, int injected) {
   if (jit::compile(h->gen, injected != 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
   PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
+  if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->predraw_kernel, h->jit_lib[0], "pbn_predraw_sliced"));
+  if (!injected) {  // the survival table of the perturbation sub-streams lives in the specialisation's constant memory
+    void* dptr = nullptr;
+    size_t bytes = 0;
+    PBN_CUDA(cudaLibraryGetGlobal(&dptr, &bytes, h->jit_lib[injected], "_ZN3pbn10kSurvTableE"));
+    if (bytes != h->surv_sliced_host.size() * sizeof(uint32_t)) return fail(PBN_ERR_JIT, "kSurvTable has %zu bytes, expected %zu", bytes, h->surv_sliced_host.size() * sizeof(uint32_t));
+    PBN_CUDA(cudaMemcpy(dptr, h->surv_sliced_host.data(), bytes, cudaMemcpyHostToDevice));
+  }
   h->sliced_threads = jit::sliced_threads(h->gen);
   h->sliced_min_blocks = jit::sliced_min_blocks(h->gen);
   return PBN_OK;
@@ -347,6 +357,7 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
   if (kernel == PBN_KERNEL_SLICED) {
     h->gen = jit::gen_net_from_desc(d);
     const std::vector<uint32_t> ss = jit::sliced_survival(d->perturb_p, N);
+    h->surv_sliced_host = ss;
     if ((rc = upload(&h->d_surv_sliced, ss.data(), ss.size())) != PBN_OK || (rc = load_sliced(h, 0)) != PBN_OK) {
       pbn_destroy(h);
       return rc;
@@ -449,6 +460,8 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   if (!a->state) return fail(PBN_ERR_INVALID, "state is null");
   if (injected && !a->sel) return fail(PBN_ERR_INVALID, "pbn_step_injected needs args->sel");
   if (!injected && (a->sel || a->pert_mask)) return fail(PBN_ERR_INVALID, "pbn_step: sel/pert_mask must be null (use pbn_step_injected)");
+  if (a->sel_planes && (injected || h->kernel != PBN_KERNEL_SLICED)) return fail(PBN_ERR_UNSUPPORTED, "sel_planes: pre-drawn selection planes are taken by pbn_step with the sliced kernel only");
+  if (a->sel_planes && (reinterpret_cast<uintptr_t>(a->sel_planes) & 15u)) return fail(PBN_ERR_INVALID, "sel_planes must be 16-byte aligned");
   if (a->env_offset < 0 || (a->env_offset & 1023)) return fail(PBN_ERR_INVALID, "env_offset=%lld must be a non-negative multiple of 1024", (long long)a->env_offset);
   if (a->target_id && h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "target_id given but no attractor table uploaded");
   if ((a->flags & PBN_STEP_PDL) && !a->step_ctr_dev) return fail(PBN_ERR_INVALID, "PBN_STEP_PDL needs step_ctr_dev");
@@ -520,6 +533,37 @@ int pbn_jit_precompile(const pbn_net_desc* d) {
 }
 
 int pbn_step(pbn_handle* h, const pbn_step_args* a, void* stream) { return step_common(h, a, stream, false); }
+
+int64_t pbn_planes_words(const pbn_handle* h, int64_t n_envs) {
+  if (!h || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "selection planes exist for the sliced kernel only");
+  const int64_t tiles = (n_envs + 1023) / 1024;
+  const int64_t words = tiles * 2 * jit::n_sel_slots(h->gen) * 32;
+  return words > 0 ? words : 4;  // never an empty buffer
+}
+
+int pbn_predraw(pbn_handle* h, const pbn_step_args* a, uint32_t* planes, void* stream_) {
+  if (!h || !a || !planes) return fail(PBN_ERR_INVALID, "null argument");
+  if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "pbn_predraw: the handle runs the scalar kernel");
+  if (a->n_envs < 0 || a->env_offset < 0 || (a->env_offset & 1023)) return fail(PBN_ERR_INVALID, "bad n_envs / env_offset");
+  if (reinterpret_cast<uintptr_t>(planes) & 15u) return fail(PBN_ERR_INVALID, "planes must be 16-byte aligned");
+  if (a->n_envs == 0 || jit::n_sel_slots(h->gen) == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  int rc = load_sliced(h, 0);
+  if (rc != PBN_OK) return rc;
+  StepParams p;
+  p.a = *a;
+  p.n = h->net;
+  p.ticket = h->d_ticket;
+  int64_t grid = (a->n_envs + 1023) / 1024;
+  const int64_t cap = (int64_t)h->num_sms * 32;
+  if (grid > cap) grid = cap;
+  void* args[] = {&p, &planes};
+  PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(h->predraw_kernel), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, 0, stream));
+  h->launches += 1;
+  return PBN_OK;
+}
 
 int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, void* stream_) {
   if (!h || !a || !io) return fail(PBN_ERR_INVALID, "null argument");

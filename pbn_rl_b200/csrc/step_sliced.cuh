@@ -64,7 +64,12 @@ constexpr int kScrPl = kScrRows + kNW * 32 * 32;     // PL input planes         
 constexpr int kScrSel0 = kScrPl + kNW * 32 * 32;     // selection planes s0          [PBN_NSEL][32]
 constexpr int kScrSel1 = kScrSel0 + PBN_NSEL * 32;   // selection planes s1          [PBN_NSEL][32]
 constexpr int kScrStat = kScrSel1 + PBN_NSEL * 32;   // 8 block-level statistics counters
-constexpr int kScrWords = kScrStat + 8;              // total (must equal PBN_SCRATCH_WORDS)
+constexpr int kScrEv = kScrStat + 8;                 // pre-drawn perturbation events, one packed word per thread [128]
+constexpr int kScrWords = kScrEv + 128;              // total (must equal PBN_SCRATCH_WORDS)
+constexpr uint32_t kPreEvOverflow = 0x80000000u;     // event walk not finished within its first Philox block: phase D redoes it
+static_assert(kSlots <= 1024, "pre-drawn event positions are packed in 10 bits");
+constexpr int kPlaneWords = 2 * PBN_NSEL * 32;       // pre-drawn selection planes of one tile: [sel0 | sel1][slot][lane]
+static_assert((kScrSel0 * 4) % 16 == 0, "TMA destination of the selection planes must be 16-byte aligned");
 static_assert(kScrWords == PBN_SCRATCH_WORDS, "host and device disagree on the scratch size");
 static_assert(PBN_THREADS == 32 * kWarps, "one tile per 4-warp CTA");
 
@@ -148,7 +153,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // Development aid: with flag bit 31 set, thread 0 of CTA 0 writes %globaltimer stamps (ns) of the phase
 // boundaries into final_state[E*W .. E*W+15], and thread 0 of every CTA its start/end stamps (+ SM id in
-// the top byte) into final_state[E*W + 16 + 2*blockIdx + {0,1}]: the caller provides the extra words.
+// the top byte) into final_state[E*W + 16 + 8*blockIdx + {0,7}] (1: input copy arrived, 2: out planes done,
+// 3..6: after phases E, D, F, G):
+// the caller provides the extra words.
 __device__ __forceinline__ void phase_stamp(const pbn_step_args& a, int i) {
   if ((a.flags & 0x80000000u) && blockIdx.x == 0 && threadIdx.x == 0 && a.final_state != nullptr) {
     unsigned long long t;
@@ -162,7 +169,7 @@ __device__ __forceinline__ void cta_stamp(const pbn_step_args& a, int which) {
     unsigned int smid;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    a.final_state[a.n_envs * kW64 + 16 + 2 * blockIdx.x + which] =
+    a.final_state[a.n_envs * kW64 + 16 + 8 * blockIdx.x + which] =
         (t & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)smid << 56);
   }
 }
@@ -218,13 +225,17 @@ __device__ __forceinline__ void sel_slot(uint64_t gid, uint64_t step, const uint
   s1 = b1;
 }
 
+// Survival table S[j] = floor((1-p)^j 2^32), j = 0..8N, of the perturbation sub-streams: filled per handle after
+// the library is loaded (constant memory: the look-ups of the geometric skip are data-dependent and
+// lane-divergent; from global memory each step of the search cost a DRAM/L2 round trip, ~2 us per event).
+__constant__ uint32_t kSurvTable[kSlots + 1];
+
 // Next event distance of the perturbation stream.
-// (cold path; the table stays in global memory / L1: it is touched by a few lanes per tile only)
-__device__ __noinline__ int pert_search(const uint32_t* __restrict__ surv, uint32_t u) {
-  int lo = 0, hi = kSlots;  // invariant: u < surv[lo] (surv[0] = 2^32 conceptually)
+__device__ __noinline__ int pert_search(uint32_t u) {
+  int lo = 0, hi = kSlots;  // invariant: u < S[lo] (S[0] = 2^32 conceptually)
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (u < __ldg(surv + mid)) lo = mid; else hi = mid - 1;
+    if (u < kSurvTable[mid]) lo = mid; else hi = mid - 1;
   }
   return lo + 1;
 }
@@ -234,6 +245,34 @@ __device__ __noinline__ int pert_search(const uint32_t* __restrict__ surv, uint3
 #include "net_update.inc"  // generated: kSelGene[], kSelK[], pbn::pbn_update_part(w, PL, OPL, SEL0, SEL1)
 
 namespace pbn {
+
+#if !PBN_INJECTED
+// Perturbation events of this thread's (column, warp) sub-stream for one step.  They depend only on
+// (column id, step counter, seed), so they are drawn early -- under the previous kernel's tail with
+// programmatic dependent launch, else behind the tile's TMA copy -- and phase D only applies them: the
+// Philox block and the dependent table look-ups of the geometric skip are a pure latency chain
+// (≈2 us per tile when it sat in D).  One packed word per thread (kPreEvOverflow: D redoes the walk).
+__device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* ev, uint64_t gid, uint64_t step_ctr, uint32_t w) {
+  uint32_t word = 0u;   // bits 0-1: count, bits 2-11 / 12-21 / 22-31: up to three slot positions
+  if (n.pert_rng && n.pert_mode != PBN_PERT_NONE) {
+    const uint32_t s_last = kSurvTable[kSlots];
+    const Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
+    int pos = -1;
+    uint32_t cnt = 0u;
+    bool done = false;
+#pragma unroll 1
+    for (uint32_t k = 0; k < 4u; ++k) {   // the four draws of the sub-stream's first block: <= 3 events + the terminating draw
+      const uint32_t u = pick4(blk, k);
+      pos += (u < s_last) ? kSlots + 1 : pert_search(u);
+      if (pos >= kSlots) { done = true; break; }
+      if (k < 3u) word |= (uint32_t)pos << (2u + 10u * k);
+      cnt = k + 1u;
+    }
+    word = done ? (word | cnt) : kPreEvOverflow;   // not finished within the block: phase D redoes the walk
+  }
+  ev[0] = word;
+}
+#endif
 
 // Stage the small read-only tables into shared memory (first tile of a CTA, after its global loads
 // were issued; everything staged here is first read after block barrier (1)).
@@ -318,6 +357,11 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   uint32_t* sel1 = scr + kScrSel1 + lane;
   uint32_t* s_stat = scr + kScrStat;
 
+#if PBN_INJECTED
+  constexpr bool planes_given = false;
+#else
+  const bool planes_given = a.sel_planes != nullptr;  // block-uniform
+#endif
   phase_stamp(a, 0);
   // ---- A0. start the tile's input traffic (consumed after C1, which hides the latency) ---------------
   // full tiles: one thread issues two TMA bulk copies (8 KB*W of state, 1024*BINS action bytes) into the
@@ -325,9 +369,12 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   if (FULL && threadIdx.x == 0) {
     fence_proxy_async();  // the previous tile's generic-proxy reads of the staging buffers are done
     const uint32_t sbytes = 1024u * 8u * kW64, abytes = 1024u * PBN_BINS;
-    mbar_expect_tx(mbar, sbytes + (a.actions != nullptr ? abytes : 0u));
+    const uint32_t pbytes = (planes_given && PBN_NSEL > 0) ? kPlaneWords * 4u : 0u;
+    mbar_expect_tx(mbar, sbytes + (a.actions != nullptr ? abytes : 0u) + pbytes);
     tma_load_1d(st_state, a.state + tile * 1024 * kW64, sbytes, mbar);
     if (a.actions != nullptr) tma_load_1d(st_act, a.actions + tile * 1024 * PBN_BINS, abytes, mbar);
+    // selection planes drawn ahead of time by pbn_predraw: straight into the SEL scratch ([sel0 | sel1][slot][lane])
+    if (pbytes) tma_load_1d(scr + kScrSel0, a.sel_planes + tile * kPlaneWords, pbytes, mbar);
   }
   uint32_t nfp = 0u;     // 4-bit flip counts of the 8 envs
   uint32_t flips = 0u;
@@ -358,10 +405,17 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 1);
-  const bool c1_first = !pre_drawn && (tile & 1) == 0;  // pre_drawn: done before griddepcontrol.wait
+  // pre_drawn: done before griddepcontrol.wait.  Otherwise alternate between the CTAs that share an SM (CTAs
+  // b, b + #SMs, b + 2 #SMs, ... land on the same SM; the tile parity would not mix: 148 is even)
+  unsigned int nsm;
+  asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+  const bool c1_first = !pre_drawn && !planes_given && ((tile / (int64_t)nsm) & 1) == 0;
   if (stage && !c1_first) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);
   phase_stamp(a, 2);
   const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
+#if !PBN_INJECTED
+  if (!pre_drawn) draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w);  // behind the TMA copy
+#endif
   // ---- C1 (even tiles: here, hiding the load latency; odd tiles: after B, so that neighbouring
   //      CTAs of the single wave are in different phases and share the SM's issue slots better)
   if (c1_first) {
@@ -373,6 +427,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   if (FULL) {
     mbar_wait(mbar, tma_parity);
     tma_parity ^= 1u;
+    cta_stamp(a, 1);
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const int le = 4 * (int)lane + 128 * (2 * (int)w + g);  // env index inside the tile
@@ -434,7 +489,15 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 6);
-  if (!c1_first && !pre_drawn) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
+  if (!c1_first && !pre_drawn && !planes_given) draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
+  if (!FULL && planes_given) {  // ragged tile: no TMA, plain loads of the pre-drawn planes
+    const uint32_t* gp = a.sel_planes + tile * kPlaneWords + lane;
+#pragma unroll 1
+    for (int r = (int)w; r < PBN_NSEL; r += kWarps) {
+      sel0[r * 32] = gp[r * 32];
+      sel1[r * 32] = gp[(PBN_NSEL + r) * 32];
+    }
+  }
   __syncthreads();  // (2) all input planes (and selection planes) are in scratch; S1 rows are dead
 
   // ---- C2. synchronous update of this warp's genes: generated LOP3 trees -> OPL planes ----------
@@ -442,6 +505,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   phase_stamp(a, 7);
   __syncthreads();  // (3) all out planes are in scratch
   phase_stamp(a, 8);
+  cta_stamp(a, 2);
 
   // target ids and episode counters of this warp's 8 envs: issued here, consumed in F (E and D hide them)
   uint32_t tg[8];
@@ -483,6 +547,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 9);
+  cta_stamp(a, 3);
   // ---- D. perturbation (row domain, sparse) ---------------------------------------------------------
   uint32_t npert = 0u;
   const int pert_mode = n.pert_mode;  // block-uniform
@@ -513,18 +578,9 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
 #else
     if (n.pert_rng) {
       // this warp's own event sub-stream: slots gene*8 + row over its 8 rows
-      const uint32_t s_last = __ldg(n.surv_sliced + kSlots);
-      uint32_t pert_next = 0u, M = 0u;
-      Philox4 pert_blk = {0u, 0u, 0u, 0u};
-      int pos = -1;
-      while (true) {
-        if ((pert_next & 3u) == 0u)
-          pert_blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
-        const uint32_t u = pick4(pert_blk, pert_next & 3u);
-        ++pert_next;
-        pos += (u < s_last) ? kSlots + 1 : pert_search(n.surv_sliced, u);
-        if (pos >= kSlots) break;
-        const uint32_t g = (uint32_t)pos >> 3, ib = (uint32_t)pos & 7u;
+      uint32_t M = 0u;
+      auto apply_event = [&](uint32_t pos) {
+        const uint32_t g = pos >> 3, ib = pos & 7u;
         const uint32_t m = 1u << (g & 31u), gw = g >> 5;
         const bool first = !((M >> ib) & 1u);
         M |= 1u << ib;
@@ -544,12 +600,34 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
               o[i][wd] = bmux(mm, ~rows[(wd * 32 + 8 * (int)w + i) * 32], o[i][wd]);
             }
           }
+      };
+      const uint32_t evw = scr[kScrEv + threadIdx.x];
+      if (evw != kPreEvOverflow) {
+        // the usual case: the events were drawn ahead of time (draw_pert_events)
+        const uint32_t cnt = evw & 3u;
+#pragma unroll 1
+        for (uint32_t k = 0; k < cnt; ++k) apply_event((evw >> (2u + 10u * k)) & 0x3FFu);
+      } else {
+        const uint32_t s_last = kSurvTable[kSlots];
+        uint32_t pert_next = 0u;
+        Philox4 pert_blk = {0u, 0u, 0u, 0u};
+        int pos = -1;
+        while (true) {
+          if ((pert_next & 3u) == 0u)
+            pert_blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
+          const uint32_t u = pick4(pert_blk, pert_next & 3u);
+          ++pert_next;
+          pos += (u < s_last) ? kSlots + 1 : pert_search(u);
+          if (pos >= kSlots) break;
+          apply_event((uint32_t)pos);
+        }
       }
     }
 #endif
   }
 
   phase_stamp(a, 10);
+  cta_stamp(a, 4);
   // ---- F. target test, counters, reward, stores ------------------------------------------------------
   uint32_t H = 0u, TR = 0u, VALID = 0u, len_sum = 0u;
   const uint32_t n_attr = (a.target_id != nullptr) ? (uint32_t)n.n_attr : 0u;
@@ -649,6 +727,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 11);
+  cta_stamp(a, 5);
   // ---- G. auto-reset of finished envs (sparse: scattered writes after the vector stores) ----------
   uint32_t D = (H | TR) & VALID;
   if (a.stats != nullptr) {
@@ -710,22 +789,28 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
   const int64_t n_tiles = (a.n_envs + 1023) >> 10;
   bool stage = true;
   bool pre_drawn = false;
+  // PBN_TUNE bit 2 (experiment): scramble the CTA -> tile map when every CTA owns exactly one tile
+  const int64_t first_tile = ((PBN_TUNE & 4) && (int64_t)gridDim.x == n_tiles) ? ((int64_t)blockIdx.x * 577) % n_tiles : (int64_t)blockIdx.x;
   if (a.flags & PBN_STEP_PDL) {
     // Programmatic dependent launch: let the next launch start as SM resources free up, draw this CTA's
     // first tile's selection planes (they depend on nothing the previous launch writes; the device step
     // counter is not bumped by PDL launches), then wait for the previous launch to complete and flush.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if ((int64_t)blockIdx.x < n_tiles) {
+    // everything of this CTA's first tile that does not depend on the state: selection planes, perturbation events
+    if ((int64_t)blockIdx.x < n_tiles && a.sel_planes == nullptr) {
       const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-      const int64_t tile = blockIdx.x;
+      const int64_t tile = first_tile;
       const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
       draw_selection_planes<false>(a, n, scr + kScrSel0 + lane, scr + kScrSel1 + lane, gid, step_ctr,
                                    tile * 1024 + 4 * (int64_t)lane, w);
+#if !PBN_INJECTED
+      draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w);
+#endif
       pre_drawn = true;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int64_t tile = first_tile; tile < n_tiles; tile += gridDim.x) {
     const bool full = (tile + 1) * 1024 <= a.n_envs;
     if (L.attractors_in_smem != 0u) {
       if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn);
@@ -736,6 +821,7 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
     stage = false;
     pre_drawn = false;
     phase_stamp(a, 12);
+    cta_stamp(a, 6);
     __syncthreads();  // scratch is reused by the next tile; statistics are complete
   }
   if (a.stats != nullptr && threadIdx.x < 7) {
@@ -743,9 +829,26 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
     if (x != 0u) atomicAdd(&a.stats[threadIdx.x], (unsigned long long)x);
   }
   phase_stamp(a, 13);
-  cta_stamp(a, 1);
+  cta_stamp(a, 7);
   bump_device_step(a, p.ticket);
   phase_stamp(a, 14);
 }
+
+#if !PBN_INJECTED
+// pbn_predraw: the selection planes of one step for every tile, into global memory.  Needs no shared
+// memory and few registers, so its CTAs fit next to the step kernel's on every SM.
+extern "C" __global__ void __launch_bounds__(PBN_THREADS, 12)
+pbn_predraw_sliced(const __grid_constant__ StepParams p, uint32_t* __restrict__ planes) {
+  const pbn_step_args& a = p.a;
+  const uint64_t step_ctr = effective_step(a);
+  const int64_t n_tiles = (a.n_envs + 1023) >> 10;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
+    uint32_t* base = planes + tile * kPlaneWords + lane;
+    draw_selection_planes<true>(a, p.n, base, base + PBN_NSEL * 32, gid, step_ctr, tile * 1024 + 4 * (int64_t)lane, w);
+  }
+}
+#endif
 
 }  // namespace pbn

@@ -13,7 +13,7 @@ import bench  # noqa: E402
 from pbn_rl_b200 import VecPBNEnv  # noqa: E402
 
 
-def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20, pdl=False):
+def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20, pdl=False, split=False):
     dev = torch.device("cuda:0")
     es = []
     for b in range(batches):
@@ -27,17 +27,31 @@ def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches
         es.append(e)
     g = torch.Generator(device=dev).manual_seed(99)
     pool = [torch.randint(0, net.n_genes + 1, (envs, 3), generator=g, device=dev, dtype=torch.uint8) for _ in range(8)]
+    pipes = [e.pipeline() for e in es] if split else None
+    bufs = [e.planes_buffer() for e in es] if split in ("main", "draw") else None
+
+    def step(i, n_total):
+        act = pool[i % 8] if actions else None
+        if split == "main":      # the step kernel alone, planes taken from a (stale) buffer
+            es[i % batches].step(act, stats=stats, planes=bufs[i % batches])
+        elif split == "draw":    # the predraw kernel alone
+            es[i % batches].predraw(bufs[i % batches])
+        elif split:
+            pipes[i % batches].step(act, last=(i >= n_total - batches), stats=stats)
+        else:
+            es[i % batches].step(act, stats=stats)
+
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
-        for i in range(4):
-            es[i % batches].step(pool[i % 8] if actions else None, stats=stats)
+        for i in range(batches):
+            step(i, batches)
         for e in es:
             e.advance_counter()
         s.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=s):
             for i in range(graph_steps):
-                es[i % batches].step(pool[i % 8] if actions else None, stats=stats)
+                step(i, graph_steps)
             for e in es:
                 e.advance_counter()
         gr.replay()
@@ -61,6 +75,8 @@ def main():
     ap.add_argument("--kernels", default="sliced")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--pdl", action="store_true")
+    ap.add_argument("--split", default="", help="'pipe': pbn_predraw on a side stream + pbn_step with pre-drawn planes; 'main' / 'draw': either kernel alone")
+    ap.add_argument("--graph-steps", type=int, default=32)
     args = ap.parse_args()
     net, attrs = bench.load_workload(args.net)
     W = net.n_words
@@ -74,7 +90,7 @@ def main():
         rows = rows[:1]
     for kernel in args.kernels.split(","):
         for label, p, ar, st, act in rows:
-            us = time_config(net, attrs, args.envs, kernel, p, ar, st, act, pdl=args.pdl)
+            us = time_config(net, attrs, args.envs, kernel, p, ar, st, act, pdl=args.pdl, split=args.split, graph_steps=args.graph_steps)
             gbs = bench.BYTES_PER_STEP[W] * args.envs / us / 1e3
             print("%-8s %-30s %9.2f us/step  %8.3e steps/s  %7.1f GB/s" % (kernel, label, us, args.envs / us * 1e6, gbs), flush=True)
 
