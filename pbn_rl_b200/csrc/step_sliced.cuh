@@ -66,8 +66,13 @@ constexpr int kScrSel1 = kScrSel0 + PBN_NSEL * 32;   // selection planes s1     
 constexpr int kScrStat = kScrSel1 + PBN_NSEL * 32;   // 8 block-level statistics counters
 constexpr int kScrEv = kScrStat + 8;                 // pre-drawn perturbation events, one packed word per thread [128]
 constexpr int kScrWords = kScrEv + 128;              // total (must equal PBN_SCRATCH_WORDS)
-constexpr uint32_t kPreEvOverflow = 0x80000000u;     // event walk not finished within its first Philox block: phase D redoes it
-static_assert(kSlots <= 1024, "pre-drawn event positions are packed in 10 bits");
+// Pre-drawn perturbation events of a thread: ascending slot positions packed into one word, kEvBits each, all-ones =
+// no event; the all-zero word (never a valid ascending list) = more than kEvCap events: phase D redoes the walk.
+constexpr uint32_t kEvBits = (kSlots < 255) ? 8u : 10u;
+constexpr uint32_t kEvCap = 32u / kEvBits;           // 4 events for N <= 31, else 3
+constexpr uint32_t kEvMask = (1u << kEvBits) - 1u;
+constexpr uint32_t kPreEvOverflow = 0u;
+static_assert(kSlots < (int)kEvMask, "pre-drawn event positions do not fit their field");
 constexpr int kPlaneWords = 2 * PBN_NSEL * 32;       // pre-drawn selection planes of one tile: [sel0 | sel1][slot][lane]
 static_assert((kScrSel0 * 4) % 16 == 0, "TMA destination of the selection planes must be 16-byte aligned");
 static_assert(kScrWords == PBN_SCRATCH_WORDS, "host and device disagree on the scratch size");
@@ -135,6 +140,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// Warm the L2 with a range that will be bulk-copied once the previous launch has completed (coherent: lines
+// the previous launch still writes are simply updated in place).
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -251,24 +261,23 @@ namespace pbn {
 // (column id, step counter, seed), so they are drawn early -- under the previous kernel's tail with
 // programmatic dependent launch, else behind the tile's TMA copy -- and phase D only applies them: the
 // Philox block and the dependent table look-ups of the geometric skip are a pure latency chain
-// (≈2 us per tile when it sat in D).  One packed word per thread (kPreEvOverflow: D redoes the walk).
+// (≈2 us per tile when it sat in D).  One packed word per thread (see kEvBits).
 __device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* ev, uint64_t gid, uint64_t step_ctr, uint32_t w) {
-  uint32_t word = 0u;   // bits 0-1: count, bits 2-11 / 12-21 / 22-31: up to three slot positions
+  uint32_t word = 0xFFFFFFFFu;   // no event
   if (n.pert_rng && n.pert_mode != PBN_PERT_NONE) {
     const uint32_t s_last = kSurvTable[kSlots];
-    const Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
+    Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
     int pos = -1;
-    uint32_t cnt = 0u;
     bool done = false;
 #pragma unroll 1
-    for (uint32_t k = 0; k < 4u; ++k) {   // the four draws of the sub-stream's first block: <= 3 events + the terminating draw
-      const uint32_t u = pick4(blk, k);
+    for (uint32_t k = 0; k <= kEvCap; ++k) {   // up to kEvCap events + the terminating draw
+      if (k == 4u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + 1u, n.rk);   // rare: fifth draw
+      const uint32_t u = pick4(blk, k & 3u);
       pos += (u < s_last) ? kSlots + 1 : pert_search(u);
       if (pos >= kSlots) { done = true; break; }
-      if (k < 3u) word |= (uint32_t)pos << (2u + 10u * k);
-      cnt = k + 1u;
+      if (k < kEvCap) word = (word & ~(kEvMask << (kEvBits * k))) | ((uint32_t)pos << (kEvBits * k));
     }
-    word = done ? (word | cnt) : kPreEvOverflow;   // not finished within the block: phase D redoes the walk
+    if (!done) word = kPreEvOverflow;       // more than kEvCap events: phase D redoes the walk
   }
   ev[0] = word;
 }
@@ -604,9 +613,12 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       const uint32_t evw = scr[kScrEv + threadIdx.x];
       if (evw != kPreEvOverflow) {
         // the usual case: the events were drawn ahead of time (draw_pert_events)
-        const uint32_t cnt = evw & 3u;
 #pragma unroll 1
-        for (uint32_t k = 0; k < cnt; ++k) apply_event((evw >> (2u + 10u * k)) & 0x3FFu);
+        for (uint32_t k = 0; k < kEvCap; ++k) {
+          const uint32_t pos = (evw >> (kEvBits * k)) & kEvMask;
+          if (pos == kEvMask) break;
+          apply_event(pos);
+        }
       } else {
         const uint32_t s_last = kSurvTable[kSlots];
         uint32_t pert_next = 0u;
@@ -740,11 +752,8 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     }
   }
   if (a.flags & PBN_STEP_AUTORESET) {
-    while (D) {
-      const int i = __ffs(D) - 1;
-      D &= D - 1u;
+    auto do_reset = [&](int i, const Philox4& r) {
       const int64_t env = e0 + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
-      const Philox4 r = philox_stream_rk((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.rk);
       uint64_t s[kW64];
       int src, tgt;
       if (attr_in_smem) {
@@ -763,6 +772,20 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       a.target_id[env] = tgt;
       if (a.source_id != nullptr) a.source_id[env] = src;
       a.t[env] = 0;
+    };
+    // two finished envs per trip: their Philox blocks are independent dependency chains
+    while (D) {
+      const int i0 = __ffs(D) - 1;
+      D &= D - 1u;
+      const bool two = D != 0u;
+      const int i1 = two ? __ffs(D) - 1 : i0;
+      D &= D - 1u;   // (0 stays 0)
+      const int64_t env0 = e0 + 128 * (2 * (int)w + (i0 >> 2)) + (i0 & 3);
+      const int64_t env1 = e0 + 128 * (2 * (int)w + (i1 >> 2)) + (i1 & 3);
+      const Philox4 r0 = philox_stream_rk((uint64_t)(a.env_offset + env0), step_ctr, PBN_RNG_RESET, 0, n.rk);
+      const Philox4 r1 = philox_stream_rk((uint64_t)(a.env_offset + env1), step_ctr, PBN_RNG_RESET, 0, n.rk);
+      do_reset(i0, r0);
+      if (two) do_reset(i1, r1);
     }
   }
 }
@@ -796,6 +819,14 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
     // first tile's selection planes (they depend on nothing the previous launch writes; the device step
     // counter is not bumped by PDL launches), then wait for the previous launch to complete and flush.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // the first tile's inputs were last touched several launches ago (they have left the L2 when the working set
+    // exceeds it): pull them in now, the bulk copies after the wait then hit the L2 instead of DRAM
+    if ((first_tile + 1) * 1024 <= a.n_envs && threadIdx.x < 4) {
+      if (threadIdx.x == 0) l2_prefetch(a.state + first_tile * 1024 * kW64, 1024u * 8u * kW64);
+      if (threadIdx.x == 1 && a.actions != nullptr) l2_prefetch(a.actions + first_tile * 1024 * PBN_BINS, 1024u * PBN_BINS);
+      if (threadIdx.x == 2 && a.target_id != nullptr) l2_prefetch(a.target_id + first_tile * 1024, 4096u);
+      if (threadIdx.x == 3 && a.t != nullptr) l2_prefetch(a.t + first_tile * 1024, 2048u);
+    }
     // everything of this CTA's first tile that does not depend on the state: selection planes, perturbation events
     if ((int64_t)blockIdx.x < n_tiles && a.sel_planes == nullptr) {
       const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;

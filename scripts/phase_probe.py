@@ -15,6 +15,8 @@ for envs in (1 << 20,):
     kw = dict(bench.ENV_KW)
     if len(sys.argv) > 2:
         kw["seed"] = int(sys.argv[2], 0)
+    if len(sys.argv) > 3:
+        kw["perturb_p"] = float(sys.argv[3])
     env = VecPBNEnv(net, envs, attrs, device="cuda:0", auto_reset=True, **kw)
     env.state[:, 0] = torch.randint(0, 1 << 28, (envs,), device="cuda")
     env.set_target(torch.randint(0, len(attrs), (envs,), device="cuda", dtype=torch.int32))
@@ -58,6 +60,8 @@ for envs in (1 << 20,):
         for label, j0, j1 in (("E (planes->rows)", 2, 3), ("D (apply events)", 3, 4), ("F (outputs)", 4, 5), ("G (reset+stats)", 5, 6), ("final sync", 6, 7)):
             x = (tx[j1] - tx[j0]) / 1e3
             print("  %-28s p1 %.2f  p50 %.2f  p90 %.2f  p99 %.2f  max %.2f" % (label, np.percentile(x, 1), np.median(x), np.percentile(x, 90), np.percentile(x, 99), x.max()))
+        dd = (tx[4] - tx[3]) / 1e3
+        print("  tiles with D > 2 us: %d (%s ...)" % ((dd > 2).sum(), np.nonzero(dd > 2)[0][:12].tolist()))
         par = np.arange(ntile) & 1
         for pv in (0, 1):
             m = par == pv
