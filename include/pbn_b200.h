@@ -48,7 +48,7 @@
  *   (SELECT, i>>2): sel_i = #{k < K_i-1 : cum[k] <= word}.  Perturbation positions are drawn
  *   by geometric skipping: words of blocks (PERTURB, 0..) in order, skip = #{j in 1..N :
  *   word < survival[j]}, pos += skip + 1, stop when pos >= N.
- *   Sliced kernel: id = global slice-group id; see DESIGN.md "Sliced random stream".
+ *   Sliced kernel: id = global slice-group id; see DESIGN.md section 4 ("Random streams").
  *   Results therefore do not depend on how envs are sharded over GPUs.
  */
 #ifndef PBN_B200_H

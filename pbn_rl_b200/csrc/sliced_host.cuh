@@ -159,7 +159,8 @@ inline int n_sel_slots(const GenNet& g) {
 
 inline int scratch_words(const GenNet& g) {
   const int NW = (g.n_genes + 31) / 32;
-  return 2 * NW * 32 * 32 + 2 * n_sel_slots(g) * 32 + 8 + 128;  // + pre-drawn perturbation events, one word per thread
+  // + pre-drawn perturbation events: one packed word per thread (8 N < 255 slots), else two
+  return 2 * NW * 32 * 32 + 2 * n_sel_slots(g) * 32 + 8 + 128 * (8 * g.n_genes < 255 ? 1 : 2);
 }
 
 inline int sliced_threads(const GenNet&) { return 128; }  // four warps per 1024-env tile

@@ -64,12 +64,15 @@ constexpr int kScrPl = kScrRows + kNW * 32 * 32;     // PL input planes         
 constexpr int kScrSel0 = kScrPl + kNW * 32 * 32;     // selection planes s0          [PBN_NSEL][32]
 constexpr int kScrSel1 = kScrSel0 + PBN_NSEL * 32;   // selection planes s1          [PBN_NSEL][32]
 constexpr int kScrStat = kScrSel1 + PBN_NSEL * 32;   // 8 block-level statistics counters
-constexpr int kScrEv = kScrStat + 8;                 // pre-drawn perturbation events, one packed word per thread [128]
-constexpr int kScrWords = kScrEv + 128;              // total (must equal PBN_SCRATCH_WORDS)
-// Pre-drawn perturbation events of a thread: ascending slot positions packed into one word, kEvBits each, all-ones =
-// no event; the all-zero word (never a valid ascending list) = more than kEvCap events: phase D redoes the walk.
+constexpr int kEvWords = (8 * PBN_N < 255) ? 1 : 2;  // packed words of pre-drawn perturbation events per thread
+constexpr int kScrEv = kScrStat + 8;                 // pre-drawn perturbation events              [kEvWords][128]
+constexpr int kScrWords = kScrEv + 128 * kEvWords;   // total (must equal PBN_SCRATCH_WORDS)
+// Pre-drawn perturbation events of a thread: ascending slot positions, kEvBits each, packed into kEvWords words;
+// all-ones = no event; an all-zero first word (never a valid ascending list) = more than kEvCap events: phase D
+// redoes the walk.
 constexpr uint32_t kEvBits = (kSlots < 255) ? 8u : 10u;
-constexpr uint32_t kEvCap = 32u / kEvBits;           // 4 events for N <= 31, else 3
+constexpr uint32_t kEvPerWord = 32u / kEvBits;
+constexpr uint32_t kEvCap = kEvPerWord * kEvWords;   // 4 events for N <= 31, else 6
 constexpr uint32_t kEvMask = (1u << kEvBits) - 1u;
 constexpr uint32_t kPreEvOverflow = 0u;
 static_assert(kSlots < (int)kEvMask, "pre-drawn event positions do not fit their field");
@@ -263,7 +266,9 @@ namespace pbn {
 // Philox block and the dependent table look-ups of the geometric skip are a pure latency chain
 // (≈2 us per tile when it sat in D).  One packed word per thread (see kEvBits).
 __device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* ev, uint64_t gid, uint64_t step_ctr, uint32_t w) {
-  uint32_t word = 0xFFFFFFFFu;   // no event
+  uint32_t word[kEvWords];
+#pragma unroll
+  for (int q = 0; q < kEvWords; ++q) word[q] = 0xFFFFFFFFu;   // no event
   if (n.pert_rng && n.pert_mode != PBN_PERT_NONE) {
     const uint32_t s_last = kSurvTable[kSlots];
     Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
@@ -271,15 +276,21 @@ __device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* e
     bool done = false;
 #pragma unroll 1
     for (uint32_t k = 0; k <= kEvCap; ++k) {   // up to kEvCap events + the terminating draw
-      if (k == 4u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + 1u, n.rk);   // rare: fifth draw
+      if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + (k >> 2), n.rk);   // rare
       const uint32_t u = pick4(blk, k & 3u);
       pos += (u < s_last) ? kSlots + 1 : pert_search(u);
       if (pos >= kSlots) { done = true; break; }
-      if (k < kEvCap) word = (word & ~(kEvMask << (kEvBits * k))) | ((uint32_t)pos << (kEvBits * k));
+      if (k < kEvCap) {
+        const uint32_t sh = kEvBits * (k % kEvPerWord);
+#pragma unroll
+        for (int q = 0; q < kEvWords; ++q)
+          if ((uint32_t)q == k / kEvPerWord) word[q] = (word[q] & ~(kEvMask << sh)) | ((uint32_t)pos << sh);
+      }
     }
-    if (!done) word = kPreEvOverflow;       // more than kEvCap events: phase D redoes the walk
+    if (!done) word[0] = kPreEvOverflow;       // more than kEvCap events: phase D redoes the walk
   }
-  ev[0] = word;
+#pragma unroll
+  for (int q = 0; q < kEvWords; ++q) ev[128 * q] = word[q];
 }
 #endif
 
@@ -610,14 +621,19 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
             }
           }
       };
-      const uint32_t evw = scr[kScrEv + threadIdx.x];
-      if (evw != kPreEvOverflow) {
+      uint32_t evw[kEvWords];
+#pragma unroll
+      for (int q = 0; q < kEvWords; ++q) evw[q] = scr[kScrEv + 128 * q + threadIdx.x];
+      if (evw[0] != kPreEvOverflow) {
         // the usual case: the events were drawn ahead of time (draw_pert_events)
+#pragma unroll
+        for (int q = 0; q < kEvWords; ++q) {
 #pragma unroll 1
-        for (uint32_t k = 0; k < kEvCap; ++k) {
-          const uint32_t pos = (evw >> (kEvBits * k)) & kEvMask;
-          if (pos == kEvMask) break;
-          apply_event(pos);
+          for (uint32_t k = 0; k < kEvPerWord; ++k) {
+            const uint32_t pos = (evw[q] >> (kEvBits * k)) & kEvMask;
+            if (pos == kEvMask) break;
+            apply_event(pos);
+          }
         }
       } else {
         const uint32_t s_last = kSurvTable[kSlots];
