@@ -377,6 +377,7 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
   n.horizon = d->horizon;
   n.pert_mode = d->perturb_mode;  // injected masks apply even when perturb_p == 0
   n.pert_rng = d->perturb_p > 0.0f ? 1u : 0u;
+  n.pert_inv_log2 = d->perturb_p > 0.0 ? (float)(1.0 / std::log2(1.0 - d->perturb_p)) : 0.0f;
   n.r_success = d->r_success;
   n.r_step = d->r_step;
   n.r_action = d->r_action;

@@ -48,6 +48,7 @@ struct NetParams {
   uint32_t pert_rng;             // 1: draw perturbations from the stream (perturb_p > 0)
   uint32_t attr_simple;          // 1: every attractor is a single fully specified state (no wildcards)
   uint32_t rk[20];               // Philox round keys (k0 + r*W0, k1 + r*W1), r = 0..9: constant-bank operands
+  float pert_inv_log2;           // 1 / log2(1 - perturb_p) (negative): first guess of the geometric skip
   const WideDesc* wide;          // [n_wide] or nullptr
   const uint64_t* wide_lut;      // multi-word truth tables of the wide predictors
 };

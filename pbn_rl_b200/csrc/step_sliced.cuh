@@ -243,9 +243,21 @@ __device__ __forceinline__ void sel_slot(uint64_t gid, uint64_t step, const uint
 // lane-divergent; from global memory each step of the search cost a DRAM/L2 round trip, ~2 us per event).
 __constant__ uint32_t kSurvTable[kSlots + 1];
 
-// Next event distance of the perturbation stream.
-__device__ __noinline__ int pert_search(uint32_t u) {
-  int lo = 0, hi = kSlots;  // invariant: u < S[lo] (S[0] = 2^32 conceptually)
+// Next event distance of the perturbation stream: 1 + max{j in 0..8N : u < S[j]} (S[0] = 2^32 conceptually).
+// S is geometric, so j is first guessed as log2(u / 2^32) / log2(1 - p) and pinned down exactly by four
+// INDEPENDENT table reads around the guess (one memory latency instead of a dependent binary search, whose
+// steps are lane-divergent); if the window misses (tiny p, float error) the binary search decides.
+__device__ __noinline__ int pert_search(const NetParams& n, uint32_t u) {
+  const uint32_t* __restrict__ S = n.surv_sliced;
+  int j0 = (int)((__log2f((float)u + 1.0f) - 32.0f) * n.pert_inv_log2);
+  j0 = min(max(j0, 1), kSlots);
+  const int ja = j0 - 1, jd = j0 + 2;
+  const bool ca = ja < 1 || u < __ldg(S + min(max(ja, 1), kSlots));
+  const bool cb = u < __ldg(S + j0);
+  const bool cc = j0 + 1 <= kSlots && u < __ldg(S + min(j0 + 1, kSlots));
+  const bool cd = jd <= kSlots && u < __ldg(S + min(jd, kSlots));
+  if (ca && !cd) return ja + (cb ? 1 : 0) + (cc ? 1 : 0) + 1;   // c(j) = (u < S[j]) is non-increasing in j
+  int lo = 0, hi = kSlots;  // invariant: u < S[lo]
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (u < kSurvTable[mid]) lo = mid; else hi = mid - 1;
@@ -278,7 +290,7 @@ __device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* e
     for (uint32_t k = 0; k <= kEvCap; ++k) {   // up to kEvCap events + the terminating draw
       if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + (k >> 2), n.rk);   // rare
       const uint32_t u = pick4(blk, k & 3u);
-      pos += (u < s_last) ? kSlots + 1 : pert_search(u);
+      pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
       if (pos >= kSlots) { done = true; break; }
       if (k < kEvCap) {
         const uint32_t sh = kEvBits * (k % kEvPerWord);
@@ -645,7 +657,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
             pert_blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
           const uint32_t u = pick4(pert_blk, pert_next & 3u);
           ++pert_next;
-          pos += (u < s_last) ? kSlots + 1 : pert_search(u);
+          pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
           if (pos >= kSlots) break;
           apply_event((uint32_t)pos);
         }
