@@ -285,3 +285,30 @@ def test_large_batch_properties(kernel):
     term = env.terminated.bool()
     ids_gpu = env.attractor_ids()
     assert torch.equal(ids_gpu[term], env.target_id[term])
+
+
+@pytest.mark.parametrize("name,e,p", [("pbn28", 1 << 17, 1e-5), ("pbn28", 8192, 0.3), ("pbn70", 1 << 15, 2e-5),
+                                      ("pbn70", 4096, 0.2), ("pbn7", 1 << 16, 3e-4)])
+def test_perturbation_stream_extremes(name, e, p):
+    """The geometric skip of the sliced kernel (float first guess + exact table window, binary search as
+    fallback; events pre-drawn into packed words, overflow redone in phase D) against the oracle's plain walk
+    over the survival table: very rare events (the float guess is least accurate) and very frequent ones
+    (every thread overflows its pre-drawn list)."""
+    import torch
+    from oracle import pbn_oracle as O
+    case = random_case(name, e, seed=13)
+    env = _env(name, e, mode="B", p=p, kernel="sliced")
+    onet = oracle_net(name)
+    ids = np.arange(e, dtype=np.uint64)
+    state, t = case["state"], case["t"]
+    _load(env, case)
+    total = 0
+    for step in range(2):
+        env.step(torch.from_numpy(case["actions"]).cuda())
+        sel, pert = O.sliced_stream(onet, p, ids, step, 0x5EED)
+        expect = _oracle_step(name, dict(case, state=state, t=t), sel, pert, "B")
+        _compare(env, expect, f"{name}/p={p}/step{step}")
+        state, t = expect[0], expect[1]
+        total += int(sum(bin(int(x)).count("1") for x in pert.reshape(-1)))
+    assert total > 0, "no perturbation event in the sample: test is vacuous"
+    assert env.stats()["perturbed"] == total
