@@ -169,12 +169,6 @@ inline int sliced_min_blocks(const GenNet& g) {
   return g.n_genes <= 32 ? 8 : (g.n_genes <= 64 ? 4 : 2);
 }
 
-// Tuning experiments (scripts/perf_probe.py): PBN_B200_TUNE sets the PBN_TUNE bit field of the generated header.
-inline int sliced_tune() {
-  if (const char* env = getenv("PBN_B200_TUNE")) return atoi(env);
-  return 0;
-}
-
 // net_gen.cuh: the constants; net_update.inc: selection tables + pbn_update_part() -- see step_sliced.cuh
 inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::string* update_inc) {
   const int N = g.n_genes, NW = (N + 31) / 32, NSEL = n_sel_slots(g);
@@ -185,8 +179,6 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
            "#define PBN_N %d\n#define PBN_NW32 %d\n#define PBN_BINS %d\n#define PBN_NSEL %d\n"
            "#define PBN_SCRATCH_WORDS %d\n#define PBN_INJECTED %d\n#define PBN_THREADS %d\n#define PBN_MIN_BLOCKS %d\n",
            N, NW, g.bins, NSEL, scratch_words(g), injected ? 1 : 0, sliced_threads(g), sliced_min_blocks(g));
-  h += buf;
-  snprintf(buf, sizeof(buf), "#define PBN_TUNE %d\n", sliced_tune());
   h += buf;
   *gen_h = h;
 

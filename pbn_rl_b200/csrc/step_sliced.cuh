@@ -374,7 +374,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
                                           uint32_t* s_surv, float* s_rew, int32_t* s_aoffs, uint32_t* s_aent,
                                           int64_t tile, uint64_t step_ctr, const bool stage, unsigned char* st_state,
                                           unsigned char* st_act, uint64_t* mbar, uint32_t& tma_parity,
-                                          const bool pre_drawn) {
+                                          const bool pre_drawn, const bool ev_drawn) {
   constexpr bool attr_in_smem = ASMEM;
   const pbn_step_args& a = p.a;
   const NetParams& n = p.n;
@@ -446,7 +446,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   phase_stamp(a, 2);
   const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
 #if !PBN_INJECTED
-  if (!pre_drawn) draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w);  // behind the TMA copy
+  if (!ev_drawn) draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w);  // behind the TMA copy
 #endif
   // ---- C1 (even tiles: here, hiding the load latency; odd tiles: after B, so that neighbouring
   //      CTAs of the single wave are in different phases and share the SM's issue slots better)
@@ -839,9 +839,9 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
   const uint64_t step_ctr = effective_step(a);
   const int64_t n_tiles = (a.n_envs + 1023) >> 10;
   bool stage = true;
-  bool pre_drawn = false;
-  // PBN_TUNE bit 2 (experiment): scramble the CTA -> tile map when every CTA owns exactly one tile
-  const int64_t first_tile = ((PBN_TUNE & 4) && (int64_t)gridDim.x == n_tiles) ? ((int64_t)blockIdx.x * 577) % n_tiles : (int64_t)blockIdx.x;
+  bool pre_drawn = false;   // selection planes of the first tile drawn before griddepcontrol.wait
+  bool ev_drawn = false;    // ... and its perturbation events
+  const int64_t first_tile = (int64_t)blockIdx.x;
   if (a.flags & PBN_STEP_PDL) {
     // Programmatic dependent launch: let the next launch start as SM resources free up, draw this CTA's
     // first tile's selection planes (they depend on nothing the previous launch writes; the device step
@@ -856,29 +856,35 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
       if (threadIdx.x == 3 && a.t != nullptr) l2_prefetch(a.t + first_tile * 1024, 2048u);
     }
     // everything of this CTA's first tile that does not depend on the state: selection planes, perturbation events
-    if ((int64_t)blockIdx.x < n_tiles && a.sel_planes == nullptr) {
+    if ((int64_t)blockIdx.x < n_tiles) {
       const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
       const int64_t tile = first_tile;
       const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
-      draw_selection_planes<false>(a, n, scr + kScrSel0 + lane, scr + kScrSel1 + lane, gid, step_ctr,
-                                   tile * 1024 + 4 * (int64_t)lane, w);
+      // (measured: letting only every other CTA of an SM draw here and the rest after phase B -- so that their
+      // Philox overlaps the others' main phases -- is slower, 23.1 vs 19.1 us: time before the wait is free)
+      if (a.sel_planes == nullptr) {
+        draw_selection_planes<false>(a, n, scr + kScrSel0 + lane, scr + kScrSel1 + lane, gid, step_ctr,
+                                     tile * 1024 + 4 * (int64_t)lane, w);
+        pre_drawn = true;
+      }
 #if !PBN_INJECTED
       draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w);
+      ev_drawn = true;
 #endif
-      pre_drawn = true;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   for (int64_t tile = first_tile; tile < n_tiles; tile += gridDim.x) {
     const bool full = (tile + 1) * 1024 <= a.n_envs;
     if (L.attractors_in_smem != 0u) {
-      if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn);
-      else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn);
+      if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
+      else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
     } else {
-      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn);
+      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
     }
     stage = false;
     pre_drawn = false;
+    ev_drawn = false;
     phase_stamp(a, 12);
     cta_stamp(a, 6);
     __syncthreads();  // scratch is reused by the next tile; statistics are complete
