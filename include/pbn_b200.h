@@ -231,6 +231,16 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* args, const pbn_host_io* i
 int pbn_predraw(pbn_handle* h, const pbn_step_args* args, uint32_t* planes, void* stream);
 int64_t pbn_planes_words(const pbn_handle* h, int64_t n_envs);
 
+/* n_steps uncontrolled network updates of every instance in ONE launch (env.step([]) n_steps times,
+ * graph_classifier/__init__.py:148; the burn-in of the attractor search; the long runs of compute_ssd_hist,
+ * train_pbn_28.py:257): the states are loaded once, stay on chip as bit-planes between updates and are
+ * written back once.  Bit-identical to n_steps calls of pbn_step with actions = NULL and step counters
+ * step_ctr .. step_ctr + n_steps - 1 as far as `state` is concerned; t / target / reward / flags are not
+ * touched, nothing is reset.  stats (DEVICE, may be NULL): PBN_STAT_STEPS and PBN_STAT_PERTURBED are
+ * accumulated.  Sliced kernel only (PBN_ERR_UNSUPPORTED otherwise: loop over pbn_step instead). */
+int pbn_rollout(pbn_handle* h, uint64_t* state, int64_t n_steps, uint64_t step_ctr, int64_t env_offset,
+                int64_t n_envs, unsigned long long* stats, void* stream);
+
 /* The same step with injected predictor choices / perturbation masks: the parity entry point
  * (deterministic core T of SURVEY.md 8a-4).  args->sel must be non-NULL. */
 int pbn_step_injected(pbn_handle* h, const pbn_step_args* args, void* stream);

@@ -32,7 +32,7 @@ EXPORTS = (
     "pbn_advance_counter", "pbn_step_host", "pbn_replay_observe", "pbn_replay_commit", "pbn_replay_sample",
     "pbn_observe", "pbn_in_target", "pbn_rollout_track", "pbn_rollout_reduce",
     "pbn_visit_count", "pbn_successor_sets", "pbn_closure_expand", "pbn_closure_reach",
-    "pbn_predraw", "pbn_planes_words",
+    "pbn_predraw", "pbn_planes_words", "pbn_rollout",
 )
 
 
@@ -173,6 +173,8 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_predraw.restype = C.c_int
     lib.pbn_planes_words.argtypes = [vp, i64]
     lib.pbn_planes_words.restype = i64
+    lib.pbn_rollout.argtypes = [vp, vp, i64, u64, i64, i64, vp, vp]
+    lib.pbn_rollout.restype = C.c_int
     lib.pbn_step_injected.argtypes = [vp, C.POINTER(StepArgs), vp]
     lib.pbn_step_injected.restype = C.c_int
     lib.pbn_reset.argtypes = [vp, vp, vp, vp, vp, vp, u64, i64, i64, vp]

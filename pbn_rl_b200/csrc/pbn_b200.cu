@@ -86,6 +86,8 @@ struct pbn_handle {
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
   cudaKernel_t jit_kernel[2] = {nullptr, nullptr};
   cudaKernel_t predraw_kernel = nullptr;  // pbn_predraw_sliced of the own-RNG specialisation
+  cudaKernel_t rollout_kernel = nullptr;  // pbn_rollout_sliced
+  uint32_t rollout_smem_opt_in = 48u * 1024u;
   std::vector<uint32_t> surv_sliced_host;  // copied into every loaded specialisation's constant memory
   int sliced_threads = 128, sliced_min_blocks = 1;
   uint32_t jit_smem_opt_in[2] = {48u * 1024u, 48u * 1024u};
@@ -106,6 +108,7 @@ static int load_sliced(pbn_handle* h, int injected) {
   PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->predraw_kernel, h->jit_lib[0], "pbn_predraw_sliced"));
+  if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->rollout_kernel, h->jit_lib[0], "pbn_rollout_sliced"));
   if (!injected) {  // the survival table of the perturbation sub-streams lives in the specialisation's constant memory
     void* dptr = nullptr;
     size_t bytes = 0;
@@ -534,6 +537,40 @@ int pbn_jit_precompile(const pbn_net_desc* d) {
 }
 
 int pbn_step(pbn_handle* h, const pbn_step_args* a, void* stream) { return step_common(h, a, stream, false); }
+
+int pbn_rollout(pbn_handle* h, uint64_t* state, int64_t n_steps, uint64_t step_ctr, int64_t env_offset, int64_t n_envs,
+                unsigned long long* stats, void* stream_) {
+  if (!h || !state) return fail(PBN_ERR_INVALID, "null argument");
+  if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "pbn_rollout: the handle runs the scalar kernel (loop over pbn_step)");
+  if (n_envs < 0 || n_steps < 0 || n_steps > 0x7FFFFFFF || env_offset < 0 || (env_offset & 1023)) return fail(PBN_ERR_INVALID, "bad n_envs / n_steps / env_offset");
+  if (n_envs == 0 || n_steps == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  int rc = load_sliced(h, 0);
+  if (rc != PBN_OK) return rc;
+  const int N = h->net.n_genes, NW = (N + 31) / 32, NSEL = jit::n_sel_slots(h->gen);
+  const uint32_t smem = (uint32_t)(2 * NW * 1024 + 2 * NSEL * 32 + 128 * (8 * N < 255 ? 1 : 2) + 32 + 8) * 4u;
+  if (smem > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "pbn_rollout needs %u B of shared memory", smem);
+  if (smem > h->rollout_smem_opt_in) {
+    PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(h->rollout_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->rollout_smem_opt_in = smem;
+  }
+  RolloutParams p;
+  p.n = h->net;
+  p.state = state;
+  p.stats = stats;
+  p.step_ctr = step_ctr;
+  p.env_offset = env_offset;
+  p.n_envs = n_envs;
+  p.n_steps = (int32_t)n_steps;
+  int64_t grid = (n_envs + 1023) / 1024;
+  const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 8;
+  if (grid > cap) grid = cap;
+  void* args[] = {&p};
+  PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(h->rollout_kernel), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, smem, stream));
+  h->launches += 1;
+  return PBN_OK;
+}
 
 int64_t pbn_planes_words(const pbn_handle* h, int64_t n_envs) {
   if (!h || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");

@@ -71,6 +71,16 @@ struct StepParams {
   unsigned int* ticket;  // handle-owned; used to bump *a.step_ctr_dev once per launch
 };
 
+// pbn_rollout: n_steps uncontrolled updates with the state kept on chip in between.
+struct RolloutParams {
+  NetParams n;
+  uint64_t* state;              // [E*W] in/out
+  unsigned long long* stats;    // [PBN_N_STATS] or nullptr
+  uint64_t step_ctr;            // Philox step counter of the first update
+  int64_t env_offset, n_envs;
+  int32_t n_steps;
+};
+
 // Effective Philox step counter of this launch (host part + optional device-resident part).
 __device__ __forceinline__ uint64_t effective_step(const pbn_step_args& a) {
   uint64_t step = a.step_ctr;

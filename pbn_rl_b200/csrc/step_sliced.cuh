@@ -900,6 +900,184 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
 }
 
 #if !PBN_INJECTED
+// ---- pbn_rollout: S uncontrolled updates (env.step([]) S times, graph_classifier/__init__.py:148; the burn-in of
+// the attractor search; compute_ssd_hist's long runs) in ONE launch.  The tile's 1024 states are loaded and
+// bit-transposed once, then stay in shared memory as bit-planes: per update only the Philox selection
+// planes, the LOP3 trees and the sparse perturbation events remain -- no HBM traffic, no transposes, no
+// per-env outputs.  Same random streams as S calls of pbn_step (step counters step_ctr .. step_ctr + S - 1),
+// so the final states are bit-identical.
+constexpr int kRollPlanes = kNW * 32 * 32;                      // one set of planes [kNW*32][32]
+constexpr int kRollSel0 = 2 * kRollPlanes;
+constexpr int kRollSel1 = kRollSel0 + PBN_NSEL * 32;
+constexpr int kRollEv = kRollSel1 + PBN_NSEL * 32;
+constexpr int kRollAny = kRollEv + 128 * kEvWords;              // mode A: rows of the column with an event [32]
+constexpr int kRollStat = kRollAny + 32;
+constexpr int kRollWords = kRollStat + 8;
+
+extern "C" __global__ void __launch_bounds__(PBN_THREADS, PBN_MIN_BLOCKS)
+pbn_rollout_sliced(const __grid_constant__ RolloutParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* scr = reinterpret_cast<uint32_t*>(smem_raw);
+  const NetParams& n = p.n;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const int64_t E = p.n_envs;
+  const int64_t n_tiles = (E + 1023) >> 10;
+  uint32_t* sel0 = scr + kRollSel0 + lane;
+  uint32_t* sel1 = scr + kRollSel1 + lane;
+  uint32_t* anym = scr + kRollAny;
+  uint32_t* s_stat = scr + kRollStat;
+  const int pert_mode = n.pert_rng ? n.pert_mode : PBN_PERT_NONE;  // block-uniform
+  pbn_step_args dummy{};
+  if (threadIdx.x < 8) s_stat[threadIdx.x] = 0u;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t e0 = tile * 1024 + 4 * (int64_t)lane;
+    const uint64_t gid = (uint64_t)(((p.env_offset >> 10) + tile) * 32 + lane);
+    uint32_t* cur = scr;                    // current planes
+    uint32_t* nxt = scr + kRollPlanes;      // next planes (first: the rows, before the transpose)
+    uint32_t valid = 0u;                    // which of this warp's 8 rows are real envs
+    // ---- rows of this warp's 8 envs -> scratch
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t env = e0 + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
+      const bool ok = env < E;
+      valid |= (ok ? 1u : 0u) << i;
+#pragma unroll
+      for (int wd = 0; wd < kNW; ++wd) {
+        const uint64_t v = ok ? p.state[env * kW64 + (wd >> 1)] : 0ull;
+        nxt[(wd * 32 + 8 * (int)w + i) * 32 + lane] = (uint32_t)(v >> (32 * (wd & 1)));
+      }
+    }
+    __syncthreads();
+    // ---- rows -> bit-planes (this warp: planes 8w..8w+7 of every word)
+#pragma unroll
+    for (int wd = 0; wd < kNW; ++wd) {
+      uint32_t q8[8];
+      transpose_quarter(nxt + wd * 32 * 32 + lane, w, q8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[(wd * 32 + 8 * (int)w + i) * 32 + lane] = q8[i];
+    }
+    uint32_t npert = 0u;
+#pragma unroll 1
+    for (int s = 0; s < p.n_steps; ++s) {
+      const uint64_t step_ctr = p.step_ctr + (uint64_t)s;
+      draw_selection_planes<true>(dummy, n, sel0, sel1, gid, step_ctr, e0, w);
+      if (pert_mode != PBN_PERT_NONE) {
+        draw_pert_events(n, scr + kRollEv + threadIdx.x, gid, step_ctr, w);
+        if (pert_mode == PBN_PERT_A && w == 0u) anym[lane] = 0u;
+      }
+      __syncthreads();   // planes `cur` complete (transpose / previous update), selection planes drawn
+      pbn_update_part(w, cur + lane, nxt + lane, sel0, sel1);
+      if (pert_mode != PBN_PERT_NONE) {
+        // this thread's events: (gene, row 8w + ib) of its column
+        uint32_t evw[kEvWords];
+#pragma unroll
+        for (int q = 0; q < kEvWords; ++q) evw[q] = scr[kRollEv + 128 * q + threadIdx.x];
+        uint32_t pos_list[kEvCap];
+        uint32_t cnt = 0u;
+        if (evw[0] != kPreEvOverflow) {
+#pragma unroll
+          for (int q = 0; q < kEvWords; ++q)
+#pragma unroll
+            for (uint32_t k = 0; k < kEvPerWord; ++k) {
+              const uint32_t pos = (evw[q] >> (kEvBits * k)) & kEvMask;
+              pos_list[q * kEvPerWord + k] = pos;
+              if (pos != kEvMask && cnt == q * kEvPerWord + k) cnt = q * kEvPerWord + k + 1u;
+            }
+        }
+        const bool overflow = evw[0] == kPreEvOverflow;
+        // apply one event to the NEXT planes (after the update of all genes is complete)
+        auto flip = [&](uint32_t pos) {
+          const uint32_t g = pos >> 3, bit = 8u * w + (pos & 7u);
+          uint32_t* word = nxt + g * 32 + lane;
+          if (pert_mode == PBN_PERT_C) {
+            if ((cur[g * 32 + lane] >> bit) & 1u) atomicAnd(word, ~(1u << bit)); else atomicOr(word, 1u << bit);
+          } else {
+            atomicXor(word, 1u << bit);
+          }
+          if ((valid >> (pos & 7u)) & 1u) ++npert;
+        };
+        if (pert_mode == PBN_PERT_A) {
+          // a perturbed step skips the update: rows with an event keep their old bits, then get the flips
+          uint32_t M = 0u;
+          if (!overflow) {
+            for (uint32_t k = 0; k < cnt; ++k) M |= 1u << (8u * w + (pos_list[k] & 7u));
+          } else {
+            const uint32_t s_last = kSurvTable[kSlots];
+            uint32_t pert_next = 0u;
+            Philox4 blk = {0u, 0u, 0u, 0u};
+            int pos = -1;
+            while (true) {
+              if ((pert_next & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
+              const uint32_t u = pick4(blk, pert_next & 3u);
+              ++pert_next;
+              pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
+              if (pos >= kSlots) break;
+              M |= 1u << (8u * w + ((uint32_t)pos & 7u));
+            }
+          }
+          if (M) atomicOr(&anym[lane], M);
+          __syncthreads();   // all out planes written, all rows-with-events known
+          const uint32_t am = anym[lane];
+          if (am) {
+#pragma unroll 1
+            for (int g = (int)w; g < PBN_N; g += kWarps) nxt[g * 32 + lane] = bmux(am, cur[g * 32 + lane], nxt[g * 32 + lane]);
+          }
+        }
+        __syncthreads();     // out planes (and the mode-A restore) complete before the flips
+        if (!overflow) {
+          for (uint32_t k = 0; k < cnt; ++k) flip(pos_list[k]);
+        } else {
+          const uint32_t s_last = kSurvTable[kSlots];
+          uint32_t pert_next = 0u;
+          Philox4 blk = {0u, 0u, 0u, 0u};
+          int pos = -1;
+          while (true) {
+            if ((pert_next & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
+            const uint32_t u = pick4(blk, pert_next & 3u);
+            ++pert_next;
+            pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
+            if (pos >= kSlots) break;
+            flip((uint32_t)pos);
+          }
+        }
+      }
+      uint32_t* t = cur; cur = nxt; nxt = t;
+    }
+    __syncthreads();         // the last update (and its flips) is complete
+    // ---- bit-planes -> this warp's 8 rows -> HBM
+    uint32_t o[8][kNW];
+#pragma unroll
+    for (int wd = 0; wd < kNW; ++wd) {
+      uint32_t q8[8];
+      transpose_quarter(cur + wd * 32 * 32 + lane, w, q8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i][wd] = q8[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t env = e0 + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
+      if (env < E) {
+#pragma unroll
+        for (int wd = 0; wd < kW64; ++wd)
+          p.state[env * kW64 + wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
+      }
+    }
+    if (p.stats != nullptr) {
+      const uint32_t nv = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(valid));
+      const uint32_t np = __reduce_add_sync(0xFFFFFFFFu, npert);
+      if (lane == 0u) {
+        atomicAdd(&s_stat[0], nv);
+        if (np) atomicAdd(&s_stat[1], np);
+      }
+    }
+    __syncthreads();         // scratch is reused by the next tile
+  }
+  if (p.stats != nullptr && threadIdx.x == 0) {
+    atomicAdd(&p.stats[PBN_STAT_STEPS], (unsigned long long)s_stat[0] * (unsigned long long)p.n_steps);
+    if (s_stat[1]) atomicAdd(&p.stats[PBN_STAT_PERTURBED], (unsigned long long)s_stat[1]);
+  }
+}
+
 // pbn_predraw: the selection planes of one step for every tile, into global memory.  Needs no shared
 // memory and few registers, so its CTAs fit next to the step kernel's on every SM.
 extern "C" __global__ void __launch_bounds__(PBN_THREADS, 12)

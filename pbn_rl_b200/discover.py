@@ -269,8 +269,7 @@ def find_attractors_rollout(network: PBNNetwork, n_rollouts: int = 1 << 16, burn
         hi = torch.randint(0, 1 << max(bits - 31, 0), (e,), generator=g, device=dev, dtype=torch.int64)
         lo = torch.randint(0, 1 << min(bits, 31), (e,), generator=g, device=dev, dtype=torch.int64)
         env.state[:, k] = (hi << 31) | lo
-    for _ in range(int(burn_in)):
-        env.step(None, stats=False)
+    env.rollout(int(burn_in), stats=False)       # one launch: the states stay on chip between the updates
     table = VisitCounter(env, table_capacity)
     table.add()
     states, counts = table.items()
@@ -321,8 +320,11 @@ def steady_state_histogram(env: VecPBNEnv, steps: int, actions: Optional[torch.T
     """Visit counts of the states (restricted to ``genes``, packed in that order, if given) seen by all
     instances of ``env`` over ``steps`` steps after ``burn_in`` steps -- the histogram behind
     ``compute_ssd_hist`` (train_pbn_28.py:257).  ``{state int: visits}``; sums to ``steps * num_envs``."""
-    for _ in range(int(burn_in)):
-        env.step(actions, stats=False)
+    if actions is None and env.step_ctr_dev is None:
+        env.rollout(int(burn_in), stats=False)
+    else:
+        for _ in range(int(burn_in)):
+            env.step(actions, stats=False)
     table = VisitCounter(env, table_capacity)
     proj = None
     if genes is not None:

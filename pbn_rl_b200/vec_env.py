@@ -363,6 +363,31 @@ class VecPBNEnv:
             self.step_ctr += 1
         return self.state, self.reward, self.terminated, self.truncated
 
+    def rollout(self, n_steps: int, stats: bool = True) -> torch.Tensor:
+        """``n_steps`` uncontrolled updates of every instance (``env.step([])`` ``n_steps`` times,
+        graph_classifier/__init__.py:148) in one launch: the states stay on chip as bit-planes between the
+        updates (``pbn_rollout``).  Only ``state`` changes -- bit-identical to ``n_steps`` calls of
+        ``step(None)`` -- counters, targets, rewards and flags are left alone and nothing is reset.  Networks
+        the sliced kernel does not take fall back to a loop of steps."""
+        n_steps = int(n_steps)
+        if n_steps <= 0:
+            return self.state
+        if self.step_ctr_dev is not None:
+            raise RuntimeError("rollout() needs the host-side step counter (device_counter=False, pdl=False)")
+        if self.kernel != "sliced":
+            saved = (self.t.clone(), self.target_id.clone(), self.auto_reset)
+            self.auto_reset = False
+            for _ in range(n_steps):
+                self.step(None, stats=stats)
+            self.t.copy_(saved[0])
+            self.target_id.copy_(saved[1])
+            self.auto_reset = saved[2]
+            return self.state
+        check(self.lib.pbn_rollout(self._h, _ptr(self.state), n_steps, self.step_ctr, self.env_offset, self.num_envs,
+                                   _ptr(self.stats_buf) if stats else None, self._stream()))
+        self.step_ctr += n_steps
+        return self.state
+
     def pipeline(self) -> "StepPipeline":
         """Two-stream stepping: the selection planes of step k+1 are drawn while step k runs."""
         return StepPipeline(self)
