@@ -27,7 +27,7 @@ from .attractors import AttractorSet
 from .network import PBNNetwork
 from .vec_env import VecPBNEnv
 
-__all__ = ["VisitCounter", "find_attractors_rollout", "attractor_reached_from", "steady_state_histogram", "successor_descriptors",
+__all__ = ["VisitCounter", "find_attractors_rollout", "attractor_reached_from", "basin_labels", "steady_state_histogram", "successor_descriptors",
            "forward_closure", "sink_sccs_of_closed_set"]
 
 
@@ -312,6 +312,26 @@ def find_attractors_rollout(network: PBNNetwork, n_rollouts: int = 1 << 16, burn
             "basin_fraction": [hits[i] / e for i in perm], "unresolved": unresolved,
             "states": [attractors[i] for i in perm]}
     return AttractorSet(attrs, n), info
+
+
+def basin_labels(env: VecPBNEnv, max_steps: int = 1024, chunk: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Which attractor every instance drains into when left alone: the loop of the basin classifier
+    (graph_classifier/__init__.py:125-148 rolls ``env.step([])`` until ``env.is_attracting_state(state)``), for all
+    instances at once.  Rolls ``chunk`` uncontrolled updates at a time (``pbn_rollout``) until every state lies in
+    an attractor of the env's table or ``max_steps`` is reached.  Returns ``(attractor_id [E] int32, -1 = none
+    reached, steps_taken [E] int32 rounded up to a multiple of ``chunk``)``; the env's states are left where the
+    rollouts ended."""
+    ids = env.attractor_ids()
+    steps = torch.zeros((env.num_envs,), dtype=torch.int32, device=env.device)
+    done = 0
+    while done < max_steps and bool((ids < 0).any().item()):
+        n = min(chunk, max_steps - done)
+        env.rollout(n, stats=False)
+        done += n
+        new = env.attractor_ids()
+        steps = torch.where((ids < 0) & (new >= 0), torch.full_like(steps, done), steps)
+        ids = torch.where(ids < 0, new, ids)     # the first attractor reached (attractors are closed when p = 0)
+    return ids, steps
 
 
 def steady_state_histogram(env: VecPBNEnv, steps: int, actions: Optional[torch.Tensor] = None,

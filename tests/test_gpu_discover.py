@@ -129,3 +129,61 @@ def test_steady_state_histogram_mass():
     proj = steady_state_histogram(env, steps=5, genes=[0, 6])
     assert sum(proj.values()) == 5 * 2048 and set(proj) <= {0, 1, 2, 3}
     env.close()
+
+
+def test_basin_labels_match_exhaustive_reachability():
+    """pbn10 without perturbation: every state is labelled with an attractor it can reach in the brute-force STG
+    (K5), and states inside an attractor are labelled with it after 0 steps."""
+    import torch
+    from pbn_rl_b200 import AttractorSet, VecPBNEnv
+    from pbn_rl_b200.attractors import _successor_sets, _successors
+    from pbn_rl_b200.discover import basin_labels
+    net = product_net("pbn10")
+    sinks = golden("k5_stg.json")["pbn10"]["sink_sccs"]
+    aset = AttractorSet([[tuple((s >> i) & 1 for i in range(10)) for s in m] for m in sinks], 10)
+    env = VecPBNEnv(net, 1024, aset, device="cuda:0", perturb_p=0.0)
+    env.set_state(torch.arange(1024, dtype=torch.int64).reshape(-1, 1), packed=True)
+    ids, steps = basin_labels(env, max_steps=512)
+    ids, steps = ids.cpu().numpy(), steps.cpu().numpy()
+    assert (ids >= 0).all()
+    can1, can0 = _successor_sets(net)
+    succ = [_successors(s, int(can1[s]), int(can0[s]), 10) for s in range(1024)]
+    reach = []                                   # attractors reachable from each state (backward closure per attractor)
+    pred = [[] for _ in range(1024)]
+    for s in range(1024):
+        for t in succ[s]:
+            pred[t].append(s)
+    for m in sinks:
+        seen, todo = set(m), list(m)
+        while todo:
+            for q in pred[todo.pop()]:
+                if q not in seen:
+                    seen.add(q)
+                    todo.append(q)
+        reach.append(seen)
+    for s in range(1024):
+        assert s in reach[ids[s]], s
+    for a, m in enumerate(sinks):
+        for s in m:
+            assert ids[s] == a and steps[s] == 0
+    env.close()
+
+
+def test_bench_runs_on_a_small_configuration():
+    """bench.py end to end (tiny batch): exactly one JSON line on stdout with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--envs", "8192", "--batches", "2", "--steps", "10", "--warmup", "3",
+                          "--no-cpu-baseline", "--e2e-steps", "2"], capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["steps"] == 10 and d["gpu_launches"] == 10 and d["value"] > 0 and d["roofline"]["bound"] == "hbm"
+    assert d["e2e"]["h2d_bytes_per_step"] == 8192 * 3
