@@ -37,9 +37,13 @@ EXPORTS = (
 
 
 class PbnError(RuntimeError):
-    def __init__(self, code: int, message: str):
+    def __init__(self, code: int, message: str = ""):
         super().__init__("pbn_b200 error %d: %s" % (code, message))
         self.code = code
+        self.message = message
+
+    def __reduce__(self):   # picklable (worker processes of build() report JIT failures)
+        return (PbnError, (self.code, self.message))
 
 
 class NetDesc(C.Structure):

@@ -147,7 +147,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 // Warm the L2 with a range that will be bulk-copied once the previous launch has completed (coherent: lines
 // the previous launch still writes are simply updated in place).
 __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+  if ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0ull)   // the bulk prefetch wants 16-byte aligned ranges; it is only a hint
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
