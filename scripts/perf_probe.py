@@ -77,10 +77,11 @@ def main():
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--split", default="", help="'pipe': pbn_predraw on a side stream + pbn_step with pre-drawn planes; 'main' / 'draw': either kernel alone")
     ap.add_argument("--graph-steps", type=int, default=32)
+    ap.add_argument("--p", type=float, default=0.001, help="perturbation probability of the 'full' row")
     args = ap.parse_args()
     net, attrs = bench.load_workload(args.net)
     W = net.n_words
-    rows = [("full (p=1e-3, reset, stats)", 0.001, True, True, True),
+    rows = [("full (p=%g, reset, stats)" % args.p, args.p, True, True, True),
             ("no perturbation", 0.0, True, True, True),
             ("no auto-reset", 0.001, False, True, True),
             ("no stats", 0.001, True, False, True),
