@@ -43,7 +43,7 @@
  *
  * Random streams (own-RNG mode): Philox4x32-10, key = (seed_lo, seed_hi),
  *   counter = (id_lo, id_hi, step_lo, (step_hi & 0xFFFF) | (kind << 28) | (idx << 16)),
- *   kind in {PBN_RNG_SELECT=0, PBN_RNG_PERTURB=1, PBN_RNG_RESET=2}, idx = block index < 4096.
+ *   kind in {PBN_RNG_SELECT=0, PBN_RNG_PERTURB=1, PBN_RNG_RESET=2, FIX=3 (sliced kernel)}, idx = block index < 4096.
  *   Scalar kernel: id = global env id (env_offset + e).  Gene i uses word i&3 of block
  *   (SELECT, i>>2): sel_i = #{k < K_i-1 : cum[k] <= word}.  Perturbation positions are drawn
  *   by geometric skipping: words of blocks (PERTURB, 0..) in order, skip = #{j in 1..N :

@@ -535,13 +535,13 @@ def sliced_survival(p: float, n: int) -> np.ndarray:
 class _WordStream:
     """Sequential 32-bit words of one (group, step, kind, sub-stream q) stream: blocks 64q + i."""
 
-    def __init__(self, gid, step_ctr, kind, k0, k1, q=0):
+    def __init__(self, gid, step_ctr, kind, k0, k1, q=0, first_word=0):
         self.gid, self.step, self.kind, self.k0, self.k1, self.q = gid, step_ctr, kind, k0, k1, q
-        self.next = 0
+        self.next = first_word
         self.blk = None
 
     def word(self):
-        if (self.next & 3) == 0:
+        if (self.next & 3) == 0 or self.blk is None:
             r = philox4x32(*_ctr(np.array([self.gid], dtype=np.uint64), self.step, self.kind,
                                  64 * self.q + ((self.next >> 2) & 63)), self.k0, self.k1)
             self.blk = [int(x[0]) for x in r]
@@ -591,15 +591,36 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
     for i, k in enumerate(ks):
         if k > 1:
             slot_of[i] = len(slot_of)
-    for g in range(ng):  # FIX sub-streams: one per (group, q = slot mod 4), shared by the slots q, q+4, ...
-        if not rej[g].any():
+    # FIX sub-streams: one per (group, q = slot mod 4), shared by the slots q, q+4, ... in that order.  The first six
+    # words of the sub-stream (block 0 and half of block 1) are three whole pair-planes (x, y), (z, w), (x', y'):
+    # rejection passes five to seven for the positions that survived a slot's own four -- but only at bits no earlier
+    # slot of the sub-stream has claimed (`taken`), so no random pair is used twice.  What is still rejected then (or
+    # was refused its bit) draws single 2-bit pairs from the rest of the sub-stream: words 6, 7, 8, ... (slots in
+    # order, lowest position first).
+    full = np.uint64(0xFFFFFFFF)
+    for q in range(4):
+        slots_q = [i for i in range(n) if i in slot_of and slot_of[i] % 4 == q and ks[i] == 3]
+        if not slots_q or not rej[:, slots_q].any():
             continue
-        for q in range(4):
-            ws = _WordStream(int(groups[g]), step_ctr, KIND_FIX, k0, k1, q)
+        blk_a = philox4x32(*_ctr(groups, step_ctr, KIND_FIX, 64 * q), k0, k1)
+        blk_b = philox4x32(*_ctr(groups, step_ctr, KIND_FIX, 64 * q + 1), k0, k1)
+        planes = [(blk_a[0].astype(np.uint64), blk_a[1].astype(np.uint64)), (blk_a[2].astype(np.uint64), blk_a[3].astype(np.uint64)),
+                  (blk_b[0].astype(np.uint64), blk_b[1].astype(np.uint64))]
+        taken = np.zeros(ng, dtype=np.uint64)
+        for i in slots_q:
+            r_ = rej[:, i].copy()
+            t = r_ & ~taken & full
+            taken |= r_
+            r_ &= ~t & full
+            for px, py in planes:
+                s0[:, i] = (s0[:, i] & ~t) | (px & t)
+                s1[:, i] = (s1[:, i] & ~t) | (py & t)
+                t = t & px & py
+            rej[:, i] = r_ | t
+        for g in np.nonzero(rej[:, slots_q].any(axis=1))[0]:
+            ws = _WordStream(int(groups[g]), step_ctr, KIND_FIX, k0, k1, q, first_word=6)
             cur, left = 0, 0
-            for i in range(n):
-                if i not in slot_of or slot_of[i] % 4 != q:
-                    continue
+            for i in slots_q:
                 r_ = int(rej[g, i])
                 while r_:
                     if left == 0:
