@@ -142,8 +142,9 @@ __device__ __forceinline__ void reset_pair(const NetParams& n, const Philox4& r,
     src = pair / A;
     tgt = pair - src * A;
   } else if (A > 1) {
+    // q = floor(x A (A-1) / 2^32), src = floor(q / (A-1)) = floor(x A / 2^32): no integer division needed
     const uint32_t q = __umulhi(r.x, (uint32_t)(A * (A - 1)));
-    src = (int)(q / (uint32_t)(A - 1));
+    src = (int)__umulhi(r.x, (uint32_t)A);
     const int tt = (int)(q - (uint32_t)src * (uint32_t)(A - 1));
     tgt = tt + (tt >= src ? 1 : 0);
   } else {
@@ -163,8 +164,9 @@ __device__ __forceinline__ void reset_draw(const NetParams& n, const Philox4& r,
     src = pair / A;
     tgt = pair - src * A;
   } else if (A > 1) {
+    // q = floor(x A (A-1) / 2^32), src = floor(q / (A-1)) = floor(x A / 2^32): no integer division needed
     const uint32_t q = __umulhi(r.x, (uint32_t)(A * (A - 1)));
-    src = (int)(q / (uint32_t)(A - 1));
+    src = (int)__umulhi(r.x, (uint32_t)A);
     const int tt = (int)(q - (uint32_t)src * (uint32_t)(A - 1));
     tgt = tt + (tt >= src ? 1 : 0);
   } else {
