@@ -838,8 +838,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     }
   }
   if (a.flags & PBN_STEP_AUTORESET) {
-    auto do_reset = [&](int i, const Philox4& r) {
-      const int64_t env = e0 + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
+    auto do_reset = [&](int64_t env, const Philox4& r) {
       uint64_t s[kW64];
       int src, tgt;
       if (attr_in_smem) {
@@ -859,19 +858,37 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       if (a.source_id != nullptr) a.source_id[env] = src;
       a.t[env] = 0;
     };
-    // two finished envs per trip: their Philox blocks are independent dependency chains
-    while (D) {
-      const int i0 = __ffs(D) - 1;
-      D &= D - 1u;
-      const bool two = D != 0u;
-      const int i1 = two ? __ffs(D) - 1 : i0;
-      D &= D - 1u;   // (0 stays 0)
-      const int64_t env0 = e0 + 128 * (2 * (int)w + (i0 >> 2)) + (i0 & 3);
-      const int64_t env1 = e0 + 128 * (2 * (int)w + (i1 >> 2)) + (i1 & 3);
-      const Philox4 r0 = philox_stream_rk((uint64_t)(a.env_offset + env0), step_ctr, PBN_RNG_RESET, 0, n.rk);
-      const Philox4 r1 = philox_stream_rk((uint64_t)(a.env_offset + env1), step_ctr, PBN_RNG_RESET, 0, n.rk);
-      do_reset(i0, r0);
-      if (two) do_reset(i1, r1);
+    // The finished envs of the warp (about 13 of its 256 per step) are dealt out over its lanes, one per lane and
+    // trip: a single Philox pass instead of a per-lane serial loop that runs for as long as the unluckiest lane.
+    __syncwarp();   // the reset of an env is written by another lane than its outputs in phase F: order the two stores
+    const uint32_t cnt = (uint32_t)__popc(D);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if ((int)lane >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint32_t excl = incl - cnt;
+    for (uint32_t base = 0; base < total; base += 32u) {   // warp-uniform trip count
+      const uint32_t j = base + lane;                      // the job of this lane
+      uint32_t L = 0u;                                     // owner: first lane whose inclusive count exceeds j
+#pragma unroll
+      for (int st = 16; st >= 1; st >>= 1) {
+        const uint32_t probe = __shfl_sync(0xFFFFFFFFu, incl, (int)min(L + (uint32_t)st - 1u, 31u));
+        if (L + (uint32_t)st - 1u < 32u && probe <= j) L += (uint32_t)st;
+      }
+      L = min(L, 31u);
+      const uint32_t eL = __shfl_sync(0xFFFFFFFFu, excl, (int)L);
+      const uint32_t DL = __shfl_sync(0xFFFFFFFFu, D, (int)L);
+      if (j < total) {
+        uint32_t m = DL;
+        for (uint32_t k = j - eL; k != 0u; --k) m &= m - 1u;   // drop the k lowest finished envs of the owner
+        const int i = __ffs(m) - 1;
+        const int64_t env = tile * 1024 + 4 * (int64_t)L + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
+        const Philox4 r = philox_stream_rk((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.rk);
+        do_reset(env, r);
+      }
     }
   }
 }
