@@ -95,7 +95,8 @@ enum {
    * its (state-independent) predictor-selection planes while the previous kernel in the stream is
    * still draining, and only then waits for it (griddepcontrol.wait).  With this flag the launch
    * does NOT increment *step_ctr_dev: pass the position inside the captured sequence as step_ctr
-   * and call pbn_advance_counter once at the end of the sequence. */
+   * and call pbn_advance_counter once at the end of the sequence.  Position 0 is launched fully
+   * serialised (it may follow the pbn_advance_counter of the previous sequence, whose write it reads). */
   PBN_STEP_PDL = 2u,
   /* Do not increment *step_ctr_dev when the launch completes (several launches that belong to the same
    * logical step, e.g. the chunks of pbn_step_host, share one counter value). */
@@ -184,7 +185,12 @@ void pbn_destroy(pbn_handle* h);
  * (model_tester.py:614-616, graph_classifier/__init__.py:129) read it.
  * attr_offset[A+1] CSR into care/value [S*W] (HOST pointers).  pair_cum: [A*A] cumulative
  * u32 thresholds over (source*A + target) pairs for reset sampling -- the curriculum of
- * env.rework_probas (bdq_model/__init__.py:203) -- or NULL = uniform over source != target. */
+ * env.rework_probas (bdq_model/__init__.py:203) -- or NULL = uniform over source != target.
+ * The device tables are allocated with spare capacity and updated IN PLACE by copies on `stream` (ordered
+ * after the steps already enqueued there): their addresses stay valid, so launches and CUDA graphs captured
+ * earlier never see freed memory.  Only when a table outgrows its capacity does the call synchronise `stream`
+ * and reallocate (graphs captured before that must be re-captured); table sizes travel in the kernel
+ * parameters, so a captured graph keeps using the sizes it was captured with.  Not legal during stream capture. */
 int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint64_t* care,
                           const uint64_t* value, int32_t n_attractors, const uint32_t* pair_cum,
                           void* stream);
@@ -320,8 +326,9 @@ int pbn_rollout_reduce(pbn_handle* h, const int32_t* count, const int32_t* pair_
  * Visit-count hash table in DEVICE memory: tags[capacity] (0 = empty slot), slot_state[capacity*W],
  * counts[capacity], capacity a power of two, all zero-initialised by the caller.  For every instance with
  * mask[e] != 0 (all if mask is NULL) counts[slot of state[e]] += 1; *overflow (DEVICE) counts states
- * that found no slot (table too full).  The tag of a state is the splitmix64-based fingerprint
- * documented in csrc/discover.cuh; distinct states with equal tags (probability 2^-64 per pair) merge. */
+ * that found no slot (table too full).  tags[] holds 2*state+1 for N <= 63 and a splitmix64 fingerprint
+ * otherwise (csrc/discover.cuh); a fingerprint match is confirmed against slot_state, so distinct states never
+ * merge.  The value 1 marks a slot whose state words are being published. */
 int pbn_visit_count(pbn_handle* h, const uint64_t* state, const uint8_t* mask, int64_t n_envs,
                     unsigned long long* tags, uint64_t* slot_state, unsigned long long* counts,
                     int64_t capacity, unsigned int* overflow, void* stream);
@@ -344,8 +351,8 @@ int pbn_closure_expand(pbn_handle* h, uint64_t* list, int64_t begin, int64_t end
                        unsigned long long* slot_index, int64_t capacity, int32_t max_free, int32_t* status,
                        void* stream);
 int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_t* flags,
-                      const unsigned long long* tags, const unsigned long long* slot_index, int64_t capacity,
-                      int32_t* changed, void* stream);
+                      const unsigned long long* tags, const uint64_t* slot_state,
+                      const unsigned long long* slot_index, int64_t capacity, int32_t* changed, void* stream);
 
 /* *step_ctr_dev += n on the stream (fully serialised): closes a sequence of PBN_STEP_PDL launches. */
 int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void* stream);

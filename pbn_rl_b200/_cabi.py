@@ -171,7 +171,7 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_successor_sets.restype = C.c_int
     lib.pbn_closure_expand.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.pbn_closure_expand.restype = C.c_int
-    lib.pbn_closure_reach.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, vp]
+    lib.pbn_closure_reach.argtypes = [vp, vp, i64, vp, vp, vp, vp, i64, vp, vp]
     lib.pbn_closure_reach.restype = C.c_int
     lib.pbn_predraw.argtypes = [vp, C.POINTER(StepArgs), vp, vp]
     lib.pbn_predraw.restype = C.c_int

@@ -15,48 +15,72 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
   return x;
 }
 
-// Fingerprint of a state: never 0 (0 marks an empty slot).  Documented so the host can re-derive it.
+// Key of a state in the tags[] column: never 0 (empty slot) and never 1 (kTagBusy).
+//   W == 1, N <= 63: tag = 2*state + 1  -- injective: distinct states never share a slot.
+//   otherwise      : a 64-bit splitmix64 fingerprint; a tag match is confirmed by comparing the state words in
+//                    slot_state (the claimer publishes them BEFORE the tag becomes visible), so distinct states
+//                    with equal fingerprints occupy different slots instead of being merged.
+constexpr unsigned long long kTagBusy = 1ull;
+
 template <int W>
-__device__ __forceinline__ uint64_t state_tag(const uint64_t (&s)[W]) {
+__device__ __forceinline__ uint64_t state_tag(const uint64_t (&s)[W], bool injective) {
+  if (W == 1 && injective) return (s[0] << 1) | 1ull;
   uint64_t h = mix64(s[0] + 0x9E3779B97F4A7C15ull);
   if (W == 2) h = mix64(h ^ (s[1] + 0xD1B54A32D192ED03ull));
-  return h == 0 ? 1ull : h;
+  return h < 2ull ? h + 2ull : h;
 }
 
 constexpr int kMaxProbe = 4096;
 
+template <int W>
+__device__ __forceinline__ bool slot_holds(const uint64_t* __restrict__ slot_state, uint64_t slot, const uint64_t (&s)[W]) {
+  bool same = true;
+#pragma unroll
+  for (int w = 0; w < W; ++w) same = same && reinterpret_cast<const volatile uint64_t*>(slot_state)[slot * W + w] == s[w];
+  return same;
+}
+
 // Insert-or-find in the open-addressing table: returns the slot (or -1 if no slot within kMaxProbe probes);
-// fresh = this call claimed the slot (exactly one caller per distinct tag sees fresh = true).
+// fresh = this call claimed the slot (exactly one caller per distinct state sees fresh = true).
+// Claim protocol: CAS 0 -> kTagBusy, write the state words, fence, store the tag.  A prober that meets kTagBusy
+// waits (bounded) for the tag: the claimer is always a running thread that needs nothing from the prober.
 template <int W>
 __device__ __forceinline__ int64_t hash_insert(const uint64_t (&s)[W], unsigned long long* __restrict__ tags,
-                                               uint64_t* __restrict__ slot_state, uint64_t cap_mask, bool& fresh) {
-  const uint64_t tag = state_tag<W>(s);
+                                               uint64_t* __restrict__ slot_state, uint64_t cap_mask, bool injective,
+                                               bool& fresh) {
+  const uint64_t tag = state_tag<W>(s, injective);
   uint64_t slot = mix64(tag) & cap_mask;
   fresh = false;
   for (int probe = 0; probe < kMaxProbe; ++probe, slot = (slot + 1) & cap_mask) {
-    unsigned long long cur = tags[slot];
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&tags[slot]);
     if (cur == 0ull) {
-      cur = atomicCAS(&tags[slot], 0ull, (unsigned long long)tag);
-      if (cur == 0ull) {  // claimed: publish the state (every later writer of this tag would write the same words)
+      cur = atomicCAS(&tags[slot], 0ull, kTagBusy);
+      if (cur == 0ull) {
 #pragma unroll
         for (int w = 0; w < W; ++w) slot_state[slot * W + w] = s[w];
+        __threadfence();
+        atomicExch(&tags[slot], (unsigned long long)tag);
         fresh = true;
         return (int64_t)slot;
       }
     }
-    if (cur == tag) return (int64_t)slot;
+    for (int spin = 0; cur == kTagBusy && spin < (1 << 16); ++spin) {
+      __nanosleep(20);
+      cur = *reinterpret_cast<volatile unsigned long long*>(&tags[slot]);
+    }
+    if (cur == tag && ((W == 1 && injective) || slot_holds<W>(slot_state, slot, s))) return (int64_t)slot;
   }
   return -1;
 }
 
 template <int W>
 __device__ __forceinline__ int64_t hash_find(const uint64_t (&s)[W], const unsigned long long* __restrict__ tags,
-                                             uint64_t cap_mask) {
-  const uint64_t tag = state_tag<W>(s);
+                                             const uint64_t* __restrict__ slot_state, uint64_t cap_mask, bool injective) {
+  const uint64_t tag = state_tag<W>(s, injective);
   uint64_t slot = mix64(tag) & cap_mask;
   for (int probe = 0; probe < kMaxProbe; ++probe, slot = (slot + 1) & cap_mask) {
     const unsigned long long cur = tags[slot];
-    if (cur == tag) return (int64_t)slot;
+    if (cur == tag && ((W == 1 && injective) || slot_holds<W>(slot_state, slot, s))) return (int64_t)slot;
     if (cur == 0ull) return -1;
   }
   return -1;
@@ -70,14 +94,14 @@ __global__ void __launch_bounds__(256) visit_count_kernel(const uint64_t* __rest
                                                          int64_t n_envs, unsigned long long* __restrict__ tags,
                                                          uint64_t* __restrict__ slot_state,
                                                          unsigned long long* __restrict__ counts, uint64_t cap_mask,
-                                                         unsigned int* __restrict__ overflow) {
+                                                         bool injective, unsigned int* __restrict__ overflow) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_envs; e += (int64_t)gridDim.x * blockDim.x) {
     if (mask != nullptr && mask[e] == 0) continue;
     uint64_t s[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) s[w] = state[e * W + w];
     bool fresh;
-    const int64_t slot = hash_insert<W>(s, tags, slot_state, cap_mask, fresh);
+    const int64_t slot = hash_insert<W>(s, tags, slot_state, cap_mask, injective, fresh);
     if (slot >= 0) atomicAdd(&counts[slot], 1ull); else atomicAdd(overflow, 1u);
   }
 }
@@ -138,7 +162,6 @@ struct ClosureShared {
   uint64_t fixed[W];
   int pos[kClosureMaxFree];
   int nfree;
-  int found;
   int abort;
 };
 
@@ -164,7 +187,6 @@ __device__ __forceinline__ void closure_prepare(const NetParams& n, const uint64
       }
     }
     sh.nfree = nf;
-    sh.found = 0;
   }
   __syncthreads();
 }
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(128) closure_expand_kernel(const __grid_consta
         uint64_t t[W];
         closure_successor<W>(sh, j, t);
         bool fresh;
-        const int64_t slot = hash_insert<W>(t, tags, slot_state, cap_mask, fresh);
+        const int64_t slot = hash_insert<W>(t, tags, slot_state, cap_mask, W == 1 && n.n_genes <= 63, fresh);
         if (slot < 0) {
           atomicMax(status, (int)kClosureTableFull);
         } else if (fresh) {
@@ -224,32 +246,35 @@ template <int W>
 __global__ void __launch_bounds__(128) closure_reach_kernel(const __grid_constant__ NetParams n, const uint64_t* __restrict__ list,
                                                            int64_t count, uint8_t* __restrict__ flags,
                                                            const unsigned long long* __restrict__ tags,
+                                                           const uint64_t* __restrict__ slot_state,
                                                            const unsigned long long* __restrict__ slot_index,
                                                            uint64_t cap_mask, int* __restrict__ changed) {
   __shared__ ClosureShared<W> sh;
+  const bool injective = W == 1 && n.n_genes <= 63;
   for (int64_t i = blockIdx.x; i < count; i += gridDim.x) {
-    if (flags[i] != 0) continue;      // uniform across the CTA
+    if (flags[i] != 0) continue;      // uniform across the CTA: flags[i] is only ever written by this CTA
     closure_prepare<W>(n, list, i, sh);
     const uint32_t total = 1u << (sh.nfree > kClosureMaxFree ? kClosureMaxFree : sh.nfree);
-    for (uint32_t j0 = 0; j0 < total; j0 += blockDim.x) {
+    bool found = false;               // CTA-uniform: decided by a barrier vote, never read from shared memory
+    for (uint32_t j0 = 0; j0 < total && !found; j0 += blockDim.x) {
       const uint32_t j = j0 + threadIdx.x;
+      bool hit = false;
       if (j < total) {
         uint64_t t[W];
         closure_successor<W>(sh, j, t);
-        const int64_t slot = hash_find<W>(t, tags, cap_mask);
+        const int64_t slot = hash_find<W>(t, tags, slot_state, cap_mask, injective);
         if (slot >= 0) {
           const unsigned long long k = slot_index[slot];
-          if (k != 0ull && flags[k - 1ull] != 0) sh.found = 1;
+          hit = k != 0ull && reinterpret_cast<const volatile uint8_t*>(flags)[k - 1ull] != 0;
         }
       }
-      __syncthreads();
-      if (sh.found) break;
+      found = __syncthreads_or(hit ? 1 : 0) != 0;
     }
-    if (threadIdx.x == 0 && sh.found) {
+    if (threadIdx.x == 0 && found) {
       flags[i] = 1;
       *changed = 1;
     }
-    __syncthreads();
+    __syncthreads();                  // sh is rewritten by the next entry's closure_prepare
   }
 }
 

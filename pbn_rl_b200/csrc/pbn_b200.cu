@@ -60,6 +60,24 @@ int upload(T** dptr, const T* host, size_t count, cudaStream_t stream = nullptr)
   return PBN_OK;
 }
 
+// Device table with spare capacity: updated in place on the caller's stream, reallocated (after a stream
+// synchronisation) only when it outgrows its capacity -- so pointers captured in CUDA graphs stay valid.
+template <typename T>
+int update_table(T** dptr, size_t* cap, const T* host, size_t count, cudaStream_t stream) {
+  if (count > *cap) {
+    PBN_CUDA(cudaStreamSynchronize(stream));  // kernels in flight may still read the old allocation
+    size_t ncap = *cap ? *cap : 64;
+    while (ncap < count) ncap *= 2;
+    if (*dptr) cudaFree(*dptr);
+    *dptr = nullptr;
+    *cap = 0;
+    PBN_CUDA(cudaMalloc(reinterpret_cast<void**>(dptr), ncap * sizeof(T)));
+    *cap = ncap;
+  }
+  if (count) PBN_CUDA(cudaMemcpyAsync(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice, stream));  // pageable source: staged before the call returns
+  return PBN_OK;
+}
+
 }  // namespace
 
 struct pbn_handle {
@@ -77,6 +95,7 @@ struct pbn_handle {
   uint64_t* d_attr_care = nullptr;
   uint64_t* d_attr_val = nullptr;
   uint32_t* d_pair_cum = nullptr;
+  size_t cap_attr_offset = 0, cap_attr_care = 0, cap_attr_val = 0, cap_pair_cum = 0;
   unsigned int* d_ticket = nullptr;
   uint32_t* d_surv_sliced = nullptr;
   WideDesc* d_wide = nullptr;
@@ -178,7 +197,10 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
   const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 8;
   if (grid > cap) grid = cap;
   void* args[] = {&p, &L};
-  if (a.flags & PBN_STEP_PDL) {
+  // The first step of a PDL sequence (position 0) is launched fully serialised: the launch before it may be the
+  // pbn_advance_counter of the previous sequence, whose write to *step_ctr_dev this kernel reads before its
+  // griddepcontrol.wait (visibility of a primary grid's writes is only guaranteed after the wait).
+  if ((a.flags & PBN_STEP_PDL) && a.step_ctr != 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)h->sliced_threads);
@@ -411,12 +433,10 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
     for (int a = 0; a < A; ++a)
       if (attr_offset[a + 1] <= attr_offset[a]) return fail(PBN_ERR_INVALID, "attractor %d is empty", a);
   }
-  // the previous tables may still be read by kernels in flight on the caller's stream
-  PBN_CUDA(cudaStreamSynchronize(stream));
   int rc;
-  if ((rc = upload(&h->d_attr_offset, attr_offset, (size_t)(A > 0 ? A + 1 : 0), stream)) != PBN_OK) return rc;
-  if ((rc = upload(&h->d_attr_care, care, (size_t)S * h->W, stream)) != PBN_OK) return rc;
-  if ((rc = upload(&h->d_attr_val, value, (size_t)S * h->W, stream)) != PBN_OK) return rc;
+  if ((rc = update_table(&h->d_attr_offset, &h->cap_attr_offset, attr_offset, (size_t)(A > 0 ? A + 1 : 0), stream)) != PBN_OK) return rc;
+  if ((rc = update_table(&h->d_attr_care, &h->cap_attr_care, care, (size_t)S * h->W, stream)) != PBN_OK) return rc;
+  if ((rc = update_table(&h->d_attr_val, &h->cap_attr_val, value, (size_t)S * h->W, stream)) != PBN_OK) return rc;
   int pair_last = 0;
   if (pair_cum && A > 0) {
     uint32_t prev = 0;
@@ -425,16 +445,13 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
       if (pair_cum[k] > prev || (k == 0 && pair_cum[0] > 0)) pair_last = k;
       prev = pair_cum[k];
     }
-    if ((rc = upload(&h->d_pair_cum, pair_cum, (size_t)A * A, stream)) != PBN_OK) return rc;
-  } else if (h->d_pair_cum) {
-    cudaFree(h->d_pair_cum);
-    h->d_pair_cum = nullptr;
+    if ((rc = update_table(&h->d_pair_cum, &h->cap_pair_cum, pair_cum, (size_t)A * A, stream)) != PBN_OK) return rc;
   }
   NetParams& n = h->net;
   n.attr_offset = h->d_attr_offset;
   n.attr_care = h->d_attr_care;
   n.attr_val = h->d_attr_val;
-  n.pair_cum = h->d_pair_cum;
+  n.pair_cum = (pair_cum && A > 0) ? h->d_pair_cum : nullptr;
   n.n_attr = A;
   n.n_attr_states = S;
   n.pair_last = pair_last;
@@ -468,6 +485,10 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   if (a->sel_planes && (reinterpret_cast<uintptr_t>(a->sel_planes) & 15u)) return fail(PBN_ERR_INVALID, "sel_planes must be 16-byte aligned");
   if (a->env_offset < 0 || (a->env_offset & 1023)) return fail(PBN_ERR_INVALID, "env_offset=%lld must be a non-negative multiple of 1024", (long long)a->env_offset);
   if (a->target_id && h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "target_id given but no attractor table uploaded");
+  {
+    const uint32_t known = PBN_STEP_AUTORESET | PBN_STEP_PDL | PBN_STEP_NO_COUNT | (jit::profile_build() ? 0x80000000u : 0u);
+    if (a->flags & ~known) return fail(PBN_ERR_INVALID, "unknown flag bits 0x%x", a->flags & ~known);
+  }
   if ((a->flags & PBN_STEP_PDL) && !a->step_ctr_dev) return fail(PBN_ERR_INVALID, "PBN_STEP_PDL needs step_ctr_dev");
   if (a->flags & PBN_STEP_AUTORESET) {
     if (h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "auto-reset needs pbn_update_attractors first");
@@ -885,8 +906,8 @@ int pbn_visit_count(pbn_handle* h, const uint64_t* state, const uint8_t* mask, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DeviceGuard guard(h->device);
   const int grid = grid_for(h, n_envs, 256, 8);
-  if (h->W == 1) visit_count_kernel<1><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, overflow);
-  else visit_count_kernel<2><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, overflow);
+  if (h->W == 1) visit_count_kernel<1><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, h->net.n_genes <= 63, overflow);
+  else visit_count_kernel<2><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, false, overflow);
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
   return PBN_OK;
@@ -924,15 +945,16 @@ int pbn_closure_expand(pbn_handle* h, uint64_t* list, int64_t begin, int64_t end
 }
 
 int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_t* flags, const unsigned long long* tags,
-                      const unsigned long long* slot_index, int64_t capacity, int32_t* changed, void* stream_) {
-  if (!h || !list || !flags || !tags || !slot_index || !changed || count < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+                      const uint64_t* slot_state, const unsigned long long* slot_index, int64_t capacity, int32_t* changed,
+                      void* stream_) {
+  if (!h || !list || !flags || !tags || !slot_state || !slot_index || !changed || count < 0) return fail(PBN_ERR_INVALID, "bad arguments");
   if (capacity < 2 || (capacity & (capacity - 1))) return fail(PBN_ERR_INVALID, "capacity=%lld must be a power of two >= 2", (long long)capacity);
   if (count == 0) return PBN_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DeviceGuard guard(h->device);
   const int grid = grid_for(h, count * 128, 128, 16);
-  if (h->W == 1) closure_reach_kernel<1><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_index, (uint64_t)capacity - 1, changed);
-  else closure_reach_kernel<2><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_index, (uint64_t)capacity - 1, changed);
+  if (h->W == 1) closure_reach_kernel<1><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_state, slot_index, (uint64_t)capacity - 1, changed);
+  else closure_reach_kernel<2><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_state, slot_index, (uint64_t)capacity - 1, changed);
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
   return PBN_OK;

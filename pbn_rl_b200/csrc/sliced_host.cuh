@@ -368,14 +368,23 @@ inline void write_file_atomic(const std::string& path, const std::vector<char>& 
   else unlink(t.c_str());
 }
 
+// PBN_B200_PROFILE=1: compile the %globaltimer phase stamps in (development builds only; flag bit 31 is
+// rejected by the ABI otherwise).
+inline bool profile_build() {
+  const char* env = getenv("PBN_B200_PROFILE");
+  return env && env[0] && env[0] != '0';
+}
+
 // Compile (or fetch from the cache) the specialisation; returns 0 or PBN_ERR_JIT with *err set.
 inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std::string* err) {
   std::string gen_h, upd;
   generate(g, injected, &gen_h, &upd);
   const std::string main_src = main_source();
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  const bool profile = profile_build();
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DPBN_PROFILE=1"};
+  const int n_opts = profile ? 5 : 4;
   std::string key = gen_h + upd + main_src + kSrc_step_sliced + kSrc_pbn_common + kSrc_philox + kSrc_pbn_b200_h;
-  for (const char* o : opts) key += o;
+  for (int i = 0; i < n_opts; ++i) key += opts[i];
   char name[64];
   snprintf(name, sizeof(name), "/sliced_%016llx.cubin", (unsigned long long)fnv1a(key));
   const std::string dir = cache_dir(), path = dir + name;
@@ -395,7 +404,7 @@ inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std
     *err = "nvrtcCreateProgram failed";
     return PBN_ERR_JIT;
   }
-  rc = n.CompileProgram(prog, 4, opts);
+  rc = n.CompileProgram(prog, n_opts, opts);
   if (rc != 0) {
     size_t ls = 0;
     std::string log;

@@ -165,19 +165,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Development aid: with flag bit 31 set, thread 0 of CTA 0 writes %globaltimer stamps (ns) of the phase
+// Development aid, compiled only into specialisations built with PBN_B200_PROFILE=1 in the environment
+// (scripts/phase_probe.py): with flag bit 31 set, thread 0 of CTA 0 writes %globaltimer stamps (ns) of the phase
 // boundaries into final_state[E*W .. E*W+15], and thread 0 of every CTA its start/end stamps (+ SM id in
 // the top byte) into final_state[E*W + 16 + 8*blockIdx + {0,7}] (1: input copy arrived, 2: out planes done,
 // 3..6: after phases E, D, F, G):
 // the caller provides the extra words.
 __device__ __forceinline__ void phase_stamp(const pbn_step_args& a, int i) {
+#ifdef PBN_PROFILE
   if ((a.flags & 0x80000000u) && blockIdx.x == 0 && threadIdx.x == 0 && a.final_state != nullptr) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     a.final_state[a.n_envs * kW64 + i] = t;
   }
+#else
+  (void)a; (void)i;
+#endif
 }
 __device__ __forceinline__ void cta_stamp(const pbn_step_args& a, int which) {
+#ifdef PBN_PROFILE
   if ((a.flags & 0x80000000u) && threadIdx.x == 0 && a.final_state != nullptr) {
     unsigned long long t;
     unsigned int smid;
@@ -186,6 +192,9 @@ __device__ __forceinline__ void cta_stamp(const pbn_step_args& a, int which) {
     a.final_state[a.n_envs * kW64 + 16 + 8 * blockIdx.x + which] =
         (t & 0x00FFFFFFFFFFFFFFull) | ((unsigned long long)smid << 56);
   }
+#else
+  (void)a; (void)which;
+#endif
 }
 
 __device__ __forceinline__ uint32_t pick4(const Philox4& b, uint32_t q) {

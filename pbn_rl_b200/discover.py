@@ -235,7 +235,7 @@ def attractor_reached_from(env: VecPBNEnv, seed_state: int, ws: Optional[_Closur
         while True:
             ws.changed.zero_()
             check(lib.pbn_closure_reach(h, ws.list.data_ptr(), count, ws.flags.data_ptr(), ws.tags.data_ptr(),
-                                        ws.slot_index.data_ptr(), ws.capacity, ws.changed.data_ptr(), env._stream()))
+                                        ws.slot_state.data_ptr(), ws.slot_index.data_ptr(), ws.capacity, ws.changed.data_ptr(), env._stream()))
             if int(ws.changed.item()) == 0:
                 break
         flags = ws.flags[:count]
