@@ -174,6 +174,10 @@ typedef struct {
   uint32_t reserved;
   const uint32_t* sel_planes;   /* [pbn_planes_words()] predictor-selection planes of THIS step drawn earlier by
                                    pbn_predraw (sliced kernel only), or NULL: the step draws them itself */
+  uint32_t* resident;           /* [pbn_resident_words()] plane-resident env state (see pbn_resident_import) or NULL.
+                                   When given, it replaces state / target_id / t (which must be NULL): the step
+                                   reads and writes the env state in the resident block; the per-env results
+                                   reward / terminated / truncated are produced as usual */
 } pbn_step_args;
 
 /* gym.make(...) construction: upload truth tables and constants, pick the kernel. */
@@ -236,6 +240,24 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* args, const pbn_host_io* i
  * args->sel_planes.  Returns PBN_ERR_UNSUPPORTED for handles running the scalar kernel. */
 int pbn_predraw(pbn_handle* h, const pbn_step_args* args, uint32_t* planes, void* stream);
 int64_t pbn_planes_words(const pbn_handle* h, int64_t n_envs);
+
+/* ---- Plane-resident env state (sliced kernel) -----------------------------------------------------------
+ * The env state an agent never looks at between steps -- packed states, target ids, episode counters -- can
+ * live on the device in the layout the bit-sliced kernel computes in (bit-planes over tiles of 1024 envs,
+ * csrc/step_planes.cuh), so that a step neither transposes nor touches per-env state words: pbn_step with
+ * args->resident set is the fastest form of env.step (bdq_model/__init__.py:177).  The row-format arrays of
+ * pbn_step_args stay the boundary format: pbn_resident_import builds the block from them (state words,
+ * target ids -- negative or >= min(A, 255) = no target --, counters; needs the attractor table for the
+ * target planes, so call it after pbn_update_attractors), pbn_resident_export writes them back (any output
+ * may be NULL).  Results are bit-identical to pbn_step on the row-format arrays (same random streams).
+ * Supported: networks the sliced kernel takes, at most 254 attractors, and either single-state attractors
+ * without wildcards (any number) or attractor tables of at most 256 (care, value) entries.
+ * pbn_resident_words: size of the block in 32-bit words (whole tiles; 128-byte aligned memory). */
+int64_t pbn_resident_words(const pbn_handle* h, int64_t n_envs);
+int pbn_resident_import(pbn_handle* h, uint32_t* resident, const uint64_t* state, const int32_t* target_id,
+                        const uint16_t* t, int64_t n_envs, void* stream);
+int pbn_resident_export(pbn_handle* h, const uint32_t* resident, uint64_t* state, int32_t* target_id,
+                        uint16_t* t, int64_t n_envs, void* stream);
 
 /* n_steps uncontrolled network updates of every instance in ONE launch (env.step([]) n_steps times,
  * graph_classifier/__init__.py:148; the burn-in of the attractor search; the long runs of compute_ssd_hist,

@@ -560,81 +560,48 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
     groups, inv = np.unique(gid, return_inverse=True)
     ng = len(groups)
     ks = [len(ps) for ps in net.probs]
-    nw = {1: 0, 2: 8, 4: 8, 3: 8}  # every gene with K > 1 owns a slot of two Philox blocks
-    total_words = sum(nw[k] for k in ks)
-    n_blocks = (total_words + 3) // 4
-    words = np.zeros((ng, max(4 * n_blocks, 4)), dtype=np.uint64)
-    for b in range(n_blocks):
-        r = philox4x32(*_ctr(groups, step_ctr, KIND_SELECT, b), k0, k1)
-        for q in range(4):
-            words[:, 4 * b + q] = r[q]
+    full = np.uint64(0xFFFFFFFF)
     s0 = np.zeros((ng, n), dtype=np.uint64)
     s1 = np.zeros((ng, n), dtype=np.uint64)
-    rej = np.zeros((ng, n), dtype=np.uint64)
-    off = 0
-    for i, k in enumerate(ks):
-        w = [words[:, off + q] for q in range(nw[k])]
-        off += nw[k]
-        if k == 2:
-            s0[:, i] = w[0]
-        elif k == 4:
-            s0[:, i], s1[:, i] = w[0], w[1]
-        elif k == 3:
-            b0, b1 = w[0].copy(), w[1].copy()
-            r_ = b0 & b1
-            for c0, c1 in ((w[2], w[3]), (w[4], w[5]), (w[6], w[7])):
-                b0 = np.where(True, (b0 & ~r_) | (c0 & r_), b0)
-                b1 = (b1 & ~r_) | (c1 & r_)
-                r_ = r_ & c0 & c1
-            s0[:, i], s1[:, i], rej[:, i] = b0, b1, r_
-    slot_of = {}
-    for i, k in enumerate(ks):
-        if k > 1:
-            slot_of[i] = len(slot_of)
-    # FIX sub-streams: one per (group, q = slot mod 4), shared by the slots q, q+4, ... in that order.  The first six
-    # words of the sub-stream (block 0 and half of block 1) are three whole pair-planes (x, y), (z, w), (x', y'):
-    # rejection passes five to seven for the positions that survived a slot's own four -- but only at bits no earlier
-    # slot of the sub-stream has claimed (`taken`), so no random pair is used twice.  What is still rejected then (or
-    # was refused its bit) draws single 2-bit pairs from the rest of the sub-stream: words 6, 7, 8, ... (slots in
-    # order, lowest position first).
-    full = np.uint64(0xFFFFFFFF)
-    for q in range(4):
-        slots_q = [i for i in range(n) if i in slot_of and slot_of[i] % 4 == q and ks[i] == 3]
-        if not slots_q or not rej[:, slots_q].any():
+    slot_gene = [i for i, k in enumerate(ks) if k > 1]
+    # SELECT: slot r (the r-th gene with K > 1) owns block (SELECT, r) = words x, y, z, w.  K=2: s0 = x; K=4: (s0, s1) =
+    # (x, y); K=3: the pairs (x, y), (z, w) -- pair value 3 is rejected and replaced by the next pair.
+    for r, i in enumerate(slot_gene):
+        x, y, z, w = (v.astype(np.uint64) for v in philox4x32(*_ctr(groups, step_ctr, KIND_SELECT, r), k0, k1))
+        if ks[i] == 2:
+            s0[:, i] = x
+        elif ks[i] == 4:
+            s0[:, i], s1[:, i] = x, y
+        elif ks[i] == 3:
+            rj = x & y
+            s0[:, i] = (x & ~rj & full) | (z & rj)
+            s1[:, i] = (y & ~rj & full) | (w & rj)
+        else:
+            raise ValueError("the sliced kernel takes 1..4 predictors per gene")
+    # Pool of part q = r mod 8: blocks (FIX, 512 q + i), i = 0, 1, ...; each block is two pair-planes (x, y), (z, w).
+    # Per pair-plane the part's K=3 slots, in slot order, take bit b if they are still at value 3 there and no earlier
+    # slot of the part has claimed bit b of this plane.  Blocks are consumed until no slot of the part is at 3
+    # anywhere in the column (columns that are done ignore further blocks).
+    for q in range(8):
+        slots_q = [i for r, i in enumerate(slot_gene) if r % 8 == q and ks[i] == 3]
+        if not slots_q:
             continue
-        blk_a = philox4x32(*_ctr(groups, step_ctr, KIND_FIX, 64 * q), k0, k1)
-        blk_b = philox4x32(*_ctr(groups, step_ctr, KIND_FIX, 64 * q + 1), k0, k1)
-        planes = [(blk_a[0].astype(np.uint64), blk_a[1].astype(np.uint64)), (blk_a[2].astype(np.uint64), blk_a[3].astype(np.uint64)),
-                  (blk_b[0].astype(np.uint64), blk_b[1].astype(np.uint64))]
-        taken = np.zeros(ng, dtype=np.uint64)
-        for i in slots_q:
-            r_ = rej[:, i].copy()
-            t = r_ & ~taken & full
-            taken |= r_
-            r_ &= ~t & full
-            for px, py in planes:
-                s0[:, i] = (s0[:, i] & ~t) | (px & t)
-                s1[:, i] = (s1[:, i] & ~t) | (py & t)
-                t = t & px & py
-            rej[:, i] = r_ | t
-        for g in np.nonzero(rej[:, slots_q].any(axis=1))[0]:
-            ws = _WordStream(int(groups[g]), step_ctr, KIND_FIX, k0, k1, q, first_word=6)
-            cur, left = 0, 0
+        for it in range(512):
+            rej_any = np.zeros(ng, dtype=np.uint64)
             for i in slots_q:
-                r_ = int(rej[g, i])
-                while r_:
-                    if left == 0:
-                        cur, left = ws.word(), 16
-                    pr = cur & 3
-                    cur >>= 2
-                    left -= 1
-                    if pr != 3:
-                        m = r_ & -r_
-                        r_ ^= m
-                        if not pr & 1:
-                            s0[g, i] = int(s0[g, i]) ^ m
-                        if not pr & 2:
-                            s1[g, i] = int(s1[g, i]) ^ m
+                rej_any |= s0[:, i] & s1[:, i]
+            act = np.nonzero(rej_any)[0]
+            if len(act) == 0:
+                break
+            blk = [v.astype(np.uint64) for v in philox4x32(*_ctr(groups[act], step_ctr, KIND_FIX, 512 * q + it), k0, k1)]
+            for px, py in ((blk[0], blk[1]), (blk[2], blk[3])):
+                av = np.full(len(act), full, dtype=np.uint64)
+                for i in slots_q:
+                    rj = s0[act, i] & s1[act, i]
+                    tk = rj & av
+                    av &= ~rj & full
+                    s0[act, i] = (s0[act, i] & ~tk & full) | (px & tk)
+                    s1[act, i] = (s1[act, i] & ~tk & full) | (py & tk)
     sh = bit.astype(np.uint64)[:, None]
     sel = (((s0[inv] >> sh) & np.uint64(1)) + 2 * ((s1[inv] >> sh) & np.uint64(1))).astype(np.uint8)
     for i, k in enumerate(ks):

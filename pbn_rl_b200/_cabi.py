@@ -33,6 +33,7 @@ EXPORTS = (
     "pbn_observe", "pbn_in_target", "pbn_rollout_track", "pbn_rollout_reduce",
     "pbn_visit_count", "pbn_successor_sets", "pbn_closure_expand", "pbn_closure_reach",
     "pbn_predraw", "pbn_planes_words", "pbn_rollout",
+    "pbn_resident_words", "pbn_resident_import", "pbn_resident_export",
 )
 
 
@@ -95,6 +96,7 @@ class StepArgs(C.Structure):
         ("flags", C.c_uint32),
         ("reserved", C.c_uint32),
         ("sel_planes", C.c_void_p),
+        ("resident", C.c_void_p),
     ]
 
 
@@ -177,6 +179,12 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_predraw.restype = C.c_int
     lib.pbn_planes_words.argtypes = [vp, i64]
     lib.pbn_planes_words.restype = i64
+    lib.pbn_resident_words.argtypes = [vp, i64]
+    lib.pbn_resident_words.restype = i64
+    lib.pbn_resident_import.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+    lib.pbn_resident_import.restype = C.c_int
+    lib.pbn_resident_export.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+    lib.pbn_resident_export.restype = C.c_int
     lib.pbn_rollout.argtypes = [vp, vp, i64, u64, i64, i64, vp, vp]
     lib.pbn_rollout.restype = C.c_int
     lib.pbn_step_injected.argtypes = [vp, C.POINTER(StepArgs), vp]

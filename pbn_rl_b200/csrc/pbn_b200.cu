@@ -14,6 +14,7 @@
 #include "replay.cuh"
 #include "evaluate.cuh"
 #include "discover.cuh"
+#include "resident.cuh"
 
 using namespace pbn;
 
@@ -104,6 +105,8 @@ struct pbn_handle {
   jit::GenNet gen;
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
   cudaKernel_t jit_kernel[2] = {nullptr, nullptr};
+  cudaKernel_t planes_kernel[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [injected][0: 4 warps, 1: 8 warps] pbn_step_planes_w*
+  uint32_t planes_smem_opt_in[2][2] = {{48u * 1024u, 48u * 1024u}, {48u * 1024u, 48u * 1024u}};
   cudaKernel_t predraw_kernel = nullptr;  // pbn_predraw_sliced of the own-RNG specialisation
   cudaKernel_t rollout_kernel = nullptr;  // pbn_rollout_sliced
   uint32_t rollout_smem_opt_in = 48u * 1024u;
@@ -126,6 +129,8 @@ static int load_sliced(pbn_handle* h, int injected) {
   if (jit::compile(h->gen, injected != 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
   PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
+  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][0], h->jit_lib[injected], "pbn_step_planes_w4"));
+  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][1], h->jit_lib[injected], "pbn_step_planes_w8"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->predraw_kernel, h->jit_lib[0], "pbn_predraw_sliced"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->rollout_kernel, h->jit_lib[0], "pbn_rollout_sliced"));
   if (!injected) {  // the survival table of the perturbation sub-streams lives in the specialisation's constant memory
@@ -214,6 +219,74 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
     PBN_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(k), args));
   } else {
     PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, L.total, stream));
+  }
+  return PBN_OK;
+}
+
+// Which networks / attractor tables the plane-resident kernel takes (include/pbn_b200.h "Plane-resident env state").
+static int resident_supported(const pbn_handle* h) {
+  if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state needs the sliced kernel");
+  if (h->net.n_attr > 254) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: %d attractors > 254", h->net.n_attr);
+  if (h->net.n_attr > 0 && !h->net.attr_simple && h->net.n_attr_states > 256)
+    return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: attractor table with %d (care, value) entries > 256 and several states per attractor", h->net.n_attr_states);
+  return PBN_OK;
+}
+
+static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream_t stream) {
+  const pbn_step_args& a = p.a;
+  int rc = resident_supported(h);
+  if (rc != PBN_OK) return rc;
+  if (!aligned_to(a.resident, 128) || !aligned_to(a.reward, 16) || !aligned_to(a.actions, 4) || !aligned_to(a.terminated, 4) || !aligned_to(a.truncated, 4))
+    return fail(PBN_ERR_INVALID, "plane-resident step needs a 128-byte aligned block, 16-byte aligned reward, 4-byte aligned actions / flags");
+  if ((rc = load_sliced(h, injected ? 1 : 0)) != PBN_OK) return rc;
+  const NetParams& n = h->net;
+  const int N = n.n_genes, NW = (N + 31) / 32;
+  PlanesLayout L{};
+  uint32_t o = (uint32_t)(32 * resident_rows(N) + 32 * N + 256) * 4u;   // IN block | O planes | misc (step_planes.cuh)
+  const uint32_t tab = (uint32_t)n.n_attr_states * NW * 4u * (n.attr_simple ? 1u : 2u) + (uint32_t)(n.n_attr + 1) * 4u + (uint32_t)n.n_attr_states + 64u;
+  L.attr_in_smem = (n.n_attr > 0 && (tab <= 24u * 1024u || !n.attr_simple)) ? 1u : 0u;
+  if (L.attr_in_smem) {
+    L.aval_off = o;
+    o += (uint32_t)n.n_attr_states * NW * 4u;
+    L.acare_off = o;
+    if (!n.attr_simple) o += (uint32_t)n.n_attr_states * NW * 4u;
+    L.aoffs_off = o;
+    o += (uint32_t)(n.n_attr + 1) * 4u;
+    L.eattr_off = o;
+    if (!n.attr_simple) o += (uint32_t)n.n_attr_states;
+    o = (o + 15u) & ~15u;
+  }
+  L.total = o;
+  if (L.total > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "plane-resident kernel needs %u B of shared memory", L.total);
+  const int64_t tiles = (a.n_envs + 1023) / 1024;
+  // 8 warps per tile halve a tile's latency (small batches: one CTA per SM or less); 4 warps per tile keep 8 tiles
+  // per SM in flight (large batches).  Both draw the same streams.
+  int v = (N > 32 || tiles < 2 * (int64_t)h->num_sms) ? 1 : 0;
+  if (const char* env = getenv("PBN_B200_PLANES_WARPS")) v = atoi(env) == 8 ? 1 : 0;
+  cudaKernel_t k = h->planes_kernel[injected ? 1 : 0][v];
+  if (L.total > h->planes_smem_opt_in[injected ? 1 : 0][v]) {
+    PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    h->planes_smem_opt_in[injected ? 1 : 0][v] = L.total;
+  }
+  int64_t grid = tiles;
+  const int64_t cap = (int64_t)h->num_sms * 64;
+  if (grid > cap) grid = cap;
+  const unsigned threads = v ? 256u : 128u;
+  void* args[] = {&p, &L};
+  if ((a.flags & PBN_STEP_PDL) && a.step_ctr != 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = L.total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PBN_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(k), args));
+  } else {
+    PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((unsigned)grid), dim3(threads), args, L.total, stream));
   }
   return PBN_OK;
 }
@@ -478,7 +551,13 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   if (!h || !a) return fail(PBN_ERR_INVALID, "null argument");
   if (a->n_envs < 0) return fail(PBN_ERR_INVALID, "n_envs=%lld", (long long)a->n_envs);
   if (a->n_envs == 0) return PBN_OK;
-  if (!a->state) return fail(PBN_ERR_INVALID, "state is null");
+  if (a->resident) {
+    if (a->state || a->target_id || a->t || a->final_state || a->sel_planes)
+      return fail(PBN_ERR_INVALID, "plane-resident step: state / target_id / t / final_state / sel_planes must be null (the block holds them)");
+    if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state needs the sliced kernel");
+  } else if (!a->state) {
+    return fail(PBN_ERR_INVALID, "state is null");
+  }
   if (injected && !a->sel) return fail(PBN_ERR_INVALID, "pbn_step_injected needs args->sel");
   if (!injected && (a->sel || a->pert_mask)) return fail(PBN_ERR_INVALID, "pbn_step: sel/pert_mask must be null (use pbn_step_injected)");
   if (a->sel_planes && (injected || h->kernel != PBN_KERNEL_SLICED)) return fail(PBN_ERR_UNSUPPORTED, "sel_planes: pre-drawn selection planes are taken by pbn_step with the sliced kernel only");
@@ -492,7 +571,7 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   if ((a->flags & PBN_STEP_PDL) && !a->step_ctr_dev) return fail(PBN_ERR_INVALID, "PBN_STEP_PDL needs step_ctr_dev");
   if (a->flags & PBN_STEP_AUTORESET) {
     if (h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "auto-reset needs pbn_update_attractors first");
-    if (!a->target_id || !a->t) return fail(PBN_ERR_INVALID, "auto-reset needs target_id and t");
+    if (!a->resident && (!a->target_id || !a->t)) return fail(PBN_ERR_INVALID, "auto-reset needs target_id and t");
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DeviceGuard guard(h->device);
@@ -501,7 +580,7 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   p.n = h->net;
   p.ticket = h->d_ticket;
   if (h->kernel == PBN_KERNEL_SLICED) {
-    const int rc = launch_sliced(h, p, injected, stream);
+    const int rc = a->resident ? launch_planes(h, p, injected, stream) : launch_sliced(h, p, injected, stream);
     if (rc == PBN_OK) h->launches += 1;
     return rc;
   }
@@ -955,6 +1034,43 @@ int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_
   const int grid = grid_for(h, count * 128, 128, 16);
   if (h->W == 1) closure_reach_kernel<1><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_state, slot_index, (uint64_t)capacity - 1, changed);
   else closure_reach_kernel<2><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_state, slot_index, (uint64_t)capacity - 1, changed);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int64_t pbn_resident_words(const pbn_handle* h, int64_t n_envs) {
+  if (!h || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  const int64_t tiles = (n_envs + 1023) / 1024;
+  return (tiles > 0 ? tiles : 1) * 32 * (int64_t)resident_rows(h->net.n_genes);
+}
+
+int pbn_resident_import(pbn_handle* h, uint32_t* resident, const uint64_t* state, const int32_t* target_id, const uint16_t* t,
+                        int64_t n_envs, void* stream_) {
+  if (!h || !resident || !state || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  int rc = resident_supported(h);
+  if (rc != PBN_OK) return rc;
+  if (n_envs == 0) return PBN_OK;
+  if (target_id && h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "target_id given but no attractor table uploaded");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, ((n_envs + 1023) / 1024) * 1024, 256, 8);
+  if (h->W == 1) resident_import_kernel<1><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
+  else resident_import_kernel<2><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
+  PBN_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return PBN_OK;
+}
+
+int pbn_resident_export(pbn_handle* h, const uint32_t* resident, uint64_t* state, int32_t* target_id, uint16_t* t,
+                        int64_t n_envs, void* stream_) {
+  if (!h || !resident || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
+  if (n_envs == 0) return PBN_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard(h->device);
+  const int grid = grid_for(h, ((n_envs + 1023) / 1024) * 1024, 256, 8);
+  if (h->W == 1) resident_export_kernel<1><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
+  else resident_export_kernel<2><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
   return PBN_OK;

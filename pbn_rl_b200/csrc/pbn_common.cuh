@@ -111,6 +111,13 @@ struct SlicedSmemLayout {
   uint32_t attractors_in_smem;
 };
 
+// Dynamic shared-memory layout of the plane-resident kernel's attractor tables (byte offsets; the fixed part of
+// the layout is compile-time, step_planes.cuh).
+struct PlanesLayout {
+  uint32_t aval_off, acare_off, aoffs_off, eattr_off, total;
+  uint32_t attr_in_smem;
+};
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // number of entries k in the non-increasing table tab[1..n] with u < tab[k]   (geometric skip)

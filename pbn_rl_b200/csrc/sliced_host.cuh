@@ -29,6 +29,7 @@ struct GenFunc {
 
 struct GenNet {
   int n_genes = 0, bins = 3, pert_mode = 0;
+  bool pert_rng = false;  // perturb_p > 0: the own-RNG specialisation draws perturbation events
   std::vector<std::vector<GenFunc>> funcs;  // per gene
 };
 
@@ -66,6 +67,7 @@ inline GenNet gen_net_from_desc(const pbn_net_desc* d) {
   g.n_genes = d->n_genes;
   g.bins = d->bins;
   g.pert_mode = d->perturb_mode;
+  g.pert_rng = d->perturb_p > 0.0;
   g.funcs.resize(d->n_genes);
   for (int i = 0; i < d->n_genes; ++i)
     for (int f = d->func_offset[i]; f < d->func_offset[i + 1]; ++f) {
@@ -169,6 +171,163 @@ inline int sliced_min_blocks(const GenNet& g) {
   return g.n_genes <= 32 ? 8 : (g.n_genes <= 64 ? 4 : 2);
 }
 
+
+// Selection groups ("parts"): slot r belongs to part r mod 8; a part draws its slots' selection planes
+// (pbn_draw_part: one private Philox block per slot, then the part's shared pool of pair-planes for the 1/16 of the
+// 1-of-3 draws that are still rejected -- see step_planes.cuh "Random streams") and evaluates its genes
+// (pbn_eval_part, plane-resident kernel).  Single-predictor genes are spread over the parts by load.
+inline void generate_parts(const GenNet& g, std::string& u) {
+  const int N = g.n_genes;
+  char buf[320];
+  std::vector<int> part(N, 0), slot_of(N, -1);
+  int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int slot = 0;
+  for (int i = 0; i < N; ++i)
+    if (g.funcs[i].size() > 1) {
+      slot_of[i] = slot;
+      part[i] = slot & 7;
+      load[slot & 7] += (int)g.funcs[i].size() + 2;
+      ++slot;
+    }
+  for (int i = 0; i < N; ++i)
+    if (g.funcs[i].size() == 1) {
+      int best = 0;
+      for (int q = 1; q < 8; ++q)
+        if (load[q] < load[best]) best = q;
+      part[i] = best;
+      load[best] += 1;
+    }
+  u += "\n#define PBN_CLAIM(k, px, py) { const uint32_t rj_ = lo[k] & hi[k]; const uint32_t tk_ = rj_ & av; av &= ~rj_; "
+       "lo[k] = bmux(tk_, px, lo[k]); hi[k] = bmux(tk_, py, hi[k]); }\n";
+  u += "// selection planes of part q: lo[k] + 2*hi[k] = predictor index of slot r = q + 8k, bit-sliced over the column's 32 envs\n";
+  u += "__device__ __forceinline__ void pbn_draw_part(uint32_t q, uint64_t gid, uint64_t step, const uint32_t (&rk)[20],\n"
+       "                                              uint32_t (&lo)[PBN_MAXS], uint32_t (&hi)[PBN_MAXS]) {\n";
+  u += "#pragma unroll\n  for (int k = 0; k < PBN_MAXS; ++k) { lo[k] = 0u; hi[k] = 0u; }\n";
+  for (int q = 0; q < 8; ++q) {
+    std::vector<int> ks;  // K of the part's slots, in slot order
+    for (int i = 0; i < N; ++i)
+      if (slot_of[i] >= 0 && (slot_of[i] & 7) == q) ks.push_back((int)g.funcs[i].size());
+    if (ks.empty()) continue;
+    snprintf(buf, sizeof(buf), "  if (q == %du) {\n", q);
+    u += buf;
+    std::string any;
+    for (size_t k = 0; k < ks.size(); ++k) {
+      const int r = q + 8 * (int)k;
+      snprintf(buf, sizeof(buf), "    { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, %du, rk);  // slot %d, K = %d\n", r, r, ks[k]);
+      u += buf;
+      if (ks[k] == 2) {
+        snprintf(buf, sizeof(buf), "      lo[%zu] = A.x; }\n", k);
+      } else if (ks[k] == 4) {
+        snprintf(buf, sizeof(buf), "      lo[%zu] = A.x; hi[%zu] = A.y; }\n", k, k);
+      } else {
+        snprintf(buf, sizeof(buf), "      const uint32_t rj = A.x & A.y; lo[%zu] = bmux(rj, A.z, A.x); hi[%zu] = bmux(rj, A.w, A.y); }\n", k, k);
+        if (!any.empty()) any += " | ";
+        snprintf(buf + 200, 100, "(lo[%zu] & hi[%zu])", k, k);
+        any += buf + 200;
+      }
+      u += buf;
+    }
+    if (!any.empty()) {
+      u += "#pragma unroll 1\n    for (uint32_t i = 0u; i < 512u; ++i) {  // the part's pool of pair-planes: FIX blocks 512 q + i\n";
+      u += "      if (!__any_sync(0xFFFFFFFFu, (" + any + ") != 0u)) break;\n";
+      snprintf(buf, sizeof(buf), "      const Philox4 P = philox_stream_rk(gid, step, PBN_RNG_FIX, %du + i, rk);\n      uint32_t av = 0xFFFFFFFFu;\n", 512 * q);
+      u += buf;
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass) u += "      av = 0xFFFFFFFFu;\n";
+        for (size_t k = 0; k < ks.size(); ++k)
+          if (ks[k] == 3) {
+            snprintf(buf, sizeof(buf), "      PBN_CLAIM(%zu, %s, %s)\n", k, pass ? "P.z" : "P.x", pass ? "P.w" : "P.y");
+            u += buf;
+          }
+      }
+      u += "    }\n";
+    }
+    u += "  }\n";
+  }
+  u += "}\n#undef PBN_CLAIM\n\n";
+
+  // ---- evaluation of a part's genes in the plane-resident kernel
+  u += "// x: s1 planes, o: out planes (on entry: the perturbation planes of the step), tg: target planes; all [gene][lane]\n"
+       "// with the lane folded into the pointer.  m: envs of the column with a perturbation event (model A).  Returns the\n"
+       "// OR over the part's genes of (next state XOR target state).\n";
+  u += "#if PBN_PERT_MODE == 1\n#define PBN_FINISH(g, v) { uint32_t v_ = bmux(m, x[(g) * 32], (v)) ^ o[(g) * 32]; o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n"
+       "#elif PBN_PERT_MODE == 2\n#define PBN_FINISH(g, v) { uint32_t v_ = (v) ^ o[(g) * 32]; o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n"
+       "#elif PBN_PERT_MODE == 3\n#define PBN_FINISH(g, v) { uint32_t v_ = bmux(o[(g) * 32], ~x[(g) * 32], (v)); o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n"
+       "#else\n#define PBN_FINISH(g, v) { uint32_t v_ = (v); o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n#endif\n";
+  u += "__device__ __forceinline__ uint32_t pbn_eval_part(uint32_t q, const uint32_t* x, uint32_t* o, const uint32_t* tg, uint32_t m,\n"
+       "                                                  const uint32_t (&lo)[PBN_MAXS], const uint32_t (&hi)[PBN_MAXS]) {\n";
+  u += "  uint32_t d = 0u;\n  (void)m;\n#define X(g) x[(g) * 32]\n";
+  for (int q = 0; q < 8; ++q) {
+    bool has = false;
+    for (int i = 0; i < N; ++i) has = has || part[i] == q;
+    if (!has) continue;
+    snprintf(buf, sizeof(buf), "  if (q == %du) {\n", q);
+    u += buf;
+    std::vector<int> used;
+    for (int i = 0; i < N; ++i) {
+      if (part[i] != q) continue;
+      for (const GenFunc& f : g.funcs[i]) {
+        std::vector<int> vars(f.in, f.in + f.arity);
+        reduce_support(f.lut, vars);
+        for (int v : vars)
+          if (std::find(used.begin(), used.end(), v) == used.end()) used.push_back(v);
+      }
+    }
+    std::sort(used.begin(), used.end());
+    for (int v : used) {
+      snprintf(buf, sizeof(buf), "    const uint32_t x%d = X(%d);\n", v, v);
+      u += buf;
+    }
+    for (int i = 0; i < N; ++i) {
+      if (part[i] != q) continue;
+      const int K = (int)g.funcs[i].size();
+      snprintf(buf, sizeof(buf), "    {  // gene %d: %d predictor(s)\n", i, K);
+      u += buf;
+      std::vector<std::string> names;
+      std::vector<std::pair<uint64_t, std::vector<int>>> seen;
+      for (int k = 0; k < K; ++k) {
+        const GenFunc& f = g.funcs[i][k];
+        std::vector<int> vars(f.in, f.in + f.arity);
+        const uint64_t red = reduce_support(f.lut, vars);
+        int same = -1;
+        for (size_t z = 0; z < seen.size(); ++z)
+          if (seen[z].first == red && seen[z].second == vars) same = (int)z;
+        seen.push_back({red, vars});
+        snprintf(buf, sizeof(buf), "f%d", k);
+        if (same >= 0) {
+          names.push_back(names[same]);
+          continue;
+        }
+        names.push_back(buf);
+        const Expr e = synth(f.lut, std::vector<int>(f.in, f.in + f.arity));
+        u += "      const uint32_t " + std::string(buf) + " = " + e.s + ";\n";
+      }
+      std::string val;
+      if (K == 1) {
+        val = names[0];
+      } else {
+        const int k = slot_of[i] >> 3;
+        snprintf(buf, sizeof(buf), "      const uint32_t s0 = lo[%d], s1 = hi[%d];\n", k, k);
+        u += buf;
+        if (K == 2) val = "bmux(s0, " + names[1] + ", " + names[0] + ")", u += "      (void)s1;\n";
+        if (K == 3) val = "bmux(s1, " + names[2] + ", bmux(s0, " + names[1] + ", " + names[0] + "))";
+        if (K == 4) val = "bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " + names[0] + "))";
+      }
+      snprintf(buf, sizeof(buf), "      PBN_FINISH(%d, ", i);
+      u += buf + val + ")\n    }\n";
+    }
+    u += "  }\n";
+  }
+  u += "#undef X\n#undef PBN_FINISH\n  return d;\n}\n";
+}
+
+// CTAs per SM the plane-resident kernel is compiled for (register cap = 65536 / (threads * blocks))
+inline int planes_min_blocks(const GenNet& g, int warps) {
+  if (const char* env = getenv(warps == 4 ? "PBN_B200_PLANES_BLOCKS_W4" : "PBN_B200_PLANES_BLOCKS_W8")) return atoi(env);
+  if (warps == 4) return g.n_genes <= 32 ? 8 : 4;
+  return g.n_genes <= 32 ? 4 : 3;
+}
+
 // net_gen.cuh: the constants; net_update.inc: selection tables + pbn_update_part() -- see step_sliced.cuh
 inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::string* update_inc) {
   const int N = g.n_genes, NW = (N + 31) / 32, NSEL = n_sel_slots(g);
@@ -179,6 +338,11 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
            "#define PBN_N %d\n#define PBN_NW32 %d\n#define PBN_BINS %d\n#define PBN_NSEL %d\n"
            "#define PBN_SCRATCH_WORDS %d\n#define PBN_INJECTED %d\n#define PBN_THREADS %d\n#define PBN_MIN_BLOCKS %d\n",
            N, NW, g.bins, NSEL, scratch_words(g), injected ? 1 : 0, sliced_threads(g), sliced_min_blocks(g));
+  h += buf;
+  // plane-resident kernel (step_planes.cuh): perturbation model is a compile-time constant there (own-RNG
+  // specialisation with perturb_p == 0: none), slots per selection group, CTAs per SM of the two variants
+  snprintf(buf, sizeof(buf), "#define PBN_PERT_MODE %d\n#define PBN_MAXS %d\n#define PBN_PLANES_MIN_BLOCKS_W4 %d\n#define PBN_PLANES_MIN_BLOCKS_W8 %d\n",
+           (injected || g.pert_rng) ? g.pert_mode : 0, (NSEL + 7) / 8 > 0 ? (NSEL + 7) / 8 : 1, planes_min_blocks(g, 4), planes_min_blocks(g, 8));
   h += buf;
   *gen_h = h;
 
@@ -282,12 +446,14 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
       }
     u += "  }\n";
   }
-  u += "#undef X\n}\n}  // namespace pbn\n";
+  u += "#undef X\n}\n";
+  generate_parts(g, u);
+  u += "}  // namespace pbn\n";
   *update_inc = u;
 }
 
 inline std::string main_source() {
-  return "#include \"../../include/pbn_b200.h\"\n#include \"net_gen.cuh\"\n#include \"step_sliced.cuh\"\n";
+  return "#include \"../../include/pbn_b200.h\"\n#include \"net_gen.cuh\"\n#include \"step_sliced.cuh\"\n#include \"step_planes.cuh\"\n";
 }
 
 // ---- NVRTC through dlopen (the library must load on machines without it) ------------------------
@@ -383,7 +549,7 @@ inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std
   const bool profile = profile_build();
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DPBN_PROFILE=1"};
   const int n_opts = profile ? 5 : 4;
-  std::string key = gen_h + upd + main_src + kSrc_step_sliced + kSrc_pbn_common + kSrc_philox + kSrc_pbn_b200_h;
+  std::string key = gen_h + upd + main_src + kSrc_step_sliced + kSrc_step_planes + kSrc_pbn_common + kSrc_philox + kSrc_pbn_b200_h;
   for (int i = 0; i < n_opts; ++i) key += opts[i];
   char name[64];
   snprintf(name, sizeof(name), "/sliced_%016llx.cubin", (unsigned long long)fnv1a(key));
@@ -395,11 +561,11 @@ inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std
     *err = "libnvrtc.so.12 not found (set PBN_B200_NVRTC) and no cached cubin at " + path;
     return PBN_ERR_JIT;
   }
-  const char* hdr_src[] = {kSrc_pbn_b200_h, kSrc_philox, kSrc_pbn_common, kSrc_step_sliced, gen_h.c_str(), upd.c_str()};
-  const char* hdr_name[] = {"../../include/pbn_b200.h", "philox.cuh", "pbn_common.cuh", "step_sliced.cuh",
+  const char* hdr_src[] = {kSrc_pbn_b200_h, kSrc_philox, kSrc_pbn_common, kSrc_step_sliced, kSrc_step_planes, gen_h.c_str(), upd.c_str()};
+  const char* hdr_name[] = {"../../include/pbn_b200.h", "philox.cuh", "pbn_common.cuh", "step_sliced.cuh", "step_planes.cuh",
                             "net_gen.cuh", "net_update.inc"};
   void* prog = nullptr;
-  int rc = n.CreateProgram(&prog, main_src.c_str(), "pbn_sliced.cu", 6, hdr_src, hdr_name);
+  int rc = n.CreateProgram(&prog, main_src.c_str(), "pbn_sliced.cu", 7, hdr_src, hdr_name);
   if (rc != 0) {
     *err = "nvrtcCreateProgram failed";
     return PBN_ERR_JIT;

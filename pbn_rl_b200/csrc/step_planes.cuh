@@ -1,0 +1,483 @@
+// Plane-resident step kernel: the fast path for env state that LIVES on the device as bit-planes.
+//
+// Resident block (caller-owned DEVICE memory, pbn_resident_words(); written by pbn_resident_import, read back by
+// pbn_resident_export): per tile of 1024 consecutive env instances kResRows rows of 32 words, word L of a row =
+// column L (the 32 envs  tile*1024 + 128*j + 4*L + c,  bit b = 4*j + c,  j = 0..7, c = 0..3 -- the same env <-> (column,
+// bit) map and therefore the same random streams as the row-format kernel, step_sliced.cuh):
+//     rows [0, N)            state planes      row g, bit b = gene g of env b
+//     rows [N, 2N)           target planes     the state of the env's target attractor (single-state attractors)
+//     rows [2N, 2N+8)        target id planes  8-bit id, 255 = no target
+//     rows [2N+8, 2N+24)     t planes          16-bit episode step counter
+// One 32-bit logic instruction advances 32 envs and nothing is ever transposed: the interventions are scattered into
+// the state planes (shared-memory atomics), the predictor functions are generated LOP3 trees, perturbations are
+// XOR planes, the target test is N XOR/OR instructions against the target planes, the counters are a bit-sliced
+// ripple-carry add and compare; only the per-env results the agent consumes (reward, terminated, truncated) leave
+// the plane domain.
+//
+// Work decomposition: a CTA of WARPS (4 or 8) warps owns one tile.  The genes are split into 8 "parts" (net_update.inc:
+// part = selection slot mod 8); a warp draws the selection planes of its part(s) into registers BEFORE
+// griddepcontrol.wait (they depend on nothing the previous launch writes) and evaluates the same genes after it, so
+// selection planes never leave the register file.  Thread (w, L) handles the per-env inputs/outputs of the column's
+// bits [32/WARPS * w, ...).  The tile's block arrives by one TMA bulk copy and leaves by bulk stores.
+//   P0  (before the wait) selection planes of the warp's parts; perturbation planes of the step -> O; zero scratch
+//   P1  TMA load of the tile block -> IN; action bytes -> flips: atomicXor into the state planes (duplicates dropped,
+//       so XOR == the OR-mask of the contract); one warp: t' = min(t+1, 65535), t' >= horizon, "has target" plane
+//   B1
+//   P2  generated LOP3 trees of the warp's genes on s1 -> perturbation -> O; difference to the target planes
+//   B2
+//   P5  hit / truncated planes -> per-env reward, terminated, truncated (vector stores); statistics; auto-reset:
+//       one Philox block per finished env, new state / target scattered into the planes lane-per-gene
+//   B3  bulk stores of the tile block
+// Two instantiations (WARPS = 4 for large batches: 8 CTAs per SM; WARPS = 8 for small ones: half the latency per
+// tile) draw identical streams and give identical results.
+//
+// Random streams: as step_sliced.cuh (SELECT / FIX pool per part, PERTURB sub-streams per 8 slice bits, RESET per env).
+// Algorithmic HBM bytes per env-step: 33 (N <= 64) / 49.  Bytes this kernel really moves per env-step:
+// (2N + 24) / 8 read + written block + BINS action bytes + 6 result bytes (N = 28: 29; N = 70: 50).
+#pragma once
+#include "pbn_common.cuh"
+
+#ifndef PBN_N
+#error "net_gen.cuh and step_sliced.cuh must be included first"
+#endif
+
+namespace pbn {
+
+constexpr int kTidPlanes = 8, kTPlanes = 16;
+constexpr int kRowTarget = PBN_N, kRowTid = 2 * PBN_N, kRowT = 2 * PBN_N + kTidPlanes;
+constexpr int kResRows = 2 * PBN_N + kTidPlanes + kTPlanes;
+constexpr int kResTileWords = kResRows * 32;
+constexpr uint32_t kNoTarget = 255u;
+// shared memory (32-bit words): [IN block | O planes | misc]; tables follow at PlanesLayout offsets
+constexpr int kPlO = kResTileWords;
+constexpr int kPlMisc = kPlO + PBN_N * 32;
+constexpr int kPlDiff = kPlMisc, kPlHit = kPlMisc + 32, kPlGe = kPlMisc + 64, kPlHt = kPlMisc + 96, kPlM = kPlMisc + 128;
+constexpr int kPlStat = kPlMisc + 160, kPlRew = kPlMisc + 168, kPlMbar = kPlMisc + 192;
+constexpr int kPlFixedWords = kPlMisc + 256;
+static_assert(2 * (PBN_BINS + 1) <= 24, "reward table does not fit its slot");
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <int WARPS>
+__device__ __forceinline__ void step_planes_body(const StepParams& p, const PlanesLayout& L) {
+  constexpr int PARTS = 8 / WARPS;            // selection / evaluation parts per warp
+  constexpr int GPT = 8 / WARPS;              // groups of 4 consecutive envs per thread
+  constexpr uint32_t kMyBits = (1u << (4 * GPT)) - 1u;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* const sm = reinterpret_cast<uint32_t*>(smem_raw);
+  const pbn_step_args& a = p.a;
+  const NetParams& n = p.n;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  uint32_t* const X = sm + lane;                          // s1 planes   [gene][lane]
+  uint32_t* const TG = sm + kRowTarget * 32 + lane;       // target planes
+  uint32_t* const TID = sm + kRowTid * 32 + lane;
+  uint32_t* const TS = sm + kRowT * 32 + lane;
+  uint32_t* const O = sm + kPlO + lane;                   // perturbation planes, then out planes
+  uint32_t* const s_stat = sm + kPlStat;
+  float* const s_rew = reinterpret_cast<float*>(sm + kPlRew);
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(sm + kPlMbar);
+  const uint32_t* const s_aval = reinterpret_cast<const uint32_t*>(smem_raw + L.aval_off);   // [entry][kNW] value words
+  const uint32_t* const s_acare = reinterpret_cast<const uint32_t*>(smem_raw + L.acare_off); // [entry][kNW] (generic tables)
+  const int32_t* const s_aoffs = reinterpret_cast<const int32_t*>(smem_raw + L.aoffs_off);   // [A+1]
+  const uint8_t* const s_eattr = smem_raw + L.eattr_off;                                     // [entry] -> attractor
+  const bool simple = n.attr_simple != 0u;
+  const bool has_attr = n.n_attr > 0;
+  const int64_t E = a.n_envs;
+  const int64_t n_tiles = (E + 1023) >> 10;
+  const int64_t first_tile = (int64_t)blockIdx.x;
+
+  if (a.flags & PBN_STEP_PDL) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (first_tile < n_tiles && threadIdx.x < 2) {   // warm the L2 with the tile's inputs (coherent, only a hint)
+      if (threadIdx.x == 0) l2_prefetch(a.resident + first_tile * kResTileWords, kResTileWords * 4u);
+      if (threadIdx.x == 1 && a.actions != nullptr && (first_tile + 1) * 1024 <= E) l2_prefetch(a.actions + first_tile * 1024 * PBN_BINS, 1024u * PBN_BINS);
+    }
+  }
+  // ---- read-only tables of the handle -> shared memory (never written by a step kernel: safe before the wait)
+  if (threadIdx.x == 0) mbar_init(mbar, 1u);
+  if (threadIdx.x < 2 * (PBN_BINS + 1)) {
+    const uint32_t nf = threadIdx.x % (PBN_BINS + 1);
+    const bool hit = threadIdx.x >= PBN_BINS + 1;
+    const float base = __fadd_rn(n.r_step, __fmul_rn(n.r_action, (float)nf));
+    s_rew[threadIdx.x] = __fadd_rn(base, hit ? n.r_success : 0.0f);
+  }
+  if (threadIdx.x < 8) s_stat[threadIdx.x] = 0u;
+  if (L.attr_in_smem) {
+    uint32_t* aval = const_cast<uint32_t*>(s_aval);
+    uint32_t* acare = const_cast<uint32_t*>(s_acare);
+    for (int i = threadIdx.x; i < n.n_attr_states * kNW; i += blockDim.x) {
+      const int en = i / kNW, wd = i - en * kNW;
+      aval[i] = (uint32_t)(n.attr_val[en * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+      if (!simple) acare[i] = (uint32_t)(n.attr_care[en * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+    }
+    for (int i = threadIdx.x; i <= n.n_attr; i += blockDim.x) const_cast<int32_t*>(s_aoffs)[i] = n.attr_offset[i];
+    if (!simple)
+      for (int at = threadIdx.x; at < n.n_attr; at += blockDim.x)
+        for (int en = n.attr_offset[at]; en < n.attr_offset[at + 1]; ++en) const_cast<uint8_t*>(s_eattr)[en] = (uint8_t)at;
+  }
+  const uint64_t step_ctr = effective_step(a);
+  uint32_t parity = 0u;
+  bool first = true;
+
+  for (int64_t tile = first_tile; tile < n_tiles; tile += gridDim.x) {
+    const bool full = (tile + 1) * 1024 <= E;
+    const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
+    const int64_t e0 = tile * 1024 + 4 * (int64_t)lane;   // env of (j = 0, c = 0) of this column
+    uint32_t VALID = 0xFFFFFFFFu;
+    if (!full) {
+      VALID = 0u;
+      for (int b = 0; b < 32; ++b)
+        if (e0 + 128 * (b >> 2) + (b & 3) < E) VALID |= 1u << b;
+    }
+    // ---- P0. everything that does not depend on the previous launch ---------------------------------------
+    if (PBN_PERT_MODE != PBN_PERT_NONE)
+      for (int i = threadIdx.x; i < PBN_N * 32; i += blockDim.x) sm[kPlO + i] = 0u;
+    if (threadIdx.x < 32) {
+      sm[kPlDiff + lane] = 0u;
+      sm[kPlHit + lane] = 0u;
+      sm[kPlM + lane] = 0u;
+    }
+    uint32_t lo[PARTS][PBN_MAXS], hi[PARTS][PBN_MAXS];
+#if PBN_INJECTED
+#pragma unroll
+    for (int h = 0; h < PARTS; ++h) {
+      const uint32_t q = w + (uint32_t)WARPS * h;
+#pragma unroll
+      for (int k = 0; k < PBN_MAXS; ++k) {
+        const int r = (int)q + 8 * k;
+        uint32_t s0 = 0u, s1 = 0u;
+        if (r < PBN_NSEL) {
+          const uint32_t g = kSelGene[r], K = kSelK[r];
+          for (int b = 0; b < 32; ++b) {
+            const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
+            uint32_t v = (env < E) ? a.sel[env * PBN_N + g] : 0u;
+            v = v < K ? v : K - 1u;
+            s0 |= (v & 1u) << b;
+            s1 |= ((v >> 1) & 1u) << b;
+          }
+        }
+        lo[h][k] = s0;
+        hi[h][k] = s1;
+      }
+    }
+#else
+#pragma unroll
+    for (int h = 0; h < PARTS; ++h) pbn_draw_part(w + (uint32_t)WARPS * h, gid, step_ctr, n.rk, lo[h], hi[h]);
+#endif
+    uint32_t npert = 0u;
+    if (PBN_PERT_MODE != PBN_PERT_NONE) {
+      __syncthreads();   // O and M are zero
+#if PBN_INJECTED
+      if (a.pert_mask != nullptr) {
+        uint32_t mb = 0u;
+        for (int i = 0; i < 4 * GPT; ++i) {
+          const uint32_t b = 4u * GPT * w + (uint32_t)i;
+          const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
+          if (env >= E) continue;
+          for (int wd = 0; wd < kNW; ++wd) {
+            uint32_t pm = (uint32_t)(a.pert_mask[env * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+            if (wd == kNW - 1) pm &= kLastMask;
+            npert += __popc(pm);
+            if (pm) mb |= 1u << b;
+            while (pm) {
+              const int g = 32 * wd + __ffs(pm) - 1;
+              pm &= pm - 1u;
+              atomicOr(&O[g * 32], 1u << b);
+            }
+          }
+        }
+        if (mb) atomicOr(&sm[kPlM + lane], mb);
+      }
+#else
+      if (w < 4u && n.pert_rng) {
+        // sub-stream w of the column: geometric skipping over the slots gene*8 + (b & 7) of slice bits 8w..8w+7
+        const uint32_t s_last = kSurvTable[kSlots];
+        uint32_t mb = 0u, k = 0u;
+        Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
+        int pos = -1;
+        while (true) {
+          if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((k >> 2) & 63u), n.rk);
+          const uint32_t u = pick4(blk, k & 3u);
+          ++k;
+          pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
+          if (pos >= kSlots) break;
+          const uint32_t b = 8u * w + ((uint32_t)pos & 7u);
+          atomicOr(&O[(pos >> 3) * 32], 1u << b);
+          mb |= 1u << b;
+          npert += (VALID >> b) & 1u;
+        }
+        if (mb) atomicOr(&sm[kPlM + lane], mb);
+      }
+#endif
+    }
+    if (first) {
+      __syncthreads();   // mbarrier initialised, tables staged
+      if (a.flags & PBN_STEP_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    // ---- P1. the tile's block; interventions -> state planes; counters ---------------------------------------
+    if (threadIdx.x == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(mbar, kResTileWords * 4u);
+      tma_load_1d(sm, a.resident + tile * kResTileWords, kResTileWords * 4u, mbar);
+    }
+    uint32_t act[GPT][PBN_BINS];   // the 4*BINS action bytes of each group of 4 envs
+#pragma unroll
+    for (int g = 0; g < GPT; ++g) {
+#pragma unroll
+      for (int k = 0; k < PBN_BINS; ++k) act[g][k] = 0u;
+      if (a.actions != nullptr) {
+        const int64_t e = e0 + 128 * (GPT * (int)w + g);
+        if (full) {
+          const uint32_t* ap = reinterpret_cast<const uint32_t*>(a.actions + e * PBN_BINS);
+#pragma unroll
+          for (int k = 0; k < PBN_BINS; ++k) act[g][k] = __ldg(ap + k);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4 * PBN_BINS; ++q) {
+            const int64_t env = e + q / PBN_BINS;
+            const uint32_t v = (env < E) ? a.actions[e * PBN_BINS + q] : 0u;
+            act[g][q >> 2] |= v << (8 * (q & 3));
+          }
+        }
+      }
+    }
+    mbar_wait(mbar, parity);
+    parity ^= 1u;
+    uint32_t nfp = 0u, flips = 0u;   // 4-bit flip counts of this thread's envs
+#pragma unroll
+    for (int g = 0; g < GPT; ++g) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t b = 4u * (GPT * w + g) + c;
+        uint32_t av[PBN_BINS];
+        uint32_t nf = 0u;
+#pragma unroll
+        for (int k = 0; k < PBN_BINS; ++k) {
+          const int q = c * PBN_BINS + k;
+          av[k] = (act[g][q >> 2] >> (8 * (q & 3))) & 0xFFu;
+          bool go = av[k] - 1u < (uint32_t)PBN_N;     // 0 = no-op, values > N are ignored
+#pragma unroll
+          for (int k2 = 0; k2 < k; ++k2) go = go && av[k2] != av[k];   // set semantics: duplicates do not cancel
+          if (go) {
+            atomicXor(&X[(av[k] - 1u) * 32], 1u << b);
+            ++nf;
+          }
+        }
+        nfp |= nf << (4 * (4 * g + c));
+        flips += ((VALID >> b) & 1u) ? nf : 0u;
+      }
+    }
+    if (w == WARPS - 1) {
+      // t' = min(t + 1, 65535) and GE = (t' >= horizon), bit-sliced; HT = the env has a target
+      uint32_t tp[kTPlanes];
+      uint32_t sat = 0xFFFFFFFFu;
+#pragma unroll
+      for (int k = 0; k < kTPlanes; ++k) {
+        tp[k] = TS[k * 32];
+        sat &= tp[k];
+      }
+      uint32_t c = ~sat;
+#pragma unroll
+      for (int k = 0; k < kTPlanes; ++k) {
+        const uint32_t nk = tp[k] ^ c;
+        c &= tp[k];
+        tp[k] = nk;
+        TS[k * 32] = nk;
+      }
+      uint32_t gt = 0u, eq = 0xFFFFFFFFu;
+      const uint32_t hz = (uint32_t)n.horizon;
+#pragma unroll
+      for (int k = kTPlanes - 1; k >= 0; --k) {
+        if ((hz >> k) & 1u) eq &= tp[k]; else gt |= eq & tp[k];
+      }
+      sm[kPlGe + lane] = hz ? (gt | eq) : 0u;
+      uint32_t all = 0xFFFFFFFFu;
+#pragma unroll
+      for (int k = 0; k < kTidPlanes; ++k) all &= TID[k * 32];
+      sm[kPlHt + lane] = has_attr ? ~all : 0u;
+    }
+    __syncthreads();   // B1: s1 planes complete
+    // ---- P2. synchronous update of this warp's genes ---------------------------------------------------------
+    {
+      const uint32_t m = (PBN_PERT_MODE == PBN_PERT_A) ? sm[kPlM + lane] : 0u;
+      uint32_t d = 0u;
+#pragma unroll
+      for (int h = 0; h < PARTS; ++h) d |= pbn_eval_part(w + (uint32_t)WARPS * h, X, O, TG, m, lo[h], hi[h]);
+      if (d) atomicOr(&sm[kPlDiff + lane], d);
+    }
+    __syncthreads();   // B2: out planes and target differences complete
+    if (!simple && has_attr) {
+      // general attractor tables (several states per attractor, wildcards): entry by entry against the out planes
+      for (int en = (int)w; en < n.n_attr_states; en += WARPS) {
+        const uint32_t aid = s_eattr[en];
+        uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < kTidPlanes; ++k) m &= ((aid >> k) & 1u) ? TID[k * 32] : ~TID[k * 32];
+        for (int g = 0; g < PBN_N && m; ++g) {
+          const uint32_t care = (s_acare[en * kNW + (g >> 5)] >> (g & 31)) & 1u, val = (s_aval[en * kNW + (g >> 5)] >> (g & 31)) & 1u;
+          if (care) m &= val ? O[g * 32] : ~O[g * 32];
+        }
+        if (m) atomicOr(&sm[kPlHit + lane], m);
+      }
+      __syncthreads();
+    }
+    // ---- P5. per-env results ------------------------------------------------------------------------------------
+    const uint32_t H = simple ? (~sm[kPlDiff + lane] & sm[kPlHt + lane]) : sm[kPlHit + lane];
+    const uint32_t TR = sm[kPlGe + lane] & ~H;
+    const uint32_t D = (H | TR) & VALID;
+#pragma unroll
+    for (int g = 0; g < GPT; ++g) {
+      const uint32_t j = GPT * w + g;
+      const uint32_t hb = (H >> (4u * j)) & 15u, tb = (TR >> (4u * j)) & 15u;
+      const int64_t e = e0 + 128 * (int64_t)j;
+      float rw[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rw[c] = s_rew[((nfp >> (4 * (4 * g + c))) & 15u) + (((hb >> c) & 1u) ? PBN_BINS + 1 : 0)];
+      const uint32_t hbytes = (hb * 0x00204081u) & 0x01010101u, tbytes = (tb * 0x00204081u) & 0x01010101u;
+      if (full) {
+        if (a.reward != nullptr) *reinterpret_cast<float4*>(a.reward + e) = make_float4(rw[0], rw[1], rw[2], rw[3]);
+        if (a.terminated != nullptr) *reinterpret_cast<uint32_t*>(a.terminated + e) = hbytes;
+        if (a.truncated != nullptr) *reinterpret_cast<uint32_t*>(a.truncated + e) = tbytes;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (e + c >= E) continue;
+          if (a.reward != nullptr) a.reward[e + c] = rw[c];
+          if (a.terminated != nullptr) a.terminated[e + c] = (uint8_t)((hb >> c) & 1u);
+          if (a.truncated != nullptr) a.truncated[e + c] = (uint8_t)((tb >> c) & 1u);
+        }
+      }
+    }
+    const uint32_t mysh = 4u * GPT * w;
+    const uint32_t Dm = (D >> mysh) & kMyBits;     // finished envs among this thread's
+    uint32_t len_sum = 0u;
+    if (w == WARPS - 1 && ((a.flags & PBN_STEP_AUTORESET) || a.stats != nullptr)) {
+      // t of the finished envs: summed for the statistics, cleared by the auto-reset
+#pragma unroll
+      for (int k = 0; k < kTPlanes; ++k) {
+        const uint32_t tk = TS[k * 32];
+        len_sum += (uint32_t)__popc(tk & D) << k;
+        if (a.flags & PBN_STEP_AUTORESET) TS[k * 32] = tk & ~D;
+      }
+    }
+    if (a.stats != nullptr) {
+      const uint32_t mine = kMyBits << mysh;
+      const uint32_t v[7] = {(uint32_t)__popc(VALID & mine), (uint32_t)__popc(Dm), (uint32_t)__popc(H & VALID & mine),
+                             (uint32_t)__popc(TR & VALID & mine), len_sum, flips, npert};
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const uint32_t x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
+        if (lane == 0u && x != 0u) atomicAdd(&s_stat[q], x);
+      }
+    }
+    // ---- auto-reset: the finished envs of the warp are dealt out over its lanes (one Philox pass per 32), then
+    //      written into the planes one env at a time with one lane per gene
+    if (a.flags & PBN_STEP_AUTORESET) {
+      const uint32_t cnt = (uint32_t)__popc(Dm);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, dd);
+        if ((int)lane >= dd) incl += v;
+      }
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      const uint32_t excl = incl - cnt;
+      for (uint32_t base = 0; base < total; base += 32u) {   // warp-uniform trip count
+        const uint32_t jb = base + lane;                     // the job of this lane
+        uint32_t Lo = 0u;                                    // owner: first lane whose inclusive count exceeds jb
+#pragma unroll
+        for (int st = 16; st >= 1; st >>= 1) {
+          const uint32_t probe = __shfl_sync(0xFFFFFFFFu, incl, (int)min(Lo + (uint32_t)st - 1u, 31u));
+          if (Lo + (uint32_t)st - 1u < 32u && probe <= jb) Lo += (uint32_t)st;
+        }
+        Lo = min(Lo, 31u);
+        const uint32_t eL = __shfl_sync(0xFFFFFFFFu, excl, (int)Lo);
+        const uint32_t DL = __shfl_sync(0xFFFFFFFFu, Dm, (int)Lo);
+        uint32_t info = 0u, sw[kNW], tw[kNW];
+#pragma unroll
+        for (int wd = 0; wd < kNW; ++wd) sw[wd] = tw[wd] = 0u;
+        if (jb < total) {
+          uint32_t mm = DL;
+          for (uint32_t k = jb - eL; k != 0u; --k) mm &= mm - 1u;   // drop the k lowest finished envs of the owner
+          const uint32_t b = mysh + (uint32_t)(__ffs(mm) - 1);
+          const int64_t env = tile * 1024 + 4 * (int64_t)Lo + 128 * (int64_t)(b >> 2) + (b & 3u);
+          const Philox4 r = philox_stream_rk((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.rk);
+          int src, tgt;
+          reset_pair(n, r, src, tgt);
+          int so, se, to;
+          if (L.attr_in_smem) { so = s_aoffs[src]; se = s_aoffs[src + 1]; to = s_aoffs[tgt]; }
+          else { so = n.attr_offset[src]; se = n.attr_offset[src + 1]; to = n.attr_offset[tgt]; }
+          const int js = so + (int)__umulhi(r.y, (uint32_t)(se - so));
+#pragma unroll
+          for (int wd = 0; wd < kNW; ++wd) {
+            if (L.attr_in_smem) {
+              sw[wd] = s_aval[js * kNW + wd];
+              tw[wd] = s_aval[to * kNW + wd];
+            } else {
+              sw[wd] = (uint32_t)(n.attr_val[(size_t)js * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+              tw[wd] = (uint32_t)(n.attr_val[(size_t)to * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+            }
+          }
+          info = Lo | (b << 5) | ((uint32_t)tgt << 10);
+          if (a.source_id != nullptr) a.source_id[env] = src;
+        }
+        const uint32_t njobs = min(32u, total - base);
+#pragma unroll 1
+        for (uint32_t k = 0; k < njobs; ++k) {
+          const uint32_t inf = __shfl_sync(0xFFFFFFFFu, info, (int)k);
+          const uint32_t Lk = inf & 31u, bit = 1u << ((inf >> 5) & 31u), tid = inf >> 10;
+#pragma unroll
+          for (int wd = 0; wd < kNW; ++wd) {
+            const uint32_t sv = __shfl_sync(0xFFFFFFFFu, sw[wd], (int)k), tv = __shfl_sync(0xFFFFFFFFu, tw[wd], (int)k);
+            const uint32_t g = 32u * wd + lane;
+            if (g < (uint32_t)PBN_N) {
+              uint32_t* po = sm + kPlO + g * 32 + Lk;
+              uint32_t* pt = sm + kRowTarget * 32 + g * 32 + Lk;
+              if ((sv >> lane) & 1u) atomicOr(po, bit); else atomicAnd(po, ~bit);
+              if ((tv >> lane) & 1u) atomicOr(pt, bit); else atomicAnd(pt, ~bit);
+            }
+          }
+          if (lane < (uint32_t)kTidPlanes) {
+            uint32_t* pi = sm + kRowTid * 32 + lane * 32 + Lk;
+            if ((tid >> lane) & 1u) atomicOr(pi, bit); else atomicAnd(pi, ~bit);
+          }
+        }
+      }
+    }
+    __syncthreads();   // B3: the tile's block is final
+    if (threadIdx.x == 0) {
+      fence_proxy_async();
+      uint32_t* gblk = a.resident + tile * kResTileWords;
+      bulk_store(gblk, sm + kPlO, PBN_N * 128u);                                   // next states
+      if (a.flags & PBN_STEP_AUTORESET)
+        bulk_store(gblk + kRowTarget * 32, sm + kRowTarget * 32, (PBN_N + kTidPlanes + kTPlanes) * 128u);
+      else
+        bulk_store(gblk + kRowT * 32, sm + kRowT * 32, kTPlanes * 128u);           // only the counters changed
+      bulk_commit_wait_read();
+    }
+    first = false;
+    if (tile + gridDim.x < n_tiles) __syncthreads();   // the next tile reuses the buffers
+  }
+  if (a.stats != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 7) {
+      const uint32_t x = s_stat[threadIdx.x];
+      if (x != 0u) atomicAdd(&a.stats[threadIdx.x], (unsigned long long)x);
+    }
+  }
+  bump_device_step(a, p.ticket);
+}
+
+extern "C" __global__ void __launch_bounds__(128, PBN_PLANES_MIN_BLOCKS_W4)
+pbn_step_planes_w4(const __grid_constant__ StepParams p, const PlanesLayout L) { step_planes_body<4>(p, L); }
+
+extern "C" __global__ void __launch_bounds__(256, PBN_PLANES_MIN_BLOCKS_W8)
+pbn_step_planes_w8(const __grid_constant__ StepParams p, const PlanesLayout L) { step_planes_body<8>(p, L); }
+
+}  // namespace pbn

@@ -29,13 +29,14 @@
 //
 // Random streams (DESIGN.md "Sliced random stream"; CPU twin: oracle/pbn_oracle.py sliced_stream)
 //   group id = (env >> 10) * 32 + ((env >> 2) & 31)  (= tile * 32 + lane), slice bit as above.
-//   SELECT: the genes with K > 1 predictors get slots r = 0, 1, ... in gene order; slot r owns
-//           Philox blocks 2r and 2r+1 = words w0..w7.  K=2 uses w0 (s0), K=4 w0,w1 (s0,s1), K=3 four
-//           pairs (w0,w1),(w2,w3),(w4,w5),(w6,w7): pair value 3 is rejected and replaced by the next
-//           pair; slots still rejected after the fourth pair (1/256 of them) draw 2-bit pairs from
-//           FIX sub-stream q = r mod 4 (Philox blocks (FIX, 64q + i); shared by the slots r = q,
-//           q+4, ... in that order; bit order inside a slot; 16 pairs per word LSB first) until one
-//           is != 3.  sel = s0 + 2*s1.
+//   SELECT: the genes with K > 1 predictors get slots r = 0, 1, ... in gene order; slot r owns Philox block
+//           (SELECT, r) = words x, y, z, w.  K=2 uses x (s0), K=4 x, y (s0, s1), K=3 the pairs (x, y), (z, w): pair
+//           value 3 is rejected and replaced by the next pair.  The 1/16 of the positions still at 3 are settled by
+//           the pool of the slot's part q = r mod 8: Philox blocks (FIX, 512 q + i), i = 0, 1, ...; each block is two
+//           pair-planes (x, y), (z, w); per pair-plane the part's K=3 slots r = q, q + 8, ... in that order take
+//           bit b of the plane if they are still at 3 there and no earlier slot of the part has claimed bit b of this
+//           plane; blocks are consumed until no slot of the part is at 3 anywhere in the column.  Exactly uniform
+//           1-of-3, all choices independent (no random pair is used twice).  sel = s0 + 2*s1.
 //   PERTURB: sub-stream q = b >> 3 (Philox blocks (PERTURB, 64q + i)) covers the 8 slice bits
 //           8q..8q+7: geometric skipping over slots gene*8 + (b & 7) with survival table S[0..8N].
 //   RESET:  per env (global env id), as in the scalar kernel.
@@ -201,75 +202,6 @@ __device__ __forceinline__ uint32_t pick4(const Philox4& b, uint32_t q) {
   return q == 0 ? b.x : q == 1 ? b.y : q == 2 ? b.z : b.w;
 }
 
-// FIX sub-stream of one (column, warp), shared by the warp's slots r = w, w + 4, ... in that order.
-// Its first six words -- block 0 (x, y, z, w) and the first half of block 1 (x', y') -- are three whole pair-planes
-// (x, y), (z, w), (x', y'): a fifth, sixth and seventh rejection pass for the positions that survived a slot's own
-// four.  A position may use bit b of the planes only if no earlier slot of this warp has claimed bit b (`taken`), so
-// no random pair is ever used twice and the choices stay exactly uniform and independent.  What is still rejected
-// after that (2^-14 of the positions), or was refused its bit, keeps the value 3 in the planes and is settled after
-// the slot loop by fix_tail(): single 2-bit pairs from the rest of the sub-stream (words z', w' of block 1, which are
-// already in registers, then blocks 2, 3, ...), slots in order, lowest position first.
-// Measured on the way here (us per step / per rollout update, 2^20 envs): a serial fix-up loop inside the slot loop,
-// entered for nearly every slot (the first design) 19.1 / 9.0; no shared planes, everything in fix_tail 23.6 / 12.9;
-// two shared planes 20.7 / 9.5; four 19.4 / 8.7 -- each call of a tail that has to compute a Philox block first stalls
-// its warp for about a microsecond, and the other three warps of the tile wait for it at the next barrier.
-constexpr int kFixPlanes = 3;
-struct FixPlanes {
-  uint32_t px[kFixPlanes], py[kFixPlanes];
-  uint32_t spare0, spare1;   // words z', w' of block 1: the first 32 single pairs of fix_tail()
-  uint32_t taken;            // bits of the shared planes an earlier slot of this warp has claimed
-  uint32_t left;             // bit k set: the warp's k-th slot (r = w + 4k) still has positions at value 3
-};
-
-__device__ __forceinline__ void fix_planes_init(FixPlanes& fx, uint64_t gid, uint64_t step, uint32_t w, const uint32_t (&rk)[20]) {
-  const Philox4 a = philox_stream_rk(gid, step, PBN_RNG_FIX, 64u * w, rk);
-  const Philox4 b = philox_stream_rk(gid, step, PBN_RNG_FIX, 64u * w + 1u, rk);
-  fx.px[0] = a.x; fx.py[0] = a.y;
-  fx.px[1] = a.z; fx.py[1] = a.w;
-  fx.px[2] = b.x; fx.py[2] = b.y;
-  fx.spare0 = b.z; fx.spare1 = b.w;
-  fx.taken = 0u;
-  fx.left = 0u;
-}
-
-// Selection planes of slot r of this column from the slot's two SELECT blocks (+ the shared FIX planes).
-__device__ __forceinline__ void sel_slot(uint64_t gid, uint64_t step, const uint32_t (&rk)[20], uint32_t r,
-                                         uint32_t K, FixPlanes& fx, uint32_t& s0, uint32_t& s1) {
-  const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, 2u * r, rk);
-  const Philox4 B = philox_stream_rk(gid, step, PBN_RNG_SELECT, 2u * r + 1u, rk);
-  uint32_t b0 = A.x, b1 = A.y;
-  if (K == 3u) {
-    uint32_t rej = b0 & b1;
-    b0 = bmux(rej, A.z, b0);
-    b1 = bmux(rej, A.w, b1);
-    rej = rej & A.z & A.w;
-    b0 = bmux(rej, B.x, b0);
-    b1 = bmux(rej, B.y, b1);
-    rej = rej & B.x & B.y;
-    b0 = bmux(rej, B.z, b0);
-    b1 = bmux(rej, B.w, b1);
-    rej = rej & B.z & B.w;
-    {
-      // passes five to seven from the shared pair-planes, only at bits no earlier slot of this warp has claimed
-      uint32_t t = rej & ~fx.taken;
-      fx.taken |= rej;
-      rej &= ~t;
-#pragma unroll
-      for (int j = 0; j < kFixPlanes; ++j) {
-        b0 = bmux(t, fx.px[j], b0);
-        b1 = bmux(t, fx.py[j], b1);
-        t &= fx.px[j] & fx.py[j];
-      }
-      rej |= t;
-    }
-    fx.left |= (rej != 0u ? 1u : 0u) << (r >> 2);   // these positions keep b0 = b1 = 1 (value 3) until fix_tail()
-  } else if (K == 2u) {
-    b1 = 0u;
-  }
-  s0 = b0;
-  s1 = b1;
-}
-
 // Survival table S[j] = floor((1-p)^j 2^32), j = 0..8N, of the perturbation sub-streams: filled per handle after
 // the library is loaded (constant memory: the look-ups of the geometric skip are data-dependent and
 // lane-divergent; from global memory each step of the search cost a DRAM/L2 round trip, ~2 us per event).
@@ -360,43 +292,6 @@ __device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSme
   }
 }
 
-// Cold path (about one warp in three per tile; no Philox block unless more than 32 pairs are needed): settle the
-// positions that are still at value 3.
-__device__ __noinline__ void fix_tail(uint32_t* sel0, uint32_t* sel1, uint64_t gid, uint64_t step, uint32_t w, const uint32_t (&rk)[20],
-                                      uint32_t spare0, uint32_t spare1, uint32_t left) {
-  uint32_t word = 0u, cnt = 0u, next = 6u;   // word index in the sub-stream: 6, 7 = z', w' of block 1
-  Philox4 blk = {0u, 0u, 0u, 0u};
-  while (left) {
-    const int r = (int)w + 4 * (__ffs(left) - 1);
-    left &= left - 1u;
-    uint32_t b0 = sel0[r * 32], b1 = sel1[r * 32];
-    uint32_t rej = b0 & b1;
-    while (rej) {
-      if (cnt == 0u) {
-        if (next == 6u) {
-          word = spare0;
-        } else if (next == 7u) {
-          word = spare1;
-        } else {
-          if ((next & 3u) == 0u) blk = philox_stream_rk(gid, step, PBN_RNG_FIX, 64u * w + ((next >> 2) & 63u), rk);
-          word = pick4(blk, next & 3u);
-        }
-        ++next;
-        cnt = 16u;
-      }
-      const uint32_t pr = word & 3u;
-      word >>= 2;
-      --cnt;
-      const uint32_t m = (pr != 3u) ? (rej & (0u - rej)) : 0u;
-      rej ^= m;
-      b0 ^= (pr & 1u) ? 0u : m;
-      b1 ^= (pr & 2u) ? 0u : m;
-    }
-    sel0[r * 32] = b0;
-    sel1[r * 32] = b1;
-  }
-}
-
 // ---- C1. selection planes of this warp's slots (independent of the state) -------------------------
 template <bool FULL>
 __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, const NetParams& n, uint32_t* sel0,
@@ -419,17 +314,20 @@ __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, co
     sel1[r * 32] = s1;
   }
 #else
-  FixPlanes fx;
-  fix_planes_init(fx, gid, step_ctr, w, n.rk);
-#pragma unroll 1
-  for (int r = (int)w; r < PBN_NSEL; r += kWarps) {
-    uint32_t s0, s1;
-    sel_slot(gid, step_ctr, n.rk, (uint32_t)r, kSelK[r], fx, s0, s1);
-    sel0[r * 32] = s0;
-    sel1[r * 32] = s1;
-  }
-  if (__any_sync(0xFFFFFFFFu, fx.left != 0u)) {
-    if (fx.left != 0u) fix_tail(sel0, sel1, gid, step_ctr, w, n.rk, fx.spare0, fx.spare1, fx.left);
+  // parts w and w + 4 (net_update.inc: pbn_draw_part; the same streams as the plane-resident kernel)
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const uint32_t q = w + 4u * (uint32_t)hh;
+    uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
+    pbn_draw_part(q, gid, step_ctr, n.rk, lo, hi);
+#pragma unroll
+    for (int k = 0; k < PBN_MAXS; ++k) {
+      const int r = (int)q + 8 * k;
+      if (r < PBN_NSEL) {
+        sel0[r * 32] = lo[k];
+        sel1[r * 32] = hi[k];
+      }
+    }
   }
 #endif
 }

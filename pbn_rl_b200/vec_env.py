@@ -156,6 +156,12 @@ class VecPBNEnv:
     dependent launch: each step draws its state-independent selection planes under the tail of the
     previous kernel; the device counter is then advanced explicitly with :meth:`advance_counter`
     at the end of a captured sequence instead of by every launch.
+    ``resident=True`` (sliced kernel) keeps the env state on the device as bit-planes between steps
+    (``pbn_resident_import`` / ``pbn_step`` with ``args.resident``): the fastest form of :meth:`step`.
+    ``state`` / ``target_id`` / ``t`` stay available as row-format tensors -- reading them exports the
+    planes, and the next step imports them again, so touch them at the boundary, not per step;
+    :meth:`step` then returns ``None`` in place of the state words.  Results are bit-identical to
+    ``resident=False``.
     """
 
     def __init__(self, network: PBNNetwork, num_envs: int, attractors: Optional[AttractorSet] = None,
@@ -163,7 +169,7 @@ class VecPBNEnv:
                  bins: int = 3, perturb_p: float = 0.0, perturb_mode: str = "A", r_success: float = 5.0,
                  r_step: float = 0.0, r_action: float = -1.0, kernel: str = "auto", env_offset: int = 0,
                  auto_reset: bool = False, pair_weights: Optional[np.ndarray] = None,
-                 device_counter: bool = False, pdl: bool = False):
+                 device_counter: bool = False, pdl: bool = False, resident: bool = False):
         self._h = None
         self.lib = _cabi.lib()  # raises if the CUDA extension is not built: no fallback
         if not torch.cuda.is_available():
@@ -196,10 +202,19 @@ class VecPBNEnv:
 
         e, w = self.num_envs, self.n_words
         dev = self.device
-        self.state = torch.zeros((e, w), dtype=torch.int64, device=dev)
-        self.target_id = torch.full((e,), -1, dtype=torch.int32, device=dev)
+        self._state = torch.zeros((e, w), dtype=torch.int64, device=dev)
+        self._target_id = torch.full((e,), -1, dtype=torch.int32, device=dev)
         self.source_id = torch.full((e,), -1, dtype=torch.int32, device=dev)
-        self.t = torch.zeros((e,), dtype=torch.int16, device=dev)  # uint16 payload
+        self._t = torch.zeros((e,), dtype=torch.int16, device=dev)  # uint16 payload
+        self.resident = bool(resident)
+        self._res = None            # the plane-resident block
+        self._planes_fresh = False  # the block holds the current env state
+        self._rows_fresh = True     # the row-format tensors hold the current env state
+        if self.resident:
+            if self.kernel != "sliced":
+                raise ValueError("resident=True needs the sliced kernel (network not eligible: kernel=%s)" % self.kernel)
+            nw = int(self.lib.pbn_resident_words(self._h, max(e, 1)))
+            self._res = torch.zeros((nw,), dtype=torch.int32, device=dev)
         self.reward = torch.zeros((e,), dtype=torch.float32, device=dev)
         self.terminated = torch.zeros((e,), dtype=torch.uint8, device=dev)
         self.truncated = torch.zeros((e,), dtype=torch.uint8, device=dev)
@@ -228,6 +243,40 @@ class VecPBNEnv:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    # ------------------------------------------------------------------ row-format view of plane-resident state
+    def _rows(self) -> None:
+        """Make the row-format tensors current (exports the resident block if it is newer) and treat them as
+        modified by the caller: the next resident step imports them again."""
+        if self.resident:
+            if not self._rows_fresh:
+                check(self.lib.pbn_resident_export(self._h, _ptr(self._res), _ptr(self._state), _ptr(self._target_id),
+                                                   _ptr(self._t), self.num_envs, self._stream()))
+                self._rows_fresh = True
+            self._planes_fresh = False
+
+    def _planes(self) -> None:
+        """Make the resident block current (imports the row-format tensors if they are newer)."""
+        if not self._planes_fresh:
+            check(self.lib.pbn_resident_import(self._h, _ptr(self._res), _ptr(self._state),
+                                               _ptr(self._target_id) if self.attractors is not None else None,
+                                               _ptr(self._t), self.num_envs, self._stream()))
+            self._planes_fresh = True
+
+    @property
+    def state(self) -> torch.Tensor:
+        self._rows()
+        return self._state
+
+    @property
+    def target_id(self) -> torch.Tensor:
+        self._rows()
+        return self._target_id
+
+    @property
+    def t(self) -> torch.Tensor:
+        self._rows()
+        return self._t
+
     @property
     def launches(self) -> int:
         out = C.c_uint64()
@@ -241,6 +290,7 @@ class VecPBNEnv:
         (the curriculum of ``env.rework_probas``)."""
         if attractors.n_genes != self.n_genes:
             raise ValueError("attractor states have %d genes, network has %d" % (attractors.n_genes, self.n_genes))
+        self._rows()  # the target planes of a resident block are built from the table: re-import after the change
         offs, care, val = attractors.tables()
         care = np.ascontiguousarray(care)
         val = np.ascontiguousarray(val)
@@ -275,13 +325,19 @@ class VecPBNEnv:
                                  self._stream()))
         return self.state, self.target_id
 
-    def _args(self, actions: Optional[torch.Tensor], final_state: Optional[torch.Tensor], stats: bool) -> StepArgs:
+    def _args(self, actions: Optional[torch.Tensor], final_state: Optional[torch.Tensor], stats: bool,
+              rows: bool = False) -> StepArgs:
         a = StepArgs()
-        a.state = _ptr(self.state)
         a.actions = _ptr(actions)
-        a.target_id = _ptr(self.target_id) if self.attractors is not None else None
         a.source_id = _ptr(self.source_id)
-        a.t = _ptr(self.t)
+        if self.resident and final_state is None and not rows:
+            self._planes()
+            self._rows_fresh = False
+            a.resident = _ptr(self._res)
+        else:
+            a.state = _ptr(self.state)
+            a.target_id = _ptr(self._target_id) if self.attractors is not None else None
+            a.t = _ptr(self._t)
         a.reward = _ptr(self.reward)
         a.terminated = _ptr(self.terminated)
         a.truncated = _ptr(self.truncated)
@@ -339,7 +395,7 @@ class VecPBNEnv:
             self.step_ctr += 1
         elif self.pdl:
             self._pos += 1
-        return self.state, self.reward, self.terminated, self.truncated
+        return (None if a.resident else self._state), self.reward, self.terminated, self.truncated
 
     def step_injected(self, actions: Optional[torch.Tensor], sel: torch.Tensor,
                       pert_mask: Optional[torch.Tensor] = None, final_state: Optional[torch.Tensor] = None,
@@ -361,7 +417,7 @@ class VecPBNEnv:
         check(self.lib.pbn_step_injected(self._h, C.byref(a), self._stream()))
         if self.step_ctr_dev is None:
             self.step_ctr += 1
-        return self.state, self.reward, self.terminated, self.truncated
+        return (None if a.resident else self._state), self.reward, self.terminated, self.truncated
 
     def rollout(self, n_steps: int, stats: bool = True) -> torch.Tensor:
         """``n_steps`` uncontrolled updates of every instance (``env.step([])`` ``n_steps`` times,
@@ -462,9 +518,10 @@ class VecPBNEnv:
             src.numpy()[...] = np.asarray(actions_host, dtype=np.uint8).reshape(self.num_envs, self.bins)
             io.actions = src.data_ptr()
         io.n_chunks = int(chunks)
+        self._rows()  # the host-buffer path works on the row-format tensors
         a = hb.get("args")
         if a is None:
-            a = hb["args"] = self._args(None, None, True)
+            a = hb["args"] = self._args(None, None, True, rows=True)
         a.step_ctr = self._pos if self.pdl else self.step_ctr
         check(self.lib.pbn_step_host(self._h, C.byref(a), C.byref(io), self._stream()))
         if self.step_ctr_dev is None:

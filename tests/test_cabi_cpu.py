@@ -107,6 +107,12 @@ HOST_HARNESS = r"""
 #define __device__
 #define __forceinline__ inline
 #define __constant__ const
+#include "philox.cuh"
+using pbn::Philox4;
+using pbn::philox_stream_rk;
+#define PBN_RNG_SELECT 0u
+#define PBN_RNG_FIX 3u
+static inline bool __any_sync(unsigned, bool p) { return p; }   // one column = one lane
 template <int IMM> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r = 0;
   for (int i = 0; i < 32; ++i) {
@@ -116,13 +122,17 @@ template <int IMM> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t 
   return r;
 }
 static inline uint32_t bmux(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (~a & c); }
+#include "net_gen.cuh"
 #include "net_update.inc"
 int main(int argc, char** argv) {
-  // stdin: N NSEL, then per case: N input planes, NSEL s0 planes, NSEL s1 planes; stdout: N out planes
+  // stdin: N NSEL cases, then per case: N input planes, NSEL s0 planes, NSEL s1 planes
+  // stdout per case: the out planes of pbn_update_part (row-format kernel), then those of pbn_eval_part
+  // (plane-resident kernel) followed by its target-difference word;
+  // then: D draws, each "gid step seed" -> the lo / hi selection planes of all slots from pbn_draw_part
   int n, nsel, cases;
   if (scanf("%d %d %d", &n, &nsel, &cases) != 3) return 1;
   const int nw = (n + 31) / 32;
-  static uint32_t x[128 * 32], o[128 * 32], s0[128 * 32], s1[128 * 32];
+  static uint32_t x[128 * 32], o[128 * 32], o2[128 * 32], tg[128 * 32], s0[128 * 32], s1[128 * 32];
   for (int c = 0; c < cases; ++c) {
     for (int i = 0; i < n; ++i) if (scanf("%u", &x[i * 32]) != 1) return 1;
     for (int i = 0; i < nsel; ++i) if (scanf("%u", &s0[i * 32]) != 1) return 1;
@@ -130,6 +140,31 @@ int main(int argc, char** argv) {
     for (int i = 0; i < nw * 32; ++i) o[i * 32] = 0xDEADBEEFu;
     for (uint32_t w = 0; w < 4; ++w) pbn::pbn_update_part(w, x, o, s0, s1);
     for (int i = 0; i < nw * 32; ++i) printf("%u ", o[i * 32]);
+    printf("\n");
+    uint32_t d = 0;
+    for (int i = 0; i < n; ++i) { o2[i * 32] = 0u; tg[i * 32] = x[((i + 1) % n) * 32]; }
+    for (uint32_t q = 0; q < 8; ++q) {
+      uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
+      for (int k = 0; k < PBN_MAXS; ++k) { const int r = (int)q + 8 * k; lo[k] = r < nsel ? s0[r * 32] : 0u; hi[k] = r < nsel ? s1[r * 32] : 0u; }
+      d |= pbn::pbn_eval_part(q, x, o2, tg, 0u, lo, hi);
+    }
+    for (int i = 0; i < n; ++i) printf("%u ", o2[i * 32]);
+    printf("%u\n", d);
+  }
+  int draws;
+  if (scanf("%d", &draws) != 1) return 1;
+  for (int c = 0; c < draws; ++c) {
+    unsigned long long gid, step, seed;
+    if (scanf("%llu %llu %llu", &gid, &step, &seed) != 3) return 1;
+    uint32_t rk[20];
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = (uint32_t)seed + r * 0x9E3779B9u; rk[2 * r + 1] = (uint32_t)(seed >> 32) + r * 0xBB67AE85u; }
+    static uint32_t L[1024], H[1024];
+    for (uint32_t q = 0; q < 8; ++q) {
+      uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
+      pbn::pbn_draw_part(q, gid, step, rk, lo, hi);
+      for (int k = 0; k < PBN_MAXS; ++k) { const int r = (int)q + 8 * k; if (r < nsel) { L[r] = lo[k]; H[r] = hi[k]; } }
+    }
+    for (int r = 0; r < nsel; ++r) printf("%u %u ", L[r], H[r]);
     printf("\n");
   }
   return 0;
@@ -139,16 +174,22 @@ int main(int argc, char** argv) {
 
 @pytest.mark.parametrize("name", NETS)
 def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
-    """Compile the generated net_update.inc with g++ and evaluate it on random bit-planes."""
+    """Compile the generated net_gen.cuh / net_update.inc with g++: the predictor trees of both kernels against the
+    truth tables on random bit-planes, and the generated selection draw (pbn_draw_part, with csrc/philox.cuh compiled
+    for the host) against the oracle's twin of the stream (oracle/pbn_oracle.py: sliced_stream)."""
     _lib()
+    from oracle import pbn_oracle as O
+    from helpers import oracle_net
     from pbn_rl_b200.vec_env import jit_source
     net = product_net(name)
     src = jit_source(net)
-    upd = src.split("// ---- net_update.inc\n")[1]
+    gen, upd = src.split("// ---- net_gen.cuh\n")[1].split("// ---- net_update.inc\n")
+    (tmp_path / "net_gen.cuh").write_text(gen)
     (tmp_path / "net_update.inc").write_text(upd)
     (tmp_path / "h.cpp").write_text(HOST_HARNESS)
     exe = tmp_path / "h"
-    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(exe), str(tmp_path / "h.cpp")], check=True)
+    csrc = ROOT / "pbn_rl_b200" / "csrc"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", str(csrc), "-o", str(exe), str(tmp_path / "h.cpp")], check=True)
     n = net.n_genes
     slots = [i for i, fs in enumerate(net.functions) if len(fs) > 1]
     rng = np.random.default_rng(1)
@@ -162,16 +203,33 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
         s1 = [(int(sum(int((v >> 1) & 1) << b for b, v in enumerate(row)))) for row in sel]
         lines.append(" ".join(str(int(v)) for v in x) + " " + " ".join(map(str, s0)) + " " + " ".join(map(str, s1)))
         data.append((x, sel))
+    draws = [(5, 0, 0x5EED), (1234567, 3, 0x5EED), ((1 << 33) + 9, (1 << 40) + 7, 0xDEADBEEF12345678)]
+    lines.append(str(len(draws)))
+    lines += ["%d %d %d" % d for d in draws]
     out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
     rows = [[int(v) for v in line.split()] for line in out.strip().splitlines()]
-    for (x, sel), got in zip(data, rows):
+    for k, (x, sel) in enumerate(data):
+        got, got2 = rows[2 * k], rows[2 * k + 1]
         for b in range(32):
             state = sum(((int(x[i]) >> b) & 1) << i for i in range(n))
             choice = [0] * n
-            for k, i in enumerate(slots):
-                choice[i] = int(sel[k][b])
+            for j, i in enumerate(slots):
+                choice[i] = int(sel[j][b])
             want = net.next_state_int(state, choice)
-            have = sum(((got[i] >> b) & 1) << i for i in range(n))
-            assert have == want
+            assert sum(((got[i] >> b) & 1) << i for i in range(n)) == want
+            assert sum(((got2[i] >> b) & 1) << i for i in range(n)) == want
         for i in range(n, len(got)):
             assert got[i] == 0  # unused planes are cleared
+        diff = 0
+        for i in range(n):
+            diff |= got2[i] ^ int(x[(i + 1) % n])
+        assert got2[n] == diff  # OR of (next state XOR target planes)
+    onet = oracle_net(name)
+    for (gid, step, seed), got in zip(draws, rows[2 * cases:]):
+        tile, lane = gid >> 5, gid & 31
+        ids = np.array([tile * 1024 + 128 * (b >> 2) + 4 * lane + (b & 3) for b in range(32)], dtype=np.uint64)
+        sel, _ = O.sliced_stream(onet, 0.0, ids, step, seed)
+        for r, i in enumerate(slots):
+            lo, hi = got[2 * r], got[2 * r + 1]
+            have = [((lo >> b) & 1) + 2 * ((hi >> b) & 1) for b in range(32)]
+            assert have == [int(v) for v in sel[:, i]], (name, gid, step, r)
