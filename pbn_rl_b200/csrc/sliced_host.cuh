@@ -250,10 +250,13 @@ inline void generate_parts(const GenNet& g, std::string& u) {
   u += "// x: s1 planes, o: out planes (on entry: the perturbation planes of the step), tg: target planes; all [gene][lane]\n"
        "// with the lane folded into the pointer.  m: envs of the column with a perturbation event (model A).  Returns the\n"
        "// OR over the part's genes of (next state XOR target state).\n";
-  u += "#if PBN_PERT_MODE == 1\n#define PBN_FINISH(g, v) { uint32_t v_ = bmux(m, x[(g) * 32], (v)) ^ o[(g) * 32]; o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n"
-       "#elif PBN_PERT_MODE == 2\n#define PBN_FINISH(g, v) { uint32_t v_ = (v) ^ o[(g) * 32]; o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n"
-       "#elif PBN_PERT_MODE == 3\n#define PBN_FINISH(g, v) { uint32_t v_ = bmux(o[(g) * 32], ~x[(g) * 32], (v)); o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n"
-       "#else\n#define PBN_FINISH(g, v) { uint32_t v_ = (v); o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n#endif\n";
+  u += "// PM: perturbation model (PBN_PERT_*), a template parameter: the kernel switches once per part\n"
+       "#define PBN_FINISH(g, v) { uint32_t v_ = (v); \\\n"
+       "    if (PM == 1) v_ = bmux(m, x[(g) * 32], v_) ^ o[(g) * 32]; \\\n"
+       "    else if (PM == 2) v_ ^= o[(g) * 32]; \\\n"
+       "    else if (PM == 3) v_ = bmux(o[(g) * 32], ~x[(g) * 32], v_); \\\n"
+       "    o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n";
+  u += "template <int PM>\n";
   u += "__device__ __forceinline__ uint32_t pbn_eval_part(uint32_t q, const uint32_t* x, uint32_t* o, const uint32_t* tg, uint32_t m,\n"
        "                                                  const uint32_t (&lo)[PBN_MAXS], const uint32_t (&hi)[PBN_MAXS]) {\n";
   u += "  uint32_t d = 0u;\n  (void)m;\n#define X(g) x[(g) * 32]\n";
@@ -339,10 +342,9 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
            "#define PBN_SCRATCH_WORDS %d\n#define PBN_INJECTED %d\n#define PBN_THREADS %d\n#define PBN_MIN_BLOCKS %d\n",
            N, NW, g.bins, NSEL, scratch_words(g), injected ? 1 : 0, sliced_threads(g), sliced_min_blocks(g));
   h += buf;
-  // plane-resident kernel (step_planes.cuh): perturbation model is a compile-time constant there (own-RNG
-  // specialisation with perturb_p == 0: none), slots per selection group, CTAs per SM of the two variants
-  snprintf(buf, sizeof(buf), "#define PBN_PERT_MODE %d\n#define PBN_MAXS %d\n#define PBN_PLANES_MIN_BLOCKS_W4 %d\n#define PBN_PLANES_MIN_BLOCKS_W8 %d\n",
-           (injected || g.pert_rng) ? g.pert_mode : 0, (NSEL + 7) / 8 > 0 ? (NSEL + 7) / 8 : 1, planes_min_blocks(g, 4), planes_min_blocks(g, 8));
+  // plane-resident kernel (step_planes.cuh): slots per selection part, CTAs per SM of the two variants
+  snprintf(buf, sizeof(buf), "#define PBN_MAXS %d\n#define PBN_PLANES_MIN_BLOCKS_W4 %d\n#define PBN_PLANES_MIN_BLOCKS_W8 %d\n",
+           (NSEL + 7) / 8 > 0 ? (NSEL + 7) / 8 : 1, planes_min_blocks(g, 4), planes_min_blocks(g, 8));
   h += buf;
   *gen_h = h;
 

@@ -86,6 +86,11 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
   const uint32_t* const s_acare = reinterpret_cast<const uint32_t*>(smem_raw + L.acare_off); // [entry][kNW] (generic tables)
   const int32_t* const s_aoffs = reinterpret_cast<const int32_t*>(smem_raw + L.aoffs_off);   // [A+1]
   const uint8_t* const s_eattr = smem_raw + L.eattr_off;                                     // [entry] -> attractor
+#if PBN_INJECTED
+  const int pm = n.pert_mode;                                   // block-uniform
+#else
+  const int pm = n.pert_rng ? n.pert_mode : PBN_PERT_NONE;
+#endif
   const bool simple = n.attr_simple != 0u;
   const bool has_attr = n.n_attr > 0;
   const int64_t E = a.n_envs;
@@ -136,7 +141,7 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
         if (e0 + 128 * (b >> 2) + (b & 3) < E) VALID |= 1u << b;
     }
     // ---- P0. everything that does not depend on the previous launch ---------------------------------------
-    if (PBN_PERT_MODE != PBN_PERT_NONE)
+    if (pm != PBN_PERT_NONE)
       for (int i = threadIdx.x; i < PBN_N * 32; i += blockDim.x) sm[kPlO + i] = 0u;
     if (threadIdx.x < 32) {
       sm[kPlDiff + lane] = 0u;
@@ -171,7 +176,7 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     for (int h = 0; h < PARTS; ++h) pbn_draw_part(w + (uint32_t)WARPS * h, gid, step_ctr, n.rk, lo[h], hi[h]);
 #endif
     uint32_t npert = 0u;
-    if (PBN_PERT_MODE != PBN_PERT_NONE) {
+    if (pm != PBN_PERT_NONE) {
       __syncthreads();   // O and M are zero
 #if PBN_INJECTED
       if (a.pert_mask != nullptr) {
@@ -305,10 +310,16 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     __syncthreads();   // B1: s1 planes complete
     // ---- P2. synchronous update of this warp's genes ---------------------------------------------------------
     {
-      const uint32_t m = (PBN_PERT_MODE == PBN_PERT_A) ? sm[kPlM + lane] : 0u;
+      const uint32_t m = (pm == PBN_PERT_A) ? sm[kPlM + lane] : 0u;
       uint32_t d = 0u;
 #pragma unroll
-      for (int h = 0; h < PARTS; ++h) d |= pbn_eval_part(w + (uint32_t)WARPS * h, X, O, TG, m, lo[h], hi[h]);
+      for (int h = 0; h < PARTS; ++h) {
+        const uint32_t q = w + (uint32_t)WARPS * h;
+        if (pm == PBN_PERT_NONE) d |= pbn_eval_part<PBN_PERT_NONE>(q, X, O, TG, m, lo[h], hi[h]);
+        else if (pm == PBN_PERT_A) d |= pbn_eval_part<PBN_PERT_A>(q, X, O, TG, m, lo[h], hi[h]);
+        else if (pm == PBN_PERT_B) d |= pbn_eval_part<PBN_PERT_B>(q, X, O, TG, m, lo[h], hi[h]);
+        else d |= pbn_eval_part<PBN_PERT_C>(q, X, O, TG, m, lo[h], hi[h]);
+      }
       if (d) atomicOr(&sm[kPlDiff + lane], d);
     }
     __syncthreads();   // B2: out planes and target differences complete

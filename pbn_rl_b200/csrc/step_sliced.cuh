@@ -292,6 +292,28 @@ __device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSme
   }
 }
 
+#if !PBN_INJECTED
+// Selection planes of parts w and w + 4 (net_update.inc: pbn_draw_part; the same streams as the plane-resident
+// kernel) into the SEL scratch.  One out-of-line copy: the kernel calls it from several places.
+__device__ __noinline__ void draw_parts_to_scratch(const uint32_t (&rk)[20], uint32_t* sel0, uint32_t* sel1, uint64_t gid,
+                                                  uint64_t step_ctr, uint32_t w) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const uint32_t q = w + 4u * (uint32_t)hh;
+    uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
+    pbn_draw_part(q, gid, step_ctr, rk, lo, hi);
+#pragma unroll
+    for (int k = 0; k < PBN_MAXS; ++k) {
+      const int r = (int)q + 8 * k;
+      if (r < PBN_NSEL) {
+        sel0[r * 32] = lo[k];
+        sel1[r * 32] = hi[k];
+      }
+    }
+  }
+}
+#endif
+
 // ---- C1. selection planes of this warp's slots (independent of the state) -------------------------
 template <bool FULL>
 __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, const NetParams& n, uint32_t* sel0,
@@ -314,21 +336,7 @@ __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, co
     sel1[r * 32] = s1;
   }
 #else
-  // parts w and w + 4 (net_update.inc: pbn_draw_part; the same streams as the plane-resident kernel)
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const uint32_t q = w + 4u * (uint32_t)hh;
-    uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
-    pbn_draw_part(q, gid, step_ctr, n.rk, lo, hi);
-#pragma unroll
-    for (int k = 0; k < PBN_MAXS; ++k) {
-      const int r = (int)q + 8 * k;
-      if (r < PBN_NSEL) {
-        sel0[r * 32] = lo[k];
-        sel1[r * 32] = hi[k];
-      }
-    }
-  }
+  draw_parts_to_scratch(n.rk, sel0, sel1, gid, step_ctr, w);
 #endif
 }
 

@@ -146,7 +146,7 @@ int main(int argc, char** argv) {
     for (uint32_t q = 0; q < 8; ++q) {
       uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
       for (int k = 0; k < PBN_MAXS; ++k) { const int r = (int)q + 8 * k; lo[k] = r < nsel ? s0[r * 32] : 0u; hi[k] = r < nsel ? s1[r * 32] : 0u; }
-      d |= pbn::pbn_eval_part(q, x, o2, tg, 0u, lo, hi);
+      d |= pbn::pbn_eval_part<0>(q, x, o2, tg, 0u, lo, hi);
     }
     for (int i = 0; i < n; ++i) printf("%u ", o2[i * 32]);
     printf("%u\n", d);
