@@ -100,7 +100,18 @@ enum {
   PBN_STEP_PDL = 2u,
   /* Do not increment *step_ctr_dev when the launch completes (several launches that belong to the same
    * logical step, e.g. the chunks of pbn_step_host, share one counter value). */
-  PBN_STEP_NO_COUNT = 4u
+  PBN_STEP_NO_COUNT = 4u,
+  /* Tile-level chaining of plane-resident steps (args->resident; implies the PBN_STEP_PDL conventions: position in
+   * the sequence as step_ctr, pbn_advance_counter at its end).  A launch at position >= 1 does not wait for the
+   * whole previous launch: each tile of 1024 envs waits only until the same tile of the previous step of the
+   * sequence has published its block (an epoch word per tile in the resident block, release/acquire), so the tails
+   * and heads of consecutive steps overlap on the device.  The caller guarantees that (1) the launches of a
+   * sequence are consecutive pbn_step calls on one stream for the same block and n_envs, with nothing enqueued
+   * between them, and (2) everything else a step reads -- the action buffers of ALL steps of the sequence -- is
+   * complete before the sequence's first step is enqueued (open-loop rollouts with pre-sampled actions; not an
+   * agent that computes step k+1's actions from step k's results).  Position 0 is launched fully serialised.  A tile
+   * whose predecessor does not show up within a bounded number of polls falls back to griddepcontrol.wait. */
+  PBN_STEP_CHAIN = 8u
 };
 enum { PBN_UNPACK_U8 = 0, PBN_UNPACK_F32 = 1 };
 
@@ -252,7 +263,8 @@ int64_t pbn_planes_words(const pbn_handle* h, int64_t n_envs);
  * may be NULL).  Results are bit-identical to pbn_step on the row-format arrays (same random streams).
  * Supported: networks the sliced kernel takes, at most 254 attractors, and either single-state attractors
  * without wildcards (any number) or attractor tables of at most 256 (care, value) entries.
- * pbn_resident_words: size of the block in 32-bit words (whole tiles; 128-byte aligned memory). */
+ * pbn_resident_words: size of the block in 32-bit words (whole tiles + one epoch word per tile for
+ * PBN_STEP_CHAIN; 128-byte aligned memory). */
 int64_t pbn_resident_words(const pbn_handle* h, int64_t n_envs);
 int pbn_resident_import(pbn_handle* h, uint32_t* resident, const uint64_t* state, const int32_t* target_id,
                         const uint16_t* t, int64_t n_envs, void* stream);

@@ -578,22 +578,22 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
             s1[:, i] = (y & ~rj & full) | (w & rj)
         else:
             raise ValueError("the sliced kernel takes 1..4 predictors per gene")
-    # Pool of part q = r mod 8: blocks (FIX, 512 q + i), i = 0, 1, ...; each block is two pair-planes (x, y), (z, w).
-    # Per pair-plane the part's K=3 slots, in slot order, take bit b if they are still at value 3 there and no earlier
-    # slot of the part has claimed bit b of this plane.  Blocks are consumed until no slot of the part is at 3
-    # anywhere in the column (columns that are done ignore further blocks).
-    for q in range(8):
-        slots_q = [i for r, i in enumerate(slot_gene) if r % 8 == q and ks[i] == 3]
+    # Pool of group q = r mod 4: blocks (FIX, 1024 q + i), i = 0, 1, ...; each block is two pair-planes (x, y), (z, w).
+    # Per pair-plane the group's K=3 slots, in slot order, take bit b if they are still at value 3 there and no
+    # earlier slot of the group has claimed bit b of this plane.  Blocks are consumed until no slot of the group is
+    # at 3 anywhere in the column (columns that are done ignore further blocks).
+    for q in range(4):
+        slots_q = [i for r, i in enumerate(slot_gene) if r % 4 == q and ks[i] == 3]
         if not slots_q:
             continue
-        for it in range(512):
+        for it in range(1024):
             rej_any = np.zeros(ng, dtype=np.uint64)
             for i in slots_q:
                 rej_any |= s0[:, i] & s1[:, i]
             act = np.nonzero(rej_any)[0]
             if len(act) == 0:
                 break
-            blk = [v.astype(np.uint64) for v in philox4x32(*_ctr(groups[act], step_ctr, KIND_FIX, 512 * q + it), k0, k1)]
+            blk = [v.astype(np.uint64) for v in philox4x32(*_ctr(groups[act], step_ctr, KIND_FIX, 1024 * q + it), k0, k1)]
             for px, py in ((blk[0], blk[1]), (blk[2], blk[3])):
                 av = np.full(len(act), full, dtype=np.uint64)
                 for i in slots_q:

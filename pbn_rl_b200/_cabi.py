@@ -20,6 +20,7 @@ KERNEL_KINDS = {"auto": 0, "scalar": 1, "sliced": 2}
 STEP_AUTORESET = 1
 STEP_PDL = 2
 STEP_NO_COUNT = 4
+STEP_CHAIN = 8
 UNPACK_U8, UNPACK_F32 = 0, 1
 N_STATS = 8
 STAT_NAMES = ("steps", "episodes", "terminated", "truncated", "ep_len_sum", "flips", "perturbed", "reserved")

@@ -241,8 +241,15 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
   if ((rc = load_sliced(h, injected ? 1 : 0)) != PBN_OK) return rc;
   const NetParams& n = h->net;
   const int N = n.n_genes, NW = (N + 31) / 32;
+  const int64_t tiles = (a.n_envs + 1023) / 1024;
+  // 8 warps per tile halve a tile's latency (small batches: one CTA per SM or less); 4 warps per tile keep 8 tiles
+  // per SM in flight (large batches).  Both draw the same streams.
+  int v = (N > 32 || tiles < 2 * (int64_t)h->num_sms) ? 1 : 0;
+  if (const char* env = getenv("PBN_B200_PLANES_WARPS")) v = atoi(env) == 8 ? 1 : 0;
+  const int maxs4 = (jit::n_sel_slots(h->gen) + 3) / 4 > 0 ? (jit::n_sel_slots(h->gen) + 3) / 4 : 1;
   PlanesLayout L{};
-  uint32_t o = (uint32_t)(32 * resident_rows(N) + 32 * N + 256) * 4u;   // IN block | O planes | misc (step_planes.cuh)
+  // dummy row | IN block | O planes | misc | reset job list | SELX (8-warp variant)   (step_planes.cuh)
+  uint32_t o = (uint32_t)(32 + 32 * resident_rows(N) + 32 * N + 256 + 512 + (v ? 4 * maxs4 * 2 * 32 : 0)) * 4u;
   const uint32_t tab = (uint32_t)n.n_attr_states * NW * 4u * (n.attr_simple ? 1u : 2u) + (uint32_t)(n.n_attr + 1) * 4u + (uint32_t)n.n_attr_states + 64u;
   L.attr_in_smem = (n.n_attr > 0 && (tab <= 24u * 1024u || !n.attr_simple)) ? 1u : 0u;
   if (L.attr_in_smem) {
@@ -258,11 +265,6 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
   }
   L.total = o;
   if (L.total > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "plane-resident kernel needs %u B of shared memory", L.total);
-  const int64_t tiles = (a.n_envs + 1023) / 1024;
-  // 8 warps per tile halve a tile's latency (small batches: one CTA per SM or less); 4 warps per tile keep 8 tiles
-  // per SM in flight (large batches).  Both draw the same streams.
-  int v = (N > 32 || tiles < 2 * (int64_t)h->num_sms) ? 1 : 0;
-  if (const char* env = getenv("PBN_B200_PLANES_WARPS")) v = atoi(env) == 8 ? 1 : 0;
   cudaKernel_t k = h->planes_kernel[injected ? 1 : 0][v];
   if (L.total > h->planes_smem_opt_in[injected ? 1 : 0][v]) {
     PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -565,10 +567,12 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   if (a->env_offset < 0 || (a->env_offset & 1023)) return fail(PBN_ERR_INVALID, "env_offset=%lld must be a non-negative multiple of 1024", (long long)a->env_offset);
   if (a->target_id && h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "target_id given but no attractor table uploaded");
   {
-    const uint32_t known = PBN_STEP_AUTORESET | PBN_STEP_PDL | PBN_STEP_NO_COUNT | (jit::profile_build() ? 0x80000000u : 0u);
+    const uint32_t known = PBN_STEP_AUTORESET | PBN_STEP_PDL | PBN_STEP_NO_COUNT | PBN_STEP_CHAIN | (jit::profile_build() ? 0x80000000u : 0u);
     if (a->flags & ~known) return fail(PBN_ERR_INVALID, "unknown flag bits 0x%x", a->flags & ~known);
   }
   if ((a->flags & PBN_STEP_PDL) && !a->step_ctr_dev) return fail(PBN_ERR_INVALID, "PBN_STEP_PDL needs step_ctr_dev");
+  if ((a->flags & PBN_STEP_CHAIN) && (!a->resident || !(a->flags & PBN_STEP_PDL) || injected))
+    return fail(PBN_ERR_INVALID, "PBN_STEP_CHAIN needs args->resident and PBN_STEP_PDL (own-RNG steps)");
   if (a->flags & PBN_STEP_AUTORESET) {
     if (h->net.n_attr == 0) return fail(PBN_ERR_NO_ATTRACTORS, "auto-reset needs pbn_update_attractors first");
     if (!a->resident && (!a->target_id || !a->t)) return fail(PBN_ERR_INVALID, "auto-reset needs target_id and t");
@@ -1042,7 +1046,8 @@ int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_
 int64_t pbn_resident_words(const pbn_handle* h, int64_t n_envs) {
   if (!h || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
   const int64_t tiles = (n_envs + 1023) / 1024;
-  return (tiles > 0 ? tiles : 1) * 32 * (int64_t)resident_rows(h->net.n_genes);
+  const int64_t nt = tiles > 0 ? tiles : 1;
+  return nt * 32 * (int64_t)resident_rows(h->net.n_genes) + ((nt + 31) / 32) * 32;   // + one epoch word per tile
 }
 
 int pbn_resident_import(pbn_handle* h, uint32_t* resident, const uint64_t* state, const int32_t* target_id, const uint16_t* t,
@@ -1057,6 +1062,10 @@ int pbn_resident_import(pbn_handle* h, uint32_t* resident, const uint64_t* state
   const int grid = grid_for(h, ((n_envs + 1023) / 1024) * 1024, 256, 8);
   if (h->W == 1) resident_import_kernel<1><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
   else resident_import_kernel<2><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
+  {
+    const int64_t nt = (n_envs + 1023) / 1024;
+    PBN_CUDA(cudaMemsetAsync(resident + nt * 32 * (int64_t)resident_rows(h->net.n_genes), 0, (size_t)((nt + 31) / 32) * 32 * 4, stream));
+  }
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
   return PBN_OK;

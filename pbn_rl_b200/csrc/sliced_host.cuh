@@ -172,10 +172,11 @@ inline int sliced_min_blocks(const GenNet& g) {
 }
 
 
-// Selection groups ("parts"): slot r belongs to part r mod 8; a part draws its slots' selection planes
-// (pbn_draw_part: one private Philox block per slot, then the part's shared pool of pair-planes for the 1/16 of the
-// 1-of-3 draws that are still rejected -- see step_planes.cuh "Random streams") and evaluates its genes
-// (pbn_eval_part, plane-resident kernel).  Single-predictor genes are spread over the parts by load.
+// Selection groups and evaluation parts: slot r belongs to group r mod 4 and to part r mod 8.  A group draws its
+// slots' selection planes (pbn_draw_group: one private Philox block per slot, then the group's shared pool of
+// pair-planes for the 1/16 of the 1-of-3 draws that are still rejected -- see step_sliced.cuh "Random streams"); a
+// part evaluates its genes (pbn_eval_part, plane-resident kernel).  Single-predictor genes are spread over the
+// parts by load.
 inline void generate_parts(const GenNet& g, std::string& u) {
   const int N = g.n_genes;
   char buf[320];
@@ -197,50 +198,79 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       part[i] = best;
       load[best] += 1;
     }
-  u += "\n#define PBN_CLAIM(k, px, py) { const uint32_t rj_ = lo[k] & hi[k]; const uint32_t tk_ = rj_ & av; av &= ~rj_; "
+  // ---- selection planes of a group: ONE copy of the code for all groups (q is a run-time, warp-uniform value), so
+  // that the warps of a tile share their instruction stream; the slot's K is a compile-time constant where the
+  // four groups agree on it, else it comes from the kSelK table.
+  const int NSEL = slot;
+  const int MAXS4 = (NSEL + 3) / 4 > 0 ? (NSEL + 3) / 4 : 1;
+  u += "\n#define PBN_CLAIM(k, m3, px, py) { const uint32_t rj_ = lo[k] & hi[k] & (m3); const uint32_t tk_ = rj_ & av; av &= ~rj_; "
        "lo[k] = bmux(tk_, px, lo[k]); hi[k] = bmux(tk_, py, hi[k]); }\n";
-  u += "// selection planes of part q: lo[k] + 2*hi[k] = predictor index of slot r = q + 8k, bit-sliced over the column's 32 envs\n";
-  u += "__device__ __forceinline__ void pbn_draw_part(uint32_t q, uint64_t gid, uint64_t step, const uint32_t (&rk)[20],\n"
-       "                                              uint32_t (&lo)[PBN_MAXS], uint32_t (&hi)[PBN_MAXS]) {\n";
-  u += "#pragma unroll\n  for (int k = 0; k < PBN_MAXS; ++k) { lo[k] = 0u; hi[k] = 0u; }\n";
-  for (int q = 0; q < 8; ++q) {
-    std::vector<int> ks;  // K of the part's slots, in slot order
-    for (int i = 0; i < N; ++i)
-      if (slot_of[i] >= 0 && (slot_of[i] & 7) == q) ks.push_back((int)g.funcs[i].size());
-    if (ks.empty()) continue;
-    snprintf(buf, sizeof(buf), "  if (q == %du) {\n", q);
-    u += buf;
-    std::string any;
-    for (size_t k = 0; k < ks.size(); ++k) {
-      const int r = q + 8 * (int)k;
-      snprintf(buf, sizeof(buf), "    { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, %du, rk);  // slot %d, K = %d\n", r, r, ks[k]);
-      u += buf;
-      if (ks[k] == 2) {
-        snprintf(buf, sizeof(buf), "      lo[%zu] = A.x; }\n", k);
-      } else if (ks[k] == 4) {
-        snprintf(buf, sizeof(buf), "      lo[%zu] = A.x; hi[%zu] = A.y; }\n", k, k);
-      } else {
-        snprintf(buf, sizeof(buf), "      const uint32_t rj = A.x & A.y; lo[%zu] = bmux(rj, A.z, A.x); hi[%zu] = bmux(rj, A.w, A.y); }\n", k, k);
-        if (!any.empty()) any += " | ";
-        snprintf(buf + 200, 100, "(lo[%zu] & hi[%zu])", k, k);
-        any += buf + 200;
-      }
-      u += buf;
+  u += "// selection planes of group q (slots r = q + 4k): lo[k] + 2*hi[k] = predictor index, bit-sliced over the column's 32 envs\n";
+  u += "__device__ __forceinline__ void pbn_draw_group(uint32_t q, uint64_t gid, uint64_t step, const uint32_t (&rk)[20],\n"
+       "                                               uint32_t (&lo)[PBN_MAXS4], uint32_t (&hi)[PBN_MAXS4]) {\n";
+  std::vector<int> kof(NSEL, 1);
+  for (int i = 0; i < N; ++i)
+    if (slot_of[i] >= 0) kof[slot_of[i]] = (int)g.funcs[i].size();
+  std::string any;
+  std::vector<std::string> m3(MAXS4);
+  for (int k = 0; k < MAXS4; ++k) {
+    int Kq[4];
+    bool same = true, some3 = false;
+    for (int q = 0; q < 4; ++q) {
+      const int r = q + 4 * k;
+      Kq[q] = r < NSEL ? kof[r] : 1;
+      same = same && Kq[q] == Kq[0];
+      some3 = some3 || Kq[q] == 3;
     }
-    if (!any.empty()) {
-      u += "#pragma unroll 1\n    for (uint32_t i = 0u; i < 512u; ++i) {  // the part's pool of pair-planes: FIX blocks 512 q + i\n";
-      u += "      if (!__any_sync(0xFFFFFFFFu, (" + any + ") != 0u)) break;\n";
-      snprintf(buf, sizeof(buf), "      const Philox4 P = philox_stream_rk(gid, step, PBN_RNG_FIX, %du + i, rk);\n      uint32_t av = 0xFFFFFFFFu;\n", 512 * q);
+    snprintf(buf, sizeof(buf), "  lo[%d] = 0u; hi[%d] = 0u;\n", k, k);
+    u += buf;
+    if (same && Kq[0] == 1) {
+      m3[k] = "";
+      continue;
+    }
+    if (same) {
+      snprintf(buf, sizeof(buf), "  { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, q + %du, rk);  // K = %d in every group\n", 4 * k, Kq[0]);
       u += buf;
-      for (int pass = 0; pass < 2; ++pass) {
-        if (pass) u += "      av = 0xFFFFFFFFu;\n";
-        for (size_t k = 0; k < ks.size(); ++k)
-          if (ks[k] == 3) {
-            snprintf(buf, sizeof(buf), "      PBN_CLAIM(%zu, %s, %s)\n", k, pass ? "P.z" : "P.x", pass ? "P.w" : "P.y");
-            u += buf;
-          }
+      if (Kq[0] == 2) snprintf(buf, sizeof(buf), "    lo[%d] = A.x; }\n", k);
+      else if (Kq[0] == 4) snprintf(buf, sizeof(buf), "    lo[%d] = A.x; hi[%d] = A.y; }\n", k, k);
+      else snprintf(buf, sizeof(buf), "    const uint32_t rj = A.x & A.y; lo[%d] = bmux(rj, A.z, A.x); hi[%d] = bmux(rj, A.w, A.y); }\n", k, k);
+      u += buf;
+      m3[k] = Kq[0] == 3 ? "0xFFFFFFFFu" : "";
+    } else {
+      snprintf(buf, sizeof(buf), "  const uint32_t K%d = (q + %du < %du) ? kSelK[q + %du] : 1u;\n", k, 4 * k, NSEL, 4 * k);
+      u += buf;
+      snprintf(buf, sizeof(buf), "  if (K%d > 1u) { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, q + %du, rk);\n", k, 4 * k);
+      u += buf;
+      snprintf(buf, sizeof(buf), "    lo[%d] = A.x; if (K%d == 4u) hi[%d] = A.y;\n", k, k, k);
+      u += buf;
+      snprintf(buf, sizeof(buf), "    if (K%d == 3u) { const uint32_t rj = A.x & A.y; lo[%d] = bmux(rj, A.z, A.x); hi[%d] = bmux(rj, A.w, A.y); } }\n", k, k, k);
+      u += buf;
+      if (some3) {
+        snprintf(buf, sizeof(buf), "  const uint32_t m3_%d = K%d == 3u ? 0xFFFFFFFFu : 0u;\n", k, k);
+        u += buf;
+        snprintf(buf, sizeof(buf), "m3_%d", k);
+        m3[k] = buf;
+      } else {
+        m3[k] = "";
       }
-      u += "    }\n";
+    }
+    if (!m3[k].empty()) {
+      if (!any.empty()) any += " | ";
+      snprintf(buf, sizeof(buf), "(lo[%d] & hi[%d]%s%s)", k, k, m3[k] == "0xFFFFFFFFu" ? "" : " & ", m3[k] == "0xFFFFFFFFu" ? "" : m3[k].c_str());
+      any += buf;
+    }
+  }
+  if (!any.empty()) {
+    u += "#pragma unroll 1\n  for (uint32_t i = 0u; i < 1024u; ++i) {  // the group's pool of pair-planes: FIX blocks 1024 q + i\n";
+    u += "    if (!__any_sync(0xFFFFFFFFu, (" + any + ") != 0u)) break;\n";
+    u += "    const Philox4 P = philox_stream_rk(gid, step, PBN_RNG_FIX, 1024u * q + i, rk);\n    uint32_t av = 0xFFFFFFFFu;\n";
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass) u += "    av = 0xFFFFFFFFu;\n";
+      for (int k = 0; k < MAXS4; ++k)
+        if (!m3[k].empty()) {
+          snprintf(buf, sizeof(buf), "    PBN_CLAIM(%d, %s, %s, %s)\n", k, m3[k].c_str(), pass ? "P.z" : "P.x", pass ? "P.w" : "P.y");
+          u += buf;
+        }
     }
     u += "  }\n";
   }
@@ -257,8 +287,9 @@ inline void generate_parts(const GenNet& g, std::string& u) {
        "    else if (PM == 3) v_ = bmux(o[(g) * 32], ~x[(g) * 32], v_); \\\n"
        "    o[(g) * 32] = v_; d |= v_ ^ tg[(g) * 32]; }\n";
   u += "template <int PM>\n";
+  u += "// lo / hi: the selection planes of group q mod 4 (pbn_draw_group); slot r of the group sits at index r >> 2\n";
   u += "__device__ __forceinline__ uint32_t pbn_eval_part(uint32_t q, const uint32_t* x, uint32_t* o, const uint32_t* tg, uint32_t m,\n"
-       "                                                  const uint32_t (&lo)[PBN_MAXS], const uint32_t (&hi)[PBN_MAXS]) {\n";
+       "                                                  const uint32_t (&lo)[PBN_MAXS4], const uint32_t (&hi)[PBN_MAXS4]) {\n";
   u += "  uint32_t d = 0u;\n  (void)m;\n#define X(g) x[(g) * 32]\n";
   for (int q = 0; q < 8; ++q) {
     bool has = false;
@@ -309,7 +340,7 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       if (K == 1) {
         val = names[0];
       } else {
-        const int k = slot_of[i] >> 3;
+        const int k = slot_of[i] >> 2;
         snprintf(buf, sizeof(buf), "      const uint32_t s0 = lo[%d], s1 = hi[%d];\n", k, k);
         u += buf;
         if (K == 2) val = "bmux(s0, " + names[1] + ", " + names[0] + ")", u += "      (void)s1;\n";
@@ -342,9 +373,9 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
            "#define PBN_SCRATCH_WORDS %d\n#define PBN_INJECTED %d\n#define PBN_THREADS %d\n#define PBN_MIN_BLOCKS %d\n",
            N, NW, g.bins, NSEL, scratch_words(g), injected ? 1 : 0, sliced_threads(g), sliced_min_blocks(g));
   h += buf;
-  // plane-resident kernel (step_planes.cuh): slots per selection part, CTAs per SM of the two variants
-  snprintf(buf, sizeof(buf), "#define PBN_MAXS %d\n#define PBN_PLANES_MIN_BLOCKS_W4 %d\n#define PBN_PLANES_MIN_BLOCKS_W8 %d\n",
-           (NSEL + 7) / 8 > 0 ? (NSEL + 7) / 8 : 1, planes_min_blocks(g, 4), planes_min_blocks(g, 8));
+  // slots per selection group; plane-resident kernel (step_planes.cuh): CTAs per SM of the two variants
+  snprintf(buf, sizeof(buf), "#define PBN_MAXS4 %d\n#define PBN_PLANES_MIN_BLOCKS_W4 %d\n#define PBN_PLANES_MIN_BLOCKS_W8 %d\n",
+           (NSEL + 3) / 4 > 0 ? (NSEL + 3) / 4 : 1, planes_min_blocks(g, 4), planes_min_blocks(g, 8));
   h += buf;
   *gen_h = h;
 

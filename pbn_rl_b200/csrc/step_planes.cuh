@@ -48,25 +48,65 @@ constexpr int kRowTarget = PBN_N, kRowTid = 2 * PBN_N, kRowT = 2 * PBN_N + kTidP
 constexpr int kResRows = 2 * PBN_N + kTidPlanes + kTPlanes;
 constexpr int kResTileWords = kResRows * 32;
 constexpr uint32_t kNoTarget = 255u;
-// shared memory (32-bit words): [IN block | O planes | misc]; tables follow at PlanesLayout offsets
-constexpr int kPlO = kResTileWords;
+// shared memory (32-bit words): [dummy row | IN block | O planes | misc | SELX (8-warp variant)]; tables follow at
+// PlanesLayout offsets.  The dummy row sits where "gene -1" would be: action value 0 (no-op) needs no test.
+constexpr int kPlIn = 32;
+constexpr int kPlO = kPlIn + kResTileWords;
 constexpr int kPlMisc = kPlO + PBN_N * 32;
 constexpr int kPlDiff = kPlMisc, kPlHit = kPlMisc + 32, kPlGe = kPlMisc + 64, kPlHt = kPlMisc + 96, kPlM = kPlMisc + 128;
 constexpr int kPlStat = kPlMisc + 160, kPlRew = kPlMisc + 168, kPlMbar = kPlMisc + 192;
-constexpr int kPlFixedWords = kPlMisc + 256;
+constexpr int kPlJobs = kPlMisc + 256;                 // [warp][envs per warp] u16 job list of the auto-reset (2 KB)
+constexpr int kPlSelx = kPlJobs + 512;                 // [group][k][lo | hi][lane]: planes of the parts of warps 4..7
+constexpr int kPlSelxWords = 4 * PBN_MAXS4 * 2 * 32;
 static_assert(2 * (PBN_BINS + 1) <= 24, "reward table does not fit its slot");
 
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_commit_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr int kChainPolls = 1 << 15;   // then the tile falls back to waiting for the whole previous launch
+
 __device__ __forceinline__ void bulk_commit_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// One action byte a of an env: if 1 <= a <= N and a differs from the env's earlier bytes p0, p1 (set semantics), toggle
+// `bit` in the plane of gene a - 1 (row a of the array at shared byte address xrow0) and add `inc` to cnt; otherwise
+// the toggle goes to the dummy row 0.  Branch-free PTX: the compiler builds a branch diamond per action byte, also
+// around a predicated atomic.
+template <int NPREV>
+__device__ __forceinline__ void flip_action(uint32_t xrow0, uint32_t a, uint32_t p0, uint32_t p1, uint32_t bit, uint32_t inc, uint32_t& cnt) {
+  if (NPREV == 0) {
+    asm volatile("{ .reg .pred p; .reg .u32 t, ad;\n sub.u32 t, %1, 1;\n setp.lt.u32 p, t, %4;\n mad.lo.u32 ad, %1, 128, %2;\n"
+                 "@p red.shared.xor.b32 [ad], %3;\n @p add.u32 %0, %0, %5;\n }"
+                 : "+r"(cnt) : "r"(a), "r"(xrow0), "r"(bit), "n"(PBN_N), "r"(inc) : "memory");
+  } else if (NPREV == 1) {
+    asm volatile("{ .reg .pred p; .reg .u32 t, ad;\n sub.u32 t, %1, 1;\n setp.lt.u32 p, t, %4;\n setp.ne.and.u32 p, %1, %6, p;\n"
+                 "selp.u32 t, %1, 0, p;\n mad.lo.u32 ad, t, 128, %2;\n red.shared.xor.b32 [ad], %3;\n @p add.u32 %0, %0, %5;\n }"
+                 : "+r"(cnt) : "r"(a), "r"(xrow0), "r"(bit), "n"(PBN_N), "r"(inc), "r"(p0) : "memory");
+  } else {
+    asm volatile("{ .reg .pred p; .reg .u32 t, ad;\n sub.u32 t, %1, 1;\n setp.lt.u32 p, t, %4;\n setp.ne.and.u32 p, %1, %6, p;\n"
+                 "setp.ne.and.u32 p, %1, %7, p;\n selp.u32 t, %1, 0, p;\n mad.lo.u32 ad, t, 128, %2;\n red.shared.xor.b32 [ad], %3;\n @p add.u32 %0, %0, %5;\n }"
+                 : "+r"(cnt) : "r"(a), "r"(xrow0), "r"(bit), "n"(PBN_N), "r"(inc), "r"(p0), "r"(p1) : "memory");
+  }
+}
+
 template <int WARPS>
 __device__ __forceinline__ void step_planes_body(const StepParams& p, const PlanesLayout& L) {
-  constexpr int PARTS = 8 / WARPS;            // selection / evaluation parts per warp
+  constexpr int PARTS = 8 / WARPS;            // evaluation parts per warp (part = w + WARPS * h)
+  constexpr int THREADS = 32 * WARPS;
   constexpr int GPT = 8 / WARPS;              // groups of 4 consecutive envs per thread
   constexpr uint32_t kMyBits = (1u << (4 * GPT)) - 1u;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -74,10 +114,10 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
   const pbn_step_args& a = p.a;
   const NetParams& n = p.n;
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  uint32_t* const X = sm + lane;                          // s1 planes   [gene][lane]
-  uint32_t* const TG = sm + kRowTarget * 32 + lane;       // target planes
-  uint32_t* const TID = sm + kRowTid * 32 + lane;
-  uint32_t* const TS = sm + kRowT * 32 + lane;
+  uint32_t* const X = sm + kPlIn + lane;                          // s1 planes   [gene][lane]
+  uint32_t* const TG = sm + kPlIn + kRowTarget * 32 + lane;       // target planes
+  uint32_t* const TID = sm + kPlIn + kRowTid * 32 + lane;
+  uint32_t* const TS = sm + kPlIn + kRowT * 32 + lane;
   uint32_t* const O = sm + kPlO + lane;                   // perturbation planes, then out planes
   uint32_t* const s_stat = sm + kPlStat;
   float* const s_rew = reinterpret_cast<float*>(sm + kPlRew);
@@ -96,6 +136,11 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
   const int64_t E = a.n_envs;
   const int64_t n_tiles = (E + 1023) >> 10;
   const int64_t first_tile = (int64_t)blockIdx.x;
+  // tile-level chaining (PBN_STEP_CHAIN): one epoch word per tile behind the tiles' blocks; a step publishes
+  // epoch[tile] = its step counter + 1 once the tile's block is written, the next step of the sequence waits for it
+  const bool chain_out = (a.flags & PBN_STEP_CHAIN) != 0u;
+  const bool chain_in = chain_out && a.step_ctr != 0u;   // position 0 is launched fully serialised
+  uint32_t* const epoch = a.resident + n_tiles * kResTileWords;
 
   if (a.flags & PBN_STEP_PDL) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -131,49 +176,62 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
   bool first = true;
 
   for (int64_t tile = first_tile; tile < n_tiles; tile += gridDim.x) {
-    const bool full = (tile + 1) * 1024 <= E;
+    const int64_t left = E - tile * 1024;                 // envs from the tile's first on
+    const bool full = left >= 1024;
     const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
     const int64_t e0 = tile * 1024 + 4 * (int64_t)lane;   // env of (j = 0, c = 0) of this column
     uint32_t VALID = 0xFFFFFFFFu;
     if (!full) {
       VALID = 0u;
       for (int b = 0; b < 32; ++b)
-        if (e0 + 128 * (b >> 2) + (b & 3) < E) VALID |= 1u << b;
+        if (4 * (int)lane + 128 * (b >> 2) + (b & 3) < (int)left) VALID |= 1u << b;
     }
     // ---- P0. everything that does not depend on the previous launch ---------------------------------------
-    if (pm != PBN_PERT_NONE)
-      for (int i = threadIdx.x; i < PBN_N * 32; i += blockDim.x) sm[kPlO + i] = 0u;
+    if (pm != PBN_PERT_NONE) {
+      uint4* const o4 = reinterpret_cast<uint4*>(sm + kPlO);
+#pragma unroll
+      for (int it = 0; it < (PBN_N * 8 + THREADS - 1) / THREADS; ++it) {
+        const int i = it * THREADS + (int)threadIdx.x;
+        if (i < PBN_N * 8) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
     if (threadIdx.x < 32) {
       sm[kPlDiff + lane] = 0u;
       sm[kPlHit + lane] = 0u;
       sm[kPlM + lane] = 0u;
     }
-    uint32_t lo[PARTS][PBN_MAXS], hi[PARTS][PBN_MAXS];
+    // selection planes of group w & 3 (slots r = (w & 3) + 4k): the 4-warp variant draws its own; in the 8-warp
+    // variant warps 0..3 draw and hand the planes of the parts of warps 4..7 over through SELX (read after B1)
+    uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];
 #if PBN_INJECTED
 #pragma unroll
-    for (int h = 0; h < PARTS; ++h) {
-      const uint32_t q = w + (uint32_t)WARPS * h;
-#pragma unroll
-      for (int k = 0; k < PBN_MAXS; ++k) {
-        const int r = (int)q + 8 * k;
-        uint32_t s0 = 0u, s1 = 0u;
-        if (r < PBN_NSEL) {
-          const uint32_t g = kSelGene[r], K = kSelK[r];
-          for (int b = 0; b < 32; ++b) {
-            const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
-            uint32_t v = (env < E) ? a.sel[env * PBN_N + g] : 0u;
-            v = v < K ? v : K - 1u;
-            s0 |= (v & 1u) << b;
-            s1 |= ((v >> 1) & 1u) << b;
-          }
+    for (int k = 0; k < PBN_MAXS4; ++k) {
+      const int r = (int)(w & 3u) + 4 * k;
+      uint32_t s0 = 0u, s1 = 0u;
+      if (r < PBN_NSEL) {
+        const uint32_t g = kSelGene[r], K = kSelK[r];
+        for (int b = 0; b < 32; ++b) {
+          const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
+          uint32_t v = (env < E) ? a.sel[env * PBN_N + g] : 0u;
+          v = v < K ? v : K - 1u;
+          s0 |= (v & 1u) << b;
+          s1 |= ((v >> 1) & 1u) << b;
         }
-        lo[h][k] = s0;
-        hi[h][k] = s1;
       }
+      lo[k] = s0;
+      hi[k] = s1;
     }
 #else
+    if (WARPS == 4 || w < 4u) {
+      pbn_draw_group(w, gid, step_ctr, n.rk, lo, hi);
+      if (WARPS == 8) {
 #pragma unroll
-    for (int h = 0; h < PARTS; ++h) pbn_draw_part(w + (uint32_t)WARPS * h, gid, step_ctr, n.rk, lo[h], hi[h]);
+        for (int k = 0; k < PBN_MAXS4; ++k) {
+          sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2) * 32 + lane] = lo[k];
+          sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2 + 1) * 32 + lane] = hi[k];
+        }
+      }
+    }
 #endif
     uint32_t npert = 0u;
     if (pm != PBN_PERT_NONE) {
@@ -202,20 +260,24 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
 #else
       if (w < 4u && n.pert_rng) {
         // sub-stream w of the column: geometric skipping over the slots gene*8 + (b & 7) of slice bits 8w..8w+7
-        const uint32_t s_last = kSurvTable[kSlots];
+        // (the next event lies pos + 1 + j slots on, j = #{i >= 1 : u < S[i]}: none is left in the rem slots after
+        // pos iff u < S[rem] -- one table read settles the usual case, the search runs for real events only)
         uint32_t mb = 0u, k = 0u;
         Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
         int pos = -1;
+        uint32_t s_rem = kSurvTable[kSlots];
         while (true) {
           if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((k >> 2) & 63u), n.rk);
           const uint32_t u = pick4(blk, k & 3u);
           ++k;
-          pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
+          if (u < s_rem) break;
+          pos += pert_search(n, u);
           if (pos >= kSlots) break;
           const uint32_t b = 8u * w + ((uint32_t)pos & 7u);
           atomicOr(&O[(pos >> 3) * 32], 1u << b);
           mb |= 1u << b;
           npert += (VALID >> b) & 1u;
+          s_rem = __ldg(n.surv_sliced + (kSlots - 1 - pos));
         }
         if (mb) atomicOr(&sm[kPlM + lane], mb);
       }
@@ -223,13 +285,22 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     }
     if (first) {
       __syncthreads();   // mbarrier initialised, tables staged
-      if (a.flags & PBN_STEP_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+      if ((a.flags & PBN_STEP_PDL) && !chain_in) asm volatile("griddepcontrol.wait;" ::: "memory");
     }
     // ---- P1. the tile's block; interventions -> state planes; counters ---------------------------------------
     if (threadIdx.x == 0) {
+      if (chain_in) {
+        const uint32_t want = (uint32_t)step_ctr;
+        bool seen = false;
+        for (int it = 0; it < kChainPolls && !seen; ++it) {
+          seen = ld_acquire_gpu(epoch + tile) == want;
+          if (!seen) __nanosleep(64);
+        }
+        if (!seen) asm volatile("griddepcontrol.wait;" ::: "memory");
+      }
       fence_proxy_async();
       mbar_expect_tx(mbar, kResTileWords * 4u);
-      tma_load_1d(sm, a.resident + tile * kResTileWords, kResTileWords * 4u, mbar);
+      tma_load_1d(sm + kPlIn, a.resident + tile * kResTileWords, kResTileWords * 4u, mbar);
     }
     uint32_t act[GPT][PBN_BINS];   // the 4*BINS action bytes of each group of 4 envs
 #pragma unroll
@@ -254,29 +325,50 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     }
     mbar_wait(mbar, parity);
     parity ^= 1u;
-    uint32_t nfp = 0u, flips = 0u;   // 4-bit flip counts of this thread's envs
+    // flips of this thread's envs: action a >= 1 toggles gene a - 1 (row a of the array that starts at the dummy row);
+    // a repeated action of an env is dropped (set semantics), so XOR equals the OR-mask of the contract
+    uint32_t nfb[GPT];               // flip counts of each group's 4 envs, one byte per env
+    uint32_t flips = 0u;
+    {
+      const uint32_t xrow0 = smem_u32(sm + kPlIn - 32 + lane);   // row a of this array = plane of gene a - 1
+      const uint32_t bit0 = 1u << (4u * GPT * w);
 #pragma unroll
-    for (int g = 0; g < GPT; ++g) {
+      for (int g = 0; g < GPT; ++g) {
+        nfb[g] = 0u;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t b = 4u * (GPT * w + g) + c;
-        uint32_t av[PBN_BINS];
-        uint32_t nf = 0u;
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t bit = bit0 << (4 * g + c);
+          uint32_t av[PBN_BINS];
 #pragma unroll
-        for (int k = 0; k < PBN_BINS; ++k) {
-          const int q = c * PBN_BINS + k;
-          av[k] = (act[g][q >> 2] >> (8 * (q & 3))) & 0xFFu;
-          bool go = av[k] - 1u < (uint32_t)PBN_N;     // 0 = no-op, values > N are ignored
+          for (int k = 0; k < PBN_BINS; ++k) {
+            const int q = c * PBN_BINS + k;
+            av[k] = __byte_perm(act[g][q >> 2], 0u, 0x4440u + (q & 3));
+            if (k == 0) {
+              flip_action<0>(xrow0, av[k], 0u, 0u, bit, 1u << (8 * c), nfb[g]);
+            } else if (k == 1) {
+              flip_action<1>(xrow0, av[k], av[0], 0u, bit, 1u << (8 * c), nfb[g]);
+            } else if (k == 2) {
+              flip_action<2>(xrow0, av[k], av[0], av[1], bit, 1u << (8 * c), nfb[g]);
+            } else {
+              bool go = av[k] - 1u < (uint32_t)PBN_N;     // 0 = no-op, values > N are ignored
 #pragma unroll
-          for (int k2 = 0; k2 < k; ++k2) go = go && av[k2] != av[k];   // set semantics: duplicates do not cancel
-          if (go) {
-            atomicXor(&X[(av[k] - 1u) * 32], 1u << b);
-            ++nf;
+              for (int k2 = 0; k2 < k; ++k2) go = go && av[k2] != av[k];
+              if (go) {
+                atomicXor(sm + kPlIn - 32 + lane + av[k] * 32u, bit);
+                nfb[g] += 1u << (8 * c);
+              }
+            }
           }
         }
-        nfp |= nf << (4 * (4 * g + c));
-        flips += ((VALID >> b) & 1u) ? nf : 0u;
+        if (full) {
+          flips += nfb[g];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if ((VALID >> (4 * (GPT * (int)w + g) + c)) & 1u) flips += (nfb[g] >> (8 * c)) & 0xFFu;
+        }
       }
+      if (full) flips = __dp4a(flips, 0x01010101u, 0u);   // sum of the byte counts
     }
     if (w == WARPS - 1) {
       // t' = min(t + 1, 65535) and GE = (t' >= horizon), bit-sliced; HT = the env has a target
@@ -311,14 +403,21 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     // ---- P2. synchronous update of this warp's genes ---------------------------------------------------------
     {
       const uint32_t m = (pm == PBN_PERT_A) ? sm[kPlM + lane] : 0u;
+      if (WARPS == 8 && !PBN_INJECTED && w >= 4u) {
+#pragma unroll
+        for (int k = 0; k < PBN_MAXS4; ++k) {
+          lo[k] = sm[kPlSelx + (((w & 3u) * PBN_MAXS4 + k) * 2) * 32 + lane];
+          hi[k] = sm[kPlSelx + (((w & 3u) * PBN_MAXS4 + k) * 2 + 1) * 32 + lane];
+        }
+      }
       uint32_t d = 0u;
 #pragma unroll
       for (int h = 0; h < PARTS; ++h) {
         const uint32_t q = w + (uint32_t)WARPS * h;
-        if (pm == PBN_PERT_NONE) d |= pbn_eval_part<PBN_PERT_NONE>(q, X, O, TG, m, lo[h], hi[h]);
-        else if (pm == PBN_PERT_A) d |= pbn_eval_part<PBN_PERT_A>(q, X, O, TG, m, lo[h], hi[h]);
-        else if (pm == PBN_PERT_B) d |= pbn_eval_part<PBN_PERT_B>(q, X, O, TG, m, lo[h], hi[h]);
-        else d |= pbn_eval_part<PBN_PERT_C>(q, X, O, TG, m, lo[h], hi[h]);
+        if (pm == PBN_PERT_NONE) d |= pbn_eval_part<PBN_PERT_NONE>(q, X, O, TG, m, lo, hi);
+        else if (pm == PBN_PERT_A) d |= pbn_eval_part<PBN_PERT_A>(q, X, O, TG, m, lo, hi);
+        else if (pm == PBN_PERT_B) d |= pbn_eval_part<PBN_PERT_B>(q, X, O, TG, m, lo, hi);
+        else d |= pbn_eval_part<PBN_PERT_C>(q, X, O, TG, m, lo, hi);
       }
       if (d) atomicOr(&sm[kPlDiff + lane], d);
     }
@@ -347,10 +446,14 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
       const uint32_t j = GPT * w + g;
       const uint32_t hb = (H >> (4u * j)) & 15u, tb = (TR >> (4u * j)) & 15u;
       const int64_t e = e0 + 128 * (int64_t)j;
+      const uint32_t hbytes = (hb * 0x00204081u) & 0x01010101u, tbytes = (tb * 0x00204081u) & 0x01010101u;
+      // reward table index of the 4 envs, one byte each: flips + (BINS + 1) * hit
+      const uint32_t idx4 = nfb[g] + hbytes * (uint32_t)(PBN_BINS + 1);
       float rw[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) rw[c] = s_rew[((nfp >> (4 * (4 * g + c))) & 15u) + (((hb >> c) & 1u) ? PBN_BINS + 1 : 0)];
-      const uint32_t hbytes = (hb * 0x00204081u) & 0x01010101u, tbytes = (tb * 0x00204081u) & 0x01010101u;
+      for (int c = 0; c < 4; ++c)
+        rw[c] = *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(s_rew) +
+                                                (c == 0 ? (idx4 << 2) & 0x3FCu : (idx4 >> (8 * c - 2)) & 0x3FCu));
       if (full) {
         if (a.reward != nullptr) *reinterpret_cast<float4*>(a.reward + e) = make_float4(rw[0], rw[1], rw[2], rw[3]);
         if (a.terminated != nullptr) *reinterpret_cast<uint32_t*>(a.terminated + e) = hbytes;
@@ -378,18 +481,25 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
       }
     }
     if (a.stats != nullptr) {
+      // per-thread counts are small: two 16-bit fields per warp reduction (terminated | truncated, flips | perturbed)
       const uint32_t mine = kMyBits << mysh;
-      const uint32_t v[7] = {(uint32_t)__popc(VALID & mine), (uint32_t)__popc(Dm), (uint32_t)__popc(H & VALID & mine),
-                             (uint32_t)__popc(TR & VALID & mine), len_sum, flips, npert};
-#pragma unroll
-      for (int q = 0; q < 7; ++q) {
-        const uint32_t x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
-        if (lane == 0u && x != 0u) atomicAdd(&s_stat[q], x);
+      const uint32_t x0 = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(H & VALID & mine) | ((uint32_t)__popc(TR & VALID & mine) << 16));
+      const uint32_t x1 = __reduce_add_sync(0xFFFFFFFFu, flips | (npert << 16));
+      uint32_t x2 = 0u;
+      if (w == WARPS - 1) x2 = __reduce_add_sync(0xFFFFFFFFu, len_sum);
+      if (lane == 0u) {
+        if (x0 & 0xFFFFu) atomicAdd(&s_stat[PBN_STAT_TERMINATED], x0 & 0xFFFFu);
+        if (x0 >> 16) atomicAdd(&s_stat[PBN_STAT_TRUNCATED], x0 >> 16);
+        if (x1 & 0xFFFFu) atomicAdd(&s_stat[PBN_STAT_FLIPS], x1 & 0xFFFFu);
+        if (x1 >> 16) atomicAdd(&s_stat[PBN_STAT_PERTURBED], x1 >> 16);
+        if (x2) atomicAdd(&s_stat[PBN_STAT_EP_LEN_SUM], x2);
       }
     }
-    // ---- auto-reset: the finished envs of the warp are dealt out over its lanes (one Philox pass per 32), then
-    //      written into the planes one env at a time with one lane per gene
+    // ---- auto-reset: the finished envs of the warp are listed in shared memory and dealt out over its lanes (one
+    //      Philox pass per 32), then each lane writes its env's new state / target into the planes gene by gene
+    //      (branch-free: AND clears the bit unless it is to be set, OR sets it)
     if (a.flags & PBN_STEP_AUTORESET) {
+      uint16_t* const jobs = reinterpret_cast<uint16_t*>(sm + kPlJobs) + w * (32 * 4 * GPT);
       const uint32_t cnt = (uint32_t)__popc(Dm);
       uint32_t incl = cnt;
 #pragma unroll
@@ -398,25 +508,19 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
         if ((int)lane >= dd) incl += v;
       }
       const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      const uint32_t excl = incl - cnt;
+      {
+        uint32_t mm = Dm, pos = incl - cnt;
+        while (mm) {
+          jobs[pos++] = (uint16_t)(lane | ((mysh + (uint32_t)(__ffs(mm) - 1)) << 5));
+          mm &= mm - 1u;
+        }
+      }
+      __syncwarp();
       for (uint32_t base = 0; base < total; base += 32u) {   // warp-uniform trip count
         const uint32_t jb = base + lane;                     // the job of this lane
-        uint32_t Lo = 0u;                                    // owner: first lane whose inclusive count exceeds jb
-#pragma unroll
-        for (int st = 16; st >= 1; st >>= 1) {
-          const uint32_t probe = __shfl_sync(0xFFFFFFFFu, incl, (int)min(Lo + (uint32_t)st - 1u, 31u));
-          if (Lo + (uint32_t)st - 1u < 32u && probe <= jb) Lo += (uint32_t)st;
-        }
-        Lo = min(Lo, 31u);
-        const uint32_t eL = __shfl_sync(0xFFFFFFFFu, excl, (int)Lo);
-        const uint32_t DL = __shfl_sync(0xFFFFFFFFu, Dm, (int)Lo);
-        uint32_t info = 0u, sw[kNW], tw[kNW];
-#pragma unroll
-        for (int wd = 0; wd < kNW; ++wd) sw[wd] = tw[wd] = 0u;
         if (jb < total) {
-          uint32_t mm = DL;
-          for (uint32_t k = jb - eL; k != 0u; --k) mm &= mm - 1u;   // drop the k lowest finished envs of the owner
-          const uint32_t b = mysh + (uint32_t)(__ffs(mm) - 1);
+          const uint32_t code = jobs[jb];
+          const uint32_t Lo = code & 31u, b = code >> 5;
           const int64_t env = tile * 1024 + 4 * (int64_t)Lo + 128 * (int64_t)(b >> 2) + (b & 3u);
           const Philox4 r = philox_stream_rk((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.rk);
           int src, tgt;
@@ -425,38 +529,38 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
           if (L.attr_in_smem) { so = s_aoffs[src]; se = s_aoffs[src + 1]; to = s_aoffs[tgt]; }
           else { so = n.attr_offset[src]; se = n.attr_offset[src + 1]; to = n.attr_offset[tgt]; }
           const int js = so + (int)__umulhi(r.y, (uint32_t)(se - so));
-#pragma unroll
-          for (int wd = 0; wd < kNW; ++wd) {
-            if (L.attr_in_smem) {
-              sw[wd] = s_aval[js * kNW + wd];
-              tw[wd] = s_aval[to * kNW + wd];
-            } else {
-              sw[wd] = (uint32_t)(n.attr_val[(size_t)js * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
-              tw[wd] = (uint32_t)(n.attr_val[(size_t)to * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
-            }
-          }
-          info = Lo | (b << 5) | ((uint32_t)tgt << 10);
           if (a.source_id != nullptr) a.source_id[env] = src;
-        }
-        const uint32_t njobs = min(32u, total - base);
-#pragma unroll 1
-        for (uint32_t k = 0; k < njobs; ++k) {
-          const uint32_t inf = __shfl_sync(0xFFFFFFFFu, info, (int)k);
-          const uint32_t Lk = inf & 31u, bit = 1u << ((inf >> 5) & 31u), tid = inf >> 10;
+          const uint32_t bit = 1u << b;
+          uint32_t* const po = sm + kPlO + Lo;
+          uint32_t* const pt = sm + kPlIn + kRowTarget * 32 + Lo;
 #pragma unroll
           for (int wd = 0; wd < kNW; ++wd) {
-            const uint32_t sv = __shfl_sync(0xFFFFFFFFu, sw[wd], (int)k), tv = __shfl_sync(0xFFFFFFFFu, tw[wd], (int)k);
-            const uint32_t g = 32u * wd + lane;
-            if (g < (uint32_t)PBN_N) {
-              uint32_t* po = sm + kPlO + g * 32 + Lk;
-              uint32_t* pt = sm + kRowTarget * 32 + g * 32 + Lk;
-              if ((sv >> lane) & 1u) atomicOr(po, bit); else atomicAnd(po, ~bit);
-              if ((tv >> lane) & 1u) atomicOr(pt, bit); else atomicAnd(pt, ~bit);
+            uint32_t sv, tv;
+            if (L.attr_in_smem) {
+              sv = s_aval[js * kNW + wd];
+              tv = s_aval[to * kNW + wd];
+            } else {
+              sv = (uint32_t)(n.attr_val[(size_t)js * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+              tv = (uint32_t)(n.attr_val[(size_t)to * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+            }
+#pragma unroll
+            for (int gb = 0; gb < 32; ++gb) {
+              const int g = 32 * wd + gb;
+              if (g < PBN_N) {
+                const uint32_t ms = (uint32_t)((int32_t)(sv << (31 - gb)) >> 31), mt = (uint32_t)((int32_t)(tv << (31 - gb)) >> 31);
+                atomicAnd(po + g * 32, ~bit | ms);
+                atomicOr(po + g * 32, bit & ms);
+                atomicAnd(pt + g * 32, ~bit | mt);
+                atomicOr(pt + g * 32, bit & mt);
+              }
             }
           }
-          if (lane < (uint32_t)kTidPlanes) {
-            uint32_t* pi = sm + kRowTid * 32 + lane * 32 + Lk;
-            if ((tid >> lane) & 1u) atomicOr(pi, bit); else atomicAnd(pi, ~bit);
+#pragma unroll
+          for (int k = 0; k < kTidPlanes; ++k) {
+            uint32_t* const pi = sm + kPlIn + kRowTid * 32 + k * 32 + Lo;
+            const uint32_t mk = 0u - (((uint32_t)tgt >> k) & 1u);
+            atomicAnd(pi, ~bit | mk);
+            atomicOr(pi, bit & mk);
           }
         }
       }
@@ -467,19 +571,28 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
       uint32_t* gblk = a.resident + tile * kResTileWords;
       bulk_store(gblk, sm + kPlO, PBN_N * 128u);                                   // next states
       if (a.flags & PBN_STEP_AUTORESET)
-        bulk_store(gblk + kRowTarget * 32, sm + kRowTarget * 32, (PBN_N + kTidPlanes + kTPlanes) * 128u);
+        bulk_store(gblk + kRowTarget * 32, sm + kPlIn + kRowTarget * 32, (PBN_N + kTidPlanes + kTPlanes) * 128u);
       else
-        bulk_store(gblk + kRowT * 32, sm + kRowT * 32, kTPlanes * 128u);           // only the counters changed
-      bulk_commit_wait_read();
+        bulk_store(gblk + kRowT * 32, sm + kPlIn + kRowT * 32, kTPlanes * 128u);   // only the counters changed
+      if (chain_out) {
+        bulk_commit_wait_all();          // the block is written, not merely read out of shared memory
+        fence_proxy_async();
+        __threadfence();
+        st_release_gpu(epoch + tile, (uint32_t)step_ctr + 1u);
+      } else {
+        bulk_commit_wait_read();
+      }
     }
     first = false;
     if (tile + gridDim.x < n_tiles) __syncthreads();   // the next tile reuses the buffers
   }
   if (a.stats != nullptr) {
     __syncthreads();
-    if (threadIdx.x < 7) {
-      const uint32_t x = s_stat[threadIdx.x];
-      if (x != 0u) atomicAdd(&a.stats[threadIdx.x], (unsigned long long)x);
+    if (threadIdx.x < PBN_N_STATS) {
+      unsigned long long x = s_stat[threadIdx.x];
+      if (threadIdx.x == PBN_STAT_STEPS) x = blockIdx.x == 0 ? (unsigned long long)E : 0ull;
+      if (threadIdx.x == PBN_STAT_EPISODES) x = (unsigned long long)s_stat[PBN_STAT_TERMINATED] + s_stat[PBN_STAT_TRUNCATED];
+      if (x != 0ull) atomicAdd(&a.stats[threadIdx.x], x);
     }
   }
   bump_device_step(a, p.ticket);

@@ -32,10 +32,10 @@
 //   SELECT: the genes with K > 1 predictors get slots r = 0, 1, ... in gene order; slot r owns Philox block
 //           (SELECT, r) = words x, y, z, w.  K=2 uses x (s0), K=4 x, y (s0, s1), K=3 the pairs (x, y), (z, w): pair
 //           value 3 is rejected and replaced by the next pair.  The 1/16 of the positions still at 3 are settled by
-//           the pool of the slot's part q = r mod 8: Philox blocks (FIX, 512 q + i), i = 0, 1, ...; each block is two
-//           pair-planes (x, y), (z, w); per pair-plane the part's K=3 slots r = q, q + 8, ... in that order take
-//           bit b of the plane if they are still at 3 there and no earlier slot of the part has claimed bit b of this
-//           plane; blocks are consumed until no slot of the part is at 3 anywhere in the column.  Exactly uniform
+//           the pool of the slot's group q = r mod 4: Philox blocks (FIX, 1024 q + i), i = 0, 1, ...; each block is two
+//           pair-planes (x, y), (z, w); per pair-plane the group's K=3 slots r = q, q + 4, ... in that order take
+//           bit b of the plane if they are still at 3 there and no earlier slot of the group has claimed bit b of this
+//           plane; blocks are consumed until no slot of the group is at 3 anywhere in the column.  Exactly uniform
 //           1-of-3, all choices independent (no random pair is used twice).  sel = s0 + 2*s1.
 //   PERTURB: sub-stream q = b >> 3 (Philox blocks (PERTURB, 64q + i)) covers the 8 slice bits
 //           8q..8q+7: geometric skipping over slots gene*8 + (b & 7) with survival table S[0..8N].
@@ -293,22 +293,18 @@ __device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSme
 }
 
 #if !PBN_INJECTED
-// Selection planes of parts w and w + 4 (net_update.inc: pbn_draw_part; the same streams as the plane-resident
-// kernel) into the SEL scratch.  One out-of-line copy: the kernel calls it from several places.
-__device__ __noinline__ void draw_parts_to_scratch(const uint32_t (&rk)[20], uint32_t* sel0, uint32_t* sel1, uint64_t gid,
+// Selection planes of group w (net_update.inc: pbn_draw_group; the same streams as the plane-resident kernel) into
+// the SEL scratch.  One out-of-line copy: the kernel calls it from several places.
+__device__ __noinline__ void draw_group_to_scratch(const uint32_t (&rk)[20], uint32_t* sel0, uint32_t* sel1, uint64_t gid,
                                                   uint64_t step_ctr, uint32_t w) {
+  uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];
+  pbn_draw_group(w, gid, step_ctr, rk, lo, hi);
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const uint32_t q = w + 4u * (uint32_t)hh;
-    uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
-    pbn_draw_part(q, gid, step_ctr, rk, lo, hi);
-#pragma unroll
-    for (int k = 0; k < PBN_MAXS; ++k) {
-      const int r = (int)q + 8 * k;
-      if (r < PBN_NSEL) {
-        sel0[r * 32] = lo[k];
-        sel1[r * 32] = hi[k];
-      }
+  for (int k = 0; k < PBN_MAXS4; ++k) {
+    const int r = (int)w + 4 * k;
+    if (r < PBN_NSEL) {
+      sel0[r * 32] = lo[k];
+      sel1[r * 32] = hi[k];
     }
   }
 }
@@ -336,7 +332,7 @@ __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, co
     sel1[r * 32] = s1;
   }
 #else
-  draw_parts_to_scratch(n.rk, sel0, sel1, gid, step_ctr, w);
+  draw_group_to_scratch(n.rk, sel0, sel1, gid, step_ctr, w);
 #endif
 }
 
@@ -589,7 +585,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
         const uint32_t m = 1u << (g & 31u), gw = g >> 5;
         const bool first = !((M >> ib) & 1u);
         M |= 1u << ib;
-        ++npert;
+        if (FULL || e0 + 128 * (2 * (int)w + (int)(ib >> 2)) + (int)(ib & 3u) < E) ++npert;   // statistics count real envs only
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll

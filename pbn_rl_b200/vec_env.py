@@ -156,6 +156,10 @@ class VecPBNEnv:
     dependent launch: each step draws its state-independent selection planes under the tail of the
     previous kernel; the device counter is then advanced explicitly with :meth:`advance_counter`
     at the end of a captured sequence instead of by every launch.
+    ``chain=True`` (needs ``resident``; implies ``pdl``) additionally chains the steps of a sequence tile by tile
+    (``PBN_STEP_CHAIN``): a step's tile waits only for the same tile of the previous step, so consecutive steps
+    overlap on the device.  Only for open-loop sequences: the action buffers of all steps of a sequence must be
+    complete before its first step is enqueued, and nothing else may be enqueued between its steps.
     ``resident=True`` (sliced kernel) keeps the env state on the device as bit-planes between steps
     (``pbn_resident_import`` / ``pbn_step`` with ``args.resident``): the fastest form of :meth:`step`.
     ``state`` / ``target_id`` / ``t`` stay available as row-format tensors -- reading them exports the
@@ -169,7 +173,7 @@ class VecPBNEnv:
                  bins: int = 3, perturb_p: float = 0.0, perturb_mode: str = "A", r_success: float = 5.0,
                  r_step: float = 0.0, r_action: float = -1.0, kernel: str = "auto", env_offset: int = 0,
                  auto_reset: bool = False, pair_weights: Optional[np.ndarray] = None,
-                 device_counter: bool = False, pdl: bool = False, resident: bool = False):
+                 device_counter: bool = False, pdl: bool = False, resident: bool = False, chain: bool = False):
         self._h = None
         self.lib = _cabi.lib()  # raises if the CUDA extension is not built: no fallback
         if not torch.cuda.is_available():
@@ -219,6 +223,10 @@ class VecPBNEnv:
         self.terminated = torch.zeros((e,), dtype=torch.uint8, device=dev)
         self.truncated = torch.zeros((e,), dtype=torch.uint8, device=dev)
         self.stats_buf = torch.zeros((_cabi.N_STATS,), dtype=torch.int64, device=dev)
+        self.chain = bool(chain)
+        if self.chain and not resident:
+            raise ValueError("chain=True needs resident=True")
+        pdl = bool(pdl) or self.chain
         self.pdl = bool(pdl)
         self.step_ctr_dev = torch.zeros((1,), dtype=torch.int64, device=dev) if (device_counter or pdl) else None
         self._pos = 0  # position inside a PDL sequence (host part of the step counter)
@@ -257,6 +265,8 @@ class VecPBNEnv:
     def _planes(self) -> None:
         """Make the resident block current (imports the row-format tensors if they are newer)."""
         if not self._planes_fresh:
+            if self.pdl and self._pos:
+                self.advance_counter()   # an import restarts the sequence: its next step is launched fully serialised
             check(self.lib.pbn_resident_import(self._h, _ptr(self._res), _ptr(self._state),
                                                _ptr(self._target_id) if self.attractors is not None else None,
                                                _ptr(self._t), self.num_envs, self._stream()))
@@ -348,6 +358,8 @@ class VecPBNEnv:
         a.env_offset = self.env_offset
         a.n_envs = self.num_envs
         a.flags = (_cabi.STEP_AUTORESET if self.auto_reset else 0) | (_cabi.STEP_PDL if self.pdl else 0)
+        if self.chain and not rows and final_state is None:
+            a.flags |= _cabi.STEP_CHAIN
         if self.pdl:
             a.step_ctr = self._pos
         return a
@@ -412,6 +424,7 @@ class VecPBNEnv:
             if pert_mask.numel() != self.num_envs * self.n_words:
                 raise ValueError("pert_mask must be [E, W]")
         a = self._args(actions, final_state, stats)
+        a.flags &= ~_cabi.STEP_CHAIN
         a.sel = _ptr(sel)
         a.pert_mask = _ptr(pert_mask)
         check(self.lib.pbn_step_injected(self._h, C.byref(a), self._stream()))

@@ -13,14 +13,14 @@ import bench  # noqa: E402
 from pbn_rl_b200 import VecPBNEnv  # noqa: E402
 
 
-def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20, pdl=False, split=False, resident=False):
+def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20, pdl=False, split=False, resident=False, chain=False):
     dev = torch.device("cuda:0")
     es = []
     for b in range(batches):
         kw = dict(bench.ENV_KW)
         kw["perturb_p"] = p
         e = VecPBNEnv(net, envs, attrs, device=dev, env_offset=b * envs, auto_reset=auto_reset, device_counter=True,
-                      kernel=kernel, pdl=pdl, resident=resident, **kw)
+                      kernel=kernel, pdl=pdl, resident=resident, chain=chain, **kw)
         g = torch.Generator(device=dev).manual_seed(b)
         e.state[:, 0] = torch.randint(0, 1 << min(net.n_genes, 62), (envs,), generator=g, device=dev)
         e.set_target(torch.randint(0, len(attrs), (envs,), generator=g, device=dev, dtype=torch.int32))
@@ -77,6 +77,8 @@ def main():
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--split", default="", help="'pipe': pbn_predraw on a side stream + pbn_step with pre-drawn planes; 'main' / 'draw': either kernel alone")
     ap.add_argument("--graph-steps", type=int, default=32)
+    ap.add_argument("--chain", action="store_true", help="tile-level chaining of resident steps (PBN_STEP_CHAIN)")
+    ap.add_argument("--batches", type=int, default=8)
     ap.add_argument("--resident", action="store_true", help="plane-resident env state (step_planes.cuh)")
     ap.add_argument("--p", type=float, default=0.001, help="perturbation probability of the 'full' row")
     args = ap.parse_args()
@@ -92,9 +94,9 @@ def main():
         rows = rows[:1]
     for kernel in args.kernels.split(","):
         for label, p, ar, st, act in rows:
-            us = time_config(net, attrs, args.envs, kernel, p, ar, st, act, pdl=args.pdl, split=args.split, graph_steps=args.graph_steps, resident=args.resident)
+            us = time_config(net, attrs, args.envs, kernel, p, ar, st, act, pdl=args.pdl, split=args.split, graph_steps=args.graph_steps, resident=args.resident or args.chain, chain=args.chain, batches=args.batches)
             gbs = bench.BYTES_PER_STEP[W] * args.envs / us / 1e3
-            print(("resident " if args.resident else "") + "%-8s %-30s %9.2f us/step  %8.3e steps/s  %7.1f GB/s" % (kernel, label, us, args.envs / us * 1e6, gbs), flush=True)
+            print(("chain " if args.chain else "resident " if args.resident else "") + "%-8s %-30s %9.2f us/step  %8.3e steps/s  %7.1f GB/s" % (kernel, label, us, args.envs / us * 1e6, gbs), flush=True)
 
 
 if __name__ == "__main__":

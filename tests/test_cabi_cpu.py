@@ -144,8 +144,8 @@ int main(int argc, char** argv) {
     uint32_t d = 0;
     for (int i = 0; i < n; ++i) { o2[i * 32] = 0u; tg[i * 32] = x[((i + 1) % n) * 32]; }
     for (uint32_t q = 0; q < 8; ++q) {
-      uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
-      for (int k = 0; k < PBN_MAXS; ++k) { const int r = (int)q + 8 * k; lo[k] = r < nsel ? s0[r * 32] : 0u; hi[k] = r < nsel ? s1[r * 32] : 0u; }
+      uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];   // the planes of group q mod 4
+      for (int k = 0; k < PBN_MAXS4; ++k) { const int r = (int)(q & 3u) + 4 * k; lo[k] = r < nsel ? s0[r * 32] : 0u; hi[k] = r < nsel ? s1[r * 32] : 0u; }
       d |= pbn::pbn_eval_part<0>(q, x, o2, tg, 0u, lo, hi);
     }
     for (int i = 0; i < n; ++i) printf("%u ", o2[i * 32]);
@@ -159,10 +159,10 @@ int main(int argc, char** argv) {
     uint32_t rk[20];
     for (int r = 0; r < 10; ++r) { rk[2 * r] = (uint32_t)seed + r * 0x9E3779B9u; rk[2 * r + 1] = (uint32_t)(seed >> 32) + r * 0xBB67AE85u; }
     static uint32_t L[1024], H[1024];
-    for (uint32_t q = 0; q < 8; ++q) {
-      uint32_t lo[PBN_MAXS], hi[PBN_MAXS];
-      pbn::pbn_draw_part(q, gid, step, rk, lo, hi);
-      for (int k = 0; k < PBN_MAXS; ++k) { const int r = (int)q + 8 * k; if (r < nsel) { L[r] = lo[k]; H[r] = hi[k]; } }
+    for (uint32_t q = 0; q < 4; ++q) {
+      uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];
+      pbn::pbn_draw_group(q, gid, step, rk, lo, hi);
+      for (int k = 0; k < PBN_MAXS4; ++k) { const int r = (int)q + 4 * k; if (r < nsel) { L[r] = lo[k]; H[r] = hi[k]; } }
     }
     for (int r = 0; r < nsel; ++r) printf("%u %u ", L[r], H[r]);
     printf("\n");
@@ -175,7 +175,7 @@ int main(int argc, char** argv) {
 @pytest.mark.parametrize("name", NETS)
 def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     """Compile the generated net_gen.cuh / net_update.inc with g++: the predictor trees of both kernels against the
-    truth tables on random bit-planes, and the generated selection draw (pbn_draw_part, with csrc/philox.cuh compiled
+    truth tables on random bit-planes, and the generated selection draw (pbn_draw_group, with csrc/philox.cuh compiled
     for the host) against the oracle's twin of the stream (oracle/pbn_oracle.py: sliced_stream)."""
     _lib()
     from oracle import pbn_oracle as O

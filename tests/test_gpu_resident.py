@@ -226,3 +226,42 @@ def test_resident_graph_pdl_sequence_matches_eager():
     assert torch.equal(env.state, ref.state)
     assert torch.equal(env.t, ref.t)
     assert torch.equal(env.reward, ref.reward)
+
+
+@pytest.mark.parametrize("name", ["pbn28", "pbn70", "pbn10"])
+def test_chained_sequence_matches_eager(name):
+    """PBN_STEP_CHAIN: graphs of tile-chained launches on ONE env batch (every step really depends on the previous
+    one, tile by tile) == eager resident steps with the host counter, over several replays."""
+    import torch
+    from pbn_rl_b200 import VecPBNEnv
+    e = 40 * 1024 + 300
+    case = random_case(name, e, seed=41)
+    n = product_net(name).n_genes
+    g = torch.Generator(device="cuda").manual_seed(4)
+    acts = [torch.randint(0, n + 1, (e, 3), generator=g, device="cuda", dtype=torch.uint8) for _ in range(8)]
+    ref = _env(name, e, mode="A", p=0.01, auto_reset=True, horizon=7)
+    _load(ref, case)
+    env = VecPBNEnv(product_net(name), e, attractor_set(name), device="cuda:0", perturb_p=0.01, perturb_mode="A",
+                    seed=0x5EED, kernel="sliced", resident=True, auto_reset=True, chain=True,
+                    **dict(KW, horizon=7))
+    _load(env, case)
+    env._planes()
+    stream = torch.cuda.Stream()
+    rewards = []
+    with torch.cuda.stream(stream):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for a in acts:
+                env.step(a)
+            env.advance_counter()
+        for rep in range(3):
+            graph.replay()
+    for rep in range(3):
+        for a in acts:
+            ref.step(a)
+    torch.cuda.synchronize()
+    assert torch.equal(env.reward, ref.reward)
+    assert torch.equal(env.state, ref.state)
+    assert torch.equal(env.t, ref.t)
+    assert torch.equal(env.target_id, ref.target_id)
+    assert env.stats() == ref.stats()
