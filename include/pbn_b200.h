@@ -95,8 +95,8 @@ enum {
    * its (state-independent) predictor-selection planes while the previous kernel in the stream is
    * still draining, and only then waits for it (griddepcontrol.wait).  With this flag the launch
    * does NOT increment *step_ctr_dev: pass the position inside the captured sequence as step_ctr
-   * and call pbn_advance_counter once at the end of the sequence.  Position 0 is launched fully
-   * serialised (it may follow the pbn_advance_counter of the previous sequence, whose write it reads). */
+   * and call pbn_advance_counter once at the end of the sequence.  A step enqueued right after its own
+   * handle's pbn_advance_counter is launched fully serialised (it reads the counter that launch writes). */
   PBN_STEP_PDL = 2u,
   /* Do not increment *step_ctr_dev when the launch completes (several launches that belong to the same
    * logical step, e.g. the chunks of pbn_step_host, share one counter value). */
@@ -109,7 +109,7 @@ enum {
    * sequence are consecutive pbn_step calls on one stream for the same block and n_envs, with nothing enqueued
    * between them, and (2) everything else a step reads -- the action buffers of ALL steps of the sequence -- is
    * complete before the sequence's first step is enqueued (open-loop rollouts with pre-sampled actions; not an
-   * agent that computes step k+1's actions from step k's results).  Position 0 is launched fully serialised.  A tile
+   * agent that computes step k+1's actions from step k's results).  Position 0 waits for the whole previous launch.  A tile
    * whose predecessor does not show up within a bounded number of polls falls back to griddepcontrol.wait. */
   PBN_STEP_CHAIN = 8u
 };

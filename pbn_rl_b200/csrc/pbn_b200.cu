@@ -21,6 +21,10 @@ using namespace pbn;
 namespace {
 
 thread_local char g_err[512] = "";
+// The handle whose pbn_advance_counter was the last launch made through the library (else null): the next step of
+// THAT handle must not start before the counter update is complete and visible, so it is launched without the
+// programmatic-serialisation attribute.  Any other launch in between is itself fully serialised behind the update.
+const void* g_last_advance = nullptr;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -202,10 +206,10 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
   const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 8;
   if (grid > cap) grid = cap;
   void* args[] = {&p, &L};
-  // The first step of a PDL sequence (position 0) is launched fully serialised: the launch before it may be the
-  // pbn_advance_counter of the previous sequence, whose write to *step_ctr_dev this kernel reads before its
-  // griddepcontrol.wait (visibility of a primary grid's writes is only guaranteed after the wait).
-  if ((a.flags & PBN_STEP_PDL) && a.step_ctr != 0) {
+  // A PDL step reads *step_ctr_dev before its griddepcontrol.wait, and a primary grid's writes are only guaranteed
+  // visible after the wait: when the launch right before this one is this handle's own pbn_advance_counter, the step
+  // is launched fully serialised instead.
+  if ((a.flags & PBN_STEP_PDL) && g_last_advance != h) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)h->sliced_threads);
@@ -270,12 +274,17 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
     PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     h->planes_smem_opt_in[injected ? 1 : 0][v] = L.total;
   }
-  int64_t grid = tiles;
+  // Tile-chained sequences (PBN_STEP_CHAIN) run best with CTAs that walk several tiles: a launch then occupies a
+  // fraction of the SMs' CTA slots, the next launches of the sequence become resident beside it, and the device
+  // always holds tiles of two or three steps in different phases (Philox draws, memory waits, logic).
+  int tpc = (a.flags & PBN_STEP_CHAIN) ? 2 : 1;
+  if (const char* env = getenv("PBN_B200_PLANES_TILES_PER_CTA")) tpc = atoi(env) > 0 ? atoi(env) : tpc;
+  int64_t grid = (tiles + tpc - 1) / tpc;
   const int64_t cap = (int64_t)h->num_sms * 64;
   if (grid > cap) grid = cap;
   const unsigned threads = v ? 256u : 128u;
   void* args[] = {&p, &L};
-  if ((a.flags & PBN_STEP_PDL) && a.step_ctr != 0) {
+  if ((a.flags & PBN_STEP_PDL) && g_last_advance != h) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(threads);
@@ -585,7 +594,7 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   p.ticket = h->d_ticket;
   if (h->kernel == PBN_KERNEL_SLICED) {
     const int rc = a->resident ? launch_planes(h, p, injected, stream) : launch_sliced(h, p, injected, stream);
-    if (rc == PBN_OK) h->launches += 1;
+    if (rc == PBN_OK) h->launches += 1, g_last_advance = nullptr;
     return rc;
   }
   const ScalarSmemLayout L = scalar_smem_layout(h->net, h->W);
@@ -608,7 +617,7 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   }
 #undef PBN_LAUNCH_SCALAR
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -672,7 +681,7 @@ int pbn_rollout(pbn_handle* h, uint64_t* state, int64_t n_steps, uint64_t step_c
   if (grid > cap) grid = cap;
   void* args[] = {&p};
   PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(h->rollout_kernel), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, smem, stream));
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -703,7 +712,7 @@ int pbn_predraw(pbn_handle* h, const pbn_step_args* a, uint32_t* planes, void* s
   if (grid > cap) grid = cap;
   void* args[] = {&p, &planes};
   PBN_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(h->predraw_kernel), dim3((unsigned)grid), dim3((unsigned)h->sliced_threads), args, 0, stream));
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -812,7 +821,7 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
       x.n_envs = n;
       export_kernel<<<16, 256, 0, h->s_d2h>>>(x);
       PBN_CUDA(cudaGetLastError());
-      h->launches += 1;
+      h->launches += 1, g_last_advance = nullptr;
       continue;
     }
     if (io->state) PBN_CUDA(cudaMemcpyAsync(io->state + e0 * W, a->state + e0 * W, (size_t)n * W * 8, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -840,7 +849,7 @@ int pbn_reset(pbn_handle* h, uint64_t* state, int32_t* target_id, int32_t* sourc
   else
     reset_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, target_id, source_id, t, done_mask, step_ctr, env_offset, n_envs);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -857,7 +866,7 @@ int pbn_unpack(pbn_handle* h, const uint64_t* state, void* out, int32_t out_kind
   else
     return fail(PBN_ERR_INVALID, "out_kind=%d unknown", out_kind);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -868,6 +877,7 @@ int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void*
   advance_counter_kernel<<<1, 1, 0, stream>>>(step_ctr_dev, n);
   PBN_CUDA(cudaGetLastError());
   h->launches += 1;
+  g_last_advance = h;
   return PBN_OK;
 }
 
@@ -888,7 +898,7 @@ int pbn_replay_observe(pbn_handle* h, const pbn_replay* r, int64_t head, const u
   DeviceGuard guard(h->device);
   replay_observe_kernel<<<grid_for(h, n_envs * h->W, 256, 8), 256, 0, stream>>>(*r, head, state, target_id, h->W, n_envs);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -905,7 +915,7 @@ int pbn_replay_commit(pbn_handle* h, const pbn_replay* r, int64_t head, const ui
   replay_commit_kernel<<<grid_for(h, n_envs * h->net.bins, 256, 8), 256, 0, stream>>>(*r, head, actions, reward, terminated, truncated,
                                                                                  next_state, h->W, h->net.bins, n_envs);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -921,12 +931,12 @@ int pbn_replay_sample(pbn_handle* h, const pbn_replay* r, const int64_t* index, 
     gather_unpack_kernel<<<grid_for(h, batch * h->net.n_genes, 256, 8), 256, 0, stream>>>(h->net, r->state, r->next_state, r->target_id, index,
                                                                                       h->W, batch, obs, next_obs);
     PBN_CUDA(cudaGetLastError());
-    h->launches += 1;
+    h->launches += 1, g_last_advance = nullptr;
   }
   if (actions || reward || done) {
     gather_scalars_kernel<<<grid_for(h, batch * h->net.bins, 256, 8), 256, 0, stream>>>(*r, index, h->net.bins, batch, actions, reward, done);
     PBN_CUDA(cudaGetLastError());
-    h->launches += 1;
+    h->launches += 1, g_last_advance = nullptr;
   }
   return PBN_OK;
 }
@@ -939,7 +949,7 @@ int pbn_observe(pbn_handle* h, const uint64_t* state, const int32_t* target_id, 
   gather_unpack_kernel<<<grid_for(h, n_envs * h->net.n_genes, 256, 8), 256, 0, stream>>>(h->net, state, nullptr, target_id, nullptr, h->W,
                                                                                      n_envs, obs, nullptr);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -952,7 +962,7 @@ int pbn_in_target(pbn_handle* h, const uint64_t* state, const int32_t* target_id
   if (h->W == 1) in_target_kernel<1><<<grid, 256, 0, stream>>>(h->net, state, target_id, out, n_envs);
   else in_target_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, target_id, out, n_envs);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -964,7 +974,7 @@ int pbn_rollout_track(pbn_handle* h, const uint8_t* terminated, uint8_t* active,
   DeviceGuard guard(h->device);
   rollout_track_kernel<<<grid_for(h, n_envs, 256, 8), 256, 0, stream>>>(terminated, active, count, max_steps, n_envs, n_active);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -977,7 +987,7 @@ int pbn_rollout_reduce(pbn_handle* h, const int32_t* count, const int32_t* pair_
   DeviceGuard guard(h->device);
   rollout_reduce_kernel<<<grid_for(h, n_envs, 256, 8), 256, 0, stream>>>(count, pair_id, n_envs, n_pairs, max_steps, matrix, hist);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -992,7 +1002,7 @@ int pbn_visit_count(pbn_handle* h, const uint64_t* state, const uint8_t* mask, i
   if (h->W == 1) visit_count_kernel<1><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, h->net.n_genes <= 63, overflow);
   else visit_count_kernel<2><<<grid, 256, 0, stream>>>(state, mask, n_envs, tags, slot_state, counts, (uint64_t)capacity - 1, false, overflow);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -1005,7 +1015,7 @@ int pbn_successor_sets(pbn_handle* h, const uint64_t* state, int64_t n_states, u
   if (h->W == 1) successor_sets_kernel<1><<<grid, 256, 0, stream>>>(h->net, state, n_states, can1, can0);
   else successor_sets_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, n_states, can1, can0);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -1023,7 +1033,7 @@ int pbn_closure_expand(pbn_handle* h, uint64_t* list, int64_t begin, int64_t end
   if (h->W == 1) closure_expand_kernel<1><<<grid, 128, 0, stream>>>(h->net, list, begin, end, list_cap, list_count, tags, slot_state, slot_index, (uint64_t)capacity - 1, max_free, status);
   else closure_expand_kernel<2><<<grid, 128, 0, stream>>>(h->net, list, begin, end, list_cap, list_count, tags, slot_state, slot_index, (uint64_t)capacity - 1, max_free, status);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -1039,7 +1049,7 @@ int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_
   if (h->W == 1) closure_reach_kernel<1><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_state, slot_index, (uint64_t)capacity - 1, changed);
   else closure_reach_kernel<2><<<grid, 128, 0, stream>>>(h->net, list, count, flags, tags, slot_state, slot_index, (uint64_t)capacity - 1, changed);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -1067,7 +1077,7 @@ int pbn_resident_import(pbn_handle* h, uint32_t* resident, const uint64_t* state
     PBN_CUDA(cudaMemsetAsync(resident + nt * 32 * (int64_t)resident_rows(h->net.n_genes), 0, (size_t)((nt + 31) / 32) * 32 * 4, stream));
   }
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -1081,7 +1091,7 @@ int pbn_resident_export(pbn_handle* h, const uint32_t* resident, uint64_t* state
   if (h->W == 1) resident_export_kernel<1><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
   else resident_export_kernel<2><<<grid, 256, 0, stream>>>(h->net, resident, state, target_id, t, n_envs);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -1093,7 +1103,7 @@ int pbn_pack(pbn_handle* h, const uint8_t* bits, uint64_t* state, int64_t n_envs
   const int grid = grid_for(h, n_envs * h->W, 256, 8);
   pack_kernel<<<grid, 256, 0, stream>>>(bits, state, h->net.n_genes, h->W, n_envs);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 
@@ -1108,7 +1118,7 @@ int pbn_attractor_id(pbn_handle* h, const uint64_t* state, int32_t* attr_id, int
   else
     attractor_id_kernel<2><<<grid, 256, 0, stream>>>(h->net, state, attr_id, n_envs);
   PBN_CUDA(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 1, g_last_advance = nullptr;
   return PBN_OK;
 }
 

@@ -580,8 +580,11 @@ inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std
   generate(g, injected, &gen_h, &upd);
   const std::string main_src = main_source();
   const bool profile = profile_build();
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-DPBN_PROFILE=1"};
-  const int n_opts = profile ? 5 : 4;
+  // PBN_B200_EXP=<n>: development experiments compiled into the kernels (never set in production)
+  std::string exp_opt = "-DPBN_EXP=0";
+  if (const char* env = getenv("PBN_B200_EXP")) exp_opt = std::string("-DPBN_EXP=") + env;
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", exp_opt.c_str(), "-DPBN_PROFILE=1"};
+  const int n_opts = profile ? 6 : 5;
   std::string key = gen_h + upd + main_src + kSrc_step_sliced + kSrc_step_planes + kSrc_pbn_common + kSrc_philox + kSrc_pbn_b200_h;
   for (int i = 0; i < n_opts; ++i) key += opts[i];
   char name[64];

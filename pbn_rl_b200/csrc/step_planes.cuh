@@ -142,6 +142,7 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
   const bool chain_in = chain_out && a.step_ctr != 0u;   // position 0 is launched fully serialised
   uint32_t* const epoch = a.resident + n_tiles * kResTileWords;
 
+  const uint64_t step_ctr = effective_step(a);   // (device counter: the load is issued first, its latency overlaps the staging)
   if (a.flags & PBN_STEP_PDL) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (first_tile < n_tiles && threadIdx.x < 2) {   // warm the L2 with the tile's inputs (coherent, only a hint)
@@ -171,7 +172,6 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
       for (int at = threadIdx.x; at < n.n_attr; at += blockDim.x)
         for (int en = n.attr_offset[at]; en < n.attr_offset[at + 1]; ++en) const_cast<uint8_t*>(s_eattr)[en] = (uint8_t)at;
   }
-  const uint64_t step_ctr = effective_step(a);
   uint32_t parity = 0u;
   bool first = true;
 
@@ -222,7 +222,10 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
       hi[k] = s1;
     }
 #else
-    if (WARPS == 4 || w < 4u) {
+    if (PBN_EXP == 5) {
+#pragma unroll
+      for (int k = 0; k < PBN_MAXS4; ++k) { lo[k] = (uint32_t)gid * 2654435761u + k; hi[k] = ~lo[k] & ((uint32_t)step_ctr + k * 77u); }
+    } else if (WARPS == 4 || w < 4u) {
       pbn_draw_group(w, gid, step_ctr, n.rk, lo, hi);
       if (WARPS == 8) {
 #pragma unroll
@@ -335,6 +338,7 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
 #pragma unroll
       for (int g = 0; g < GPT; ++g) {
         nfb[g] = 0u;
+        if (PBN_EXP == 6) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t bit = bit0 << (4 * g + c);
@@ -414,6 +418,10 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
 #pragma unroll
       for (int h = 0; h < PARTS; ++h) {
         const uint32_t q = w + (uint32_t)WARPS * h;
+#if PBN_EXP == 4
+        d |= pbn_eval_part<PBN_PERT_A>(q, X, O, TG, m, lo, hi);
+        continue;
+#endif
         if (pm == PBN_PERT_NONE) d |= pbn_eval_part<PBN_PERT_NONE>(q, X, O, TG, m, lo, hi);
         else if (pm == PBN_PERT_A) d |= pbn_eval_part<PBN_PERT_A>(q, X, O, TG, m, lo, hi);
         else if (pm == PBN_PERT_B) d |= pbn_eval_part<PBN_PERT_B>(q, X, O, TG, m, lo, hi);
@@ -498,7 +506,7 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     // ---- auto-reset: the finished envs of the warp are listed in shared memory and dealt out over its lanes (one
     //      Philox pass per 32), then each lane writes its env's new state / target into the planes gene by gene
     //      (branch-free: AND clears the bit unless it is to be set, OR sets it)
-    if (a.flags & PBN_STEP_AUTORESET) {
+    if ((a.flags & PBN_STEP_AUTORESET) && PBN_EXP != 2) {
       uint16_t* const jobs = reinterpret_cast<uint16_t*>(sm + kPlJobs) + w * (32 * 4 * GPT);
       const uint32_t cnt = (uint32_t)__popc(Dm);
       uint32_t incl = cnt;
@@ -548,10 +556,15 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
               const int g = 32 * wd + gb;
               if (g < PBN_N) {
                 const uint32_t ms = (uint32_t)((int32_t)(sv << (31 - gb)) >> 31), mt = (uint32_t)((int32_t)(tv << (31 - gb)) >> 31);
+#if PBN_EXP == 3
+                po[g * 32] = (po[g * 32] & (~bit | ms)) | (bit & ms);   // experiment: plain read-modify-write (races)
+                pt[g * 32] = (pt[g * 32] & (~bit | mt)) | (bit & mt);
+#else
                 atomicAnd(po + g * 32, ~bit | ms);
                 atomicOr(po + g * 32, bit & ms);
                 atomicAnd(pt + g * 32, ~bit | mt);
                 atomicOr(pt + g * 32, bit & mt);
+#endif
               }
             }
           }
@@ -566,6 +579,17 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
       }
     }
     __syncthreads();   // B3: the tile's block is final
+    if (a.stats != nullptr && threadIdx.x >= 32u && threadIdx.x < 32u + PBN_N_STATS) {
+      // the tile's statistics (every shared-memory counter was updated before B3); warp 1 does it while thread 0 is
+      // busy with the block's stores, nobody waits for anybody after B3
+      const uint32_t i = threadIdx.x - 32u;
+      unsigned long long x = s_stat[i];
+      if (i == PBN_STAT_STEPS) x = (unsigned long long)(left < 1024 ? left : 1024);
+      if (i == PBN_STAT_EPISODES) x = (unsigned long long)s_stat[PBN_STAT_TERMINATED] + s_stat[PBN_STAT_TRUNCATED];
+      __syncwarp(0xFFu);
+      s_stat[i] = 0u;
+      if (x != 0ull) atomicAdd(&a.stats[i], x);
+    }
     if (threadIdx.x == 0) {
       fence_proxy_async();
       uint32_t* gblk = a.resident + tile * kResTileWords;
@@ -585,15 +609,6 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     }
     first = false;
     if (tile + gridDim.x < n_tiles) __syncthreads();   // the next tile reuses the buffers
-  }
-  if (a.stats != nullptr) {
-    __syncthreads();
-    if (threadIdx.x < PBN_N_STATS) {
-      unsigned long long x = s_stat[threadIdx.x];
-      if (threadIdx.x == PBN_STAT_STEPS) x = blockIdx.x == 0 ? (unsigned long long)E : 0ull;
-      if (threadIdx.x == PBN_STAT_EPISODES) x = (unsigned long long)s_stat[PBN_STAT_TERMINATED] + s_stat[PBN_STAT_TRUNCATED];
-      if (x != 0ull) atomicAdd(&a.stats[threadIdx.x], x);
-    }
   }
   bump_device_step(a, p.ticket);
 }
