@@ -195,7 +195,9 @@ def run_reference(args):
         busy += t
     arm.close()
     value = total / busy
-    sample = "%d processes x %d env-steps per step, single-env oracle port, %s" % (cores, per_proc, args.net)
+    sample = ("%d processes x %d env-steps per bench step (a bounded sample of the 2^20-env workload: ms_per_step of this arm is "
+              "the time of that sample, not of 2^20 env-steps; the rate is what compares), single-env oracle port, %s"
+              % (cores, per_proc, args.net))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": K, "warmup": Wm, "ms_per_step": 1e3 * busy / max(K, 1),
@@ -223,54 +225,38 @@ def workload_config(args, world, kernel):
         "graph_steps": min(args.graph_steps, max(1, args.steps or 1)), "kernel": kernel,
         "launch": "CUDA graph of %d step launches%s" % (min(args.graph_steps, max(1, args.steps or 1)), "" if getattr(args, "no_pdl", False) else
                                                         ", programmatic dependent launch (selection planes drawn under the previous kernel's tail)"), "parallelism": "env-sharded x%d" % world,
+        "state_layout": "plane-resident (pbn_step with args->resident%s)" % (", tile-chained launches" if getattr(args, "chain", False) else "")
+        if getattr(args, "resident", False) or getattr(args, "chain", False) else "row-format u64 words",
     }
 
 
-def make_env(net, attrs, args, device, env_offset, device_counter=True):
+def make_env(net, attrs, args, device, env_offset, device_counter=True, n_envs=None, resident=None, chain=None):
     import torch
     from pbn_rl_b200 import VecPBNEnv
-    env = VecPBNEnv(net, args.envs, attrs, device=device, env_offset=env_offset, auto_reset=True,
-                    device_counter=device_counter, pdl=not args.no_pdl, kernel=args.kernel, **ENV_KW)
+    e = args.envs if n_envs is None else n_envs
+    resident = (args.resident or args.chain) if resident is None else resident
+    chain = args.chain if chain is None else chain
+    env = VecPBNEnv(net, e, attrs, device=device, env_offset=env_offset, auto_reset=True,
+                    device_counter=device_counter, pdl=not args.no_pdl, kernel=args.kernel, resident=resident, chain=chain, **ENV_KW)
     g = torch.Generator(device=device).manual_seed(env_offset + 1)
     n = net.n_genes
+    st = env.state
     for w in range(net.n_words):
         bits = min(64, n - 64 * w)
-        hi = torch.randint(0, 1 << max(bits - 31, 0), (args.envs,), generator=g, device=device, dtype=torch.int64)
-        lo = torch.randint(0, 1 << min(bits, 31), (args.envs,), generator=g, device=device, dtype=torch.int64)
-        env.state[:, w] = (hi << 31) | lo
-    env.set_target(torch.randint(0, len(attrs), (args.envs,), generator=g, device=device, dtype=torch.int32))
+        hi = torch.randint(0, 1 << max(bits - 31, 0), (e,), generator=g, device=device, dtype=torch.int64)
+        lo = torch.randint(0, 1 << min(bits, 31), (e,), generator=g, device=device, dtype=torch.int64)
+        st[:, w] = (hi << 31) | lo
+    env.set_target(torch.randint(0, len(attrs), (e,), generator=g, device=device, dtype=torch.int32))
     return env
 
 
-def run_gpu(args):
+def time_steps(envs, pool, K, G, Wm, stream, world):
+    """EXACTLY K timed step launches (K // G replays of a G-step CUDA graph + one tail graph) after Wm warm-up steps;
+    barrier + synchronize on both sides, CUDA events on the launching stream.  Returns milliseconds (this rank)."""
     import torch
     import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    net, attrs = load_workload(args.net)
-    W = net.n_words
-
-    # R independent env batches (each `envs` instances); batch b of rank r owns global env ids
-    # [(r*R + b) * envs, ...): disjoint Philox streams everywhere.
-    R = args.batches
-    envs = [make_env(net, attrs, args, device, (rank * R + b) * args.envs) for b in range(R)]
-    g = torch.Generator(device=device).manual_seed(1234 + rank)
-    pool = [torch.randint(0, net.n_genes + 1, (args.envs, 3), generator=g, device=device, dtype=torch.uint8)
-            for _ in range(args.action_pool)]
-    kernel = envs[0].kernel
-
-    K = max(1, args.steps)                     # EXACTLY K timed steps: K // G replays of a G-step graph + one tail graph
-    G = min(args.graph_steps, K)
+    R = len(envs)
     tail_steps = K % G
-    Wm = max(3, args.warmup)
-    stream = torch.cuda.Stream(device)
-    stats_total = torch.zeros(8, dtype=torch.int64, device=device)
 
     def enqueue(i):
         envs[i % R].step(pool[i % len(pool)])
@@ -298,9 +284,6 @@ def run_gpu(args):
                     e.advance_counter()
             tail.replay()
         stream.synchronize()
-
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -314,17 +297,62 @@ def run_gpu(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        clocks = sampler.stop()
-        ms = ev0.elapsed_time(ev1)
+        return ev0.elapsed_time(ev1)
+
+
+def max_over_ranks(ms, device, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    net, attrs = load_workload(args.net)
+    W = net.n_words
+
+    from pbn_rl_b200.dist import bind_to_gpu_numa
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank, rank=rank, world=world)   # before any page-locked allocation
+
+    # R independent env batches (each `envs` instances); batch b of rank r owns global env ids
+    # [(r*R + b) * envs, ...): disjoint Philox streams everywhere.
+    R = args.batches
+    envs = [make_env(net, attrs, args, device, (rank * R + b) * args.envs) for b in range(R)]
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    pool = [torch.randint(0, net.n_genes + 1, (args.envs, 3), generator=g, device=device, dtype=torch.uint8)
+            for _ in range(args.action_pool)]
+    kernel = envs[0].kernel
+
+    K = max(1, args.steps)                     # EXACTLY K timed steps
+    G = min(args.graph_steps, K)
+    Wm = max(3, args.warmup)
+    stream = torch.cuda.Stream(device)
+    stats_total = torch.zeros(8, dtype=torch.int64, device=device)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = time_steps(envs, pool, K, G, Wm, stream, world)
+    clocks = sampler.stop()
 
     # episode statistics: the only cross-GPU exchange of the path (one small NCCL all-reduce)
     for e in envs:
         stats_total += e.stats_buf
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats_total, op=dist.ReduceOp.SUM)
-    ms = float(t_ms.item())
+    ms = max_over_ranks(ms, device, world)
     value = args.envs * world * K / (ms * 1e-3)
     ms_per_step = ms / K
     bytes_per = BYTES_PER_STEP[W]
@@ -334,6 +362,24 @@ def run_gpu(args):
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # BASELINE config 3 as written ("2^20 envs sharded over 1/2/4/8 B200"): the SAME total batch cut over the ranks,
+    # envs / world instances per GPU (strong scaling); efficiency = this value / the weak-scaling value above, whose
+    # per-rank work is the whole batch
+    strong = None
+    if world > 1 or args.strong:
+        per = max(1024, (args.envs // world) // 1024 * 1024)
+        senvs = [make_env(net, attrs, args, device, ((world * R) + rank * R + b) * args.envs, n_envs=per) for b in range(R)]
+        spool = [p[:per].contiguous() for p in pool]
+        Ks = max(G, (K // 4) // G * G)
+        sms = max_over_ranks(time_steps(senvs, spool, Ks, G, Wm, stream, world), device, world)
+        sval = per * world * Ks / (sms * 1e-3)
+        strong = {"value": sval, "unit": UNIT, "ms_per_step": sms / Ks, "steps": Ks, "envs_per_gpu": per, "total_envs": per * world,
+                  "efficiency": sval / value, "efficiency_basis": "this value / the weak-scaling `value` of the same run (N x 2^20 envs)",
+                  "kernel_variant": "one 1024-env tile per CTA; below 2 tiles per SM the plane-resident kernel would switch to 8 warps per tile"}
+        for e in senvs:
+            e.close()
+        del senvs
 
     # DRAM traffic of the step kernel per launch, from the committed ncu capture of this command
     traffic = None
@@ -346,7 +392,7 @@ def run_gpu(args):
 
     # end-to-end through the public API with host buffers (rank-local, every rank does it)
     import numpy as np
-    e2e_env = envs[0]
+    e2e_env = envs[0] if not (args.resident or args.chain) else make_env(net, attrs, args, device, (2 * world * R + rank) * args.envs, resident=False, chain=False)
     host_actions = []
     for p in pool[:4]:  # the step's inputs live in pinned host memory, as the contract asks
         pa = e2e_env.pinned_actions()
@@ -354,9 +400,21 @@ def run_gpu(args):
         host_actions.append(pa)
     n_e2e = args.e2e_steps
 
+    packed_ok = net.n_genes <= 30
+    host_actions16 = []
+    if packed_ok:
+        for p in pool[:4]:
+            pa = e2e_env.pinned_actions16()
+            pa.numpy().view(np.uint16)[...] = e2e_env.pack_actions16(p.cpu().numpy())
+            host_actions16.append(pa)
+
     def time_e2e(compact):
+        def one(i):
+            if compact == "packed":
+                return e2e_env.step_host(None, compact="packed", actions16=host_actions16[i % 4])
+            return e2e_env.step_host(host_actions[i % 4], compact=compact)
         for i in range(3):
-            e2e_env.step_host(host_actions[i % 4], compact=compact)
+            one(i)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -364,29 +422,41 @@ def run_gpu(args):
         t0 = time.perf_counter()
         ee0.record()
         for i in range(n_e2e):
-            out = e2e_env.step_host(host_actions[i % 4], compact=compact)
+            out = one(i)
         ee1.record()
         torch.cuda.synchronize()
         secs = max(time.perf_counter() - t0, ee0.elapsed_time(ee1) * 1e-3)
         t_e2e = torch.tensor([secs], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        assert out["reward"].shape[0] == args.envs
+        assert next(iter(out.values())).shape[0] == args.envs
         return args.envs * world * n_e2e / float(t_e2e.item())
 
-    # full-width results (int64 state words, fp32 reward, terminated, truncated) and, for N <= 32, the
-    # compact form of the same results (uint32 state, fp32 reward, done byte): fewer PCIe bytes per env-step
+    # three forms of the same results: full width (int64 state words, fp32 reward, terminated, truncated), compact
+    # (uint32 state + fp32 reward + done byte, N <= 32) and packed (one uint32 = state | flags, actions as 3 x 5 bits
+    # in a uint16, N <= 30: the reward follows from the caller's actions and the terminated bit via pbn_reward_table)
     e2e_full = time_e2e(False)
     compact_ok = net.n_genes <= 32
-    e2e_value = time_e2e(True) if compact_ok else e2e_full
-    h2d, d2h = e2e_env.host_bytes_per_step_compact if compact_ok else e2e_env.host_bytes_per_step
+    e2e_compact = time_e2e(True) if compact_ok else None
+    e2e_packed = time_e2e("packed") if packed_ok else None
+    if packed_ok:
+        e2e_value, (h2d, d2h) = e2e_packed, e2e_env.host_bytes_per_step_packed
+        results = "one uint32 per env = state | terminated << 30 | truncated << 31; actions packed 3 x 5 bits in a uint16 (step_host(actions16=, compact='packed'))"
+    elif compact_ok:
+        e2e_value, (h2d, d2h) = e2e_compact, e2e_env.host_bytes_per_step_compact
+        results = "uint32 state + fp32 reward + done byte per env (step_host(compact=True))"
+    else:
+        e2e_value, (h2d, d2h) = e2e_full, e2e_env.host_bytes_per_step
+        results = "int64 state words + fp32 reward + terminated + truncated per env"
     e2e_note = {
-        "results": "uint32 state + fp32 reward + done byte per env (step_host(compact=True))" if compact_ok
-        else "int64 state words + fp32 reward + terminated + truncated per env",
+        "results": results,
         "full_width_value": e2e_full, "full_width_d2h_bytes_per_step": e2e_env.host_bytes_per_step[1],
+        "compact_value": e2e_compact, "compact_d2h_bytes_per_step": e2e_env.host_bytes_per_step_compact[1] if compact_ok else None,
         "transfer": "pbn_step_host: actions uploaded from pinned memory by the copy engine, results written "
                     "by an export kernel straight into pinned host memory (zero-copy over PCIe), 2 chunks pipelined",
+        "numa": numa,
     }
+    os.sched_setaffinity(0, affinity0)   # the CPU legs below use every host core again
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -396,6 +466,14 @@ def run_gpu(args):
         arm.close()
         cpu = {"value": n / busy, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d processes x %.0f s of single-env oracle steps (%d env-steps), %s" % (cores, args.cpu_seconds, n, args.net)}
+
+    extra_configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        for e in envs:
+            e.close()
+        del envs, pool
+        torch.cuda.empty_cache()
+        extra_configs = run_extra_configs(args, device, stream, peak)
 
     if rank == 0:
         stats = dict(zip(("steps", "episodes", "terminated", "truncated", "ep_len_sum", "flips", "perturbed"),
@@ -410,6 +488,8 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "e2e": dict({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                          "steps": n_e2e}, **e2e_note),
+            "strong": strong,
+            "configs": extra_configs,
             "gpu_launches": K,
             "clocks": clocks,
             "episode_stats": stats,
@@ -417,6 +497,98 @@ def run_gpu(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extra_configs(args, device, stream, peak):
+    """The other BASELINE.json configs, each a short run of the same protocol (rank 0, one GPU): config 2 (Bittner-10 x
+    4096 envs: fixture K4 recomputed on the GPU + throughput), config 4 (70-gene network, two-word states, 2^20 envs,
+    with its own roofline line), uncontrolled multi-step rollouts (pbn_rollout), and the plane-resident forms of the
+    headline workload."""
+    import copy
+    import hashlib
+
+    import numpy as np
+    import torch
+    from pbn_rl_b200 import VecPBNEnv
+    out = {}
+    G = 64
+
+    def short_run(a, net, attrs, K, R, resident=False, chain=False):
+        envs = [make_env(net, attrs, a, device, (100 + b) * a.envs, resident=resident, chain=chain) for b in range(R)]
+        g = torch.Generator(device=device).manual_seed(77)
+        pool = [torch.randint(0, net.n_genes + 1, (a.envs, 3), generator=g, device=device, dtype=torch.uint8) for _ in range(8)]
+        ms = time_steps(envs, pool, K, min(G, K), 16, stream, 1)
+        for e in envs:
+            e.close()
+        return ms / K
+
+    # ---- config 2: Bittner-10 x 4096 envs
+    net10, attrs10 = load_workload("pbn10")
+    n = net10.n_genes
+    x = np.array([((j + 1) * 0x9E3779B97F4A7C15) & ((1 << n) - 1) for j in range(4096)], dtype=np.uint64).reshape(-1, 1)
+    jj, ii = np.arange(4096)[:, None], np.arange(n)[None, :]
+    sels = [np.full((4096, n), k, dtype=np.uint8) for k in range(3)] + [((ii + jj) % 3).astype(np.uint8)]
+    env = VecPBNEnv(net10, 4096, None, device=device, perturb_mode="none", horizon=0, kernel=args.kernel)
+    h = hashlib.sha256()
+    for sel in sels:
+        env.set_state(torch.from_numpy(x.astype(np.int64)), packed=True)
+        env.step_injected(None, torch.from_numpy(sel))
+        torch.cuda.synchronize()
+        h.update(env.state.cpu().numpy().astype("<u8").tobytes())
+    env.close()
+    want = json.loads((GOLD / "k4_transitions.json").read_text())["pbn10"]["sha256"]
+    a10 = copy.copy(args)
+    a10.net, a10.envs = "pbn10", 4096
+    us = short_run(a10, net10, attrs10, 1280, 8) * 1e3
+    out["pbn10_4096"] = {"value": 4096 / us * 1e6, "unit": UNIT, "us_per_step": us, "k4_known_answer_bit_exact": h.hexdigest() == want,
+                         "note": "4 tiles of 1024 envs: launch-latency bound; the K4 fixture (tests/golden/k4_transitions.json) is "
+                                 "recomputed with injected selections on this GPU"}
+    # ---- config 4: 70-gene network, 2^20 envs, two-word states (49 algorithmic bytes per env-step)
+    net70, attrs70 = load_workload("pbn70")
+    a70 = copy.copy(args)
+    a70.net, a70.envs = "pbn70", 1 << 20
+    us = short_run(a70, net70, attrs70, 640, 8) * 1e3
+    ach = BYTES_PER_STEP[2] * a70.envs / us / 1e3
+    traffic = None
+    try:
+        traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get("pbn70", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    out["pbn70_2e20"] = {"value": a70.envs / us * 1e6, "unit": UNIT, "us_per_step": us,
+                         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                      "traffic": traffic, "bytes_per_env_step": BYTES_PER_STEP[2]}}
+    # ---- uncontrolled rollouts: 64 updates per launch, states on chip in between (pbn_rollout)
+    net28, attrs28 = load_workload("pbn28")
+    a28 = copy.copy(args)
+    a28.net, a28.envs = "pbn28", 1 << 20
+    envs = [VecPBNEnv(net28, 1 << 20, attrs28, device=device, env_offset=(200 + b) << 20, kernel=args.kernel, **ENV_KW) for b in range(8)]
+    for e in envs:
+        e.rollout(4)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(16):
+            envs[i % 8].rollout(64)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (16 * 64)
+    for e in envs:
+        e.close()
+    out["rollout_pbn28"] = {"value": (1 << 20) / us * 1e6, "unit": UNIT, "us_per_update": us,
+                            "note": "pbn_rollout: 64 uncontrolled updates per launch (env.step([]) x 64), p = 1e-3"}
+    # ---- the headline workload with plane-resident env state (same random streams, bit-identical results)
+    if not (args.resident or args.chain):
+        try:
+            us_r = short_run(a28, net28, attrs28, 640, 8, resident=True) * 1e3
+            us_c = short_run(a28, net28, attrs28, 640, 8, resident=True, chain=True) * 1e3
+            out["resident_pbn28"] = {"us_per_step_pdl": us_r, "us_per_step_chained": us_c,
+                                     "note": "pbn_step with args->resident (csrc/step_planes.cuh): no transposes and 29 instead of 33 "
+                                             "bytes per env-step, but the auto-reset scatter into the planes makes it slower than the "
+                                             "row-format kernel on this workload (5 % of the envs reset per step)"}
+        except Exception as exc:   # the resident form is optional
+            out["resident_pbn28"] = {"error": str(exc)[:200]}
+    return out
 
 
 _JSON_FD = None
@@ -454,6 +626,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream-serialised launches instead of programmatic dependent launch")
+    ap.add_argument("--resident", action="store_true", help="plane-resident env state (pbn_step with args->resident)")
+    ap.add_argument("--chain", action="store_true", help="plane-resident state with tile-chained launches (PBN_STEP_CHAIN)")
+    ap.add_argument("--strong", action="store_true", help="also time the strong-scaling form at N = 1 (envs / N per GPU)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (pbn10 x 4096, pbn70, rollout)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps_ref = args.steps if args.steps is not None else 20

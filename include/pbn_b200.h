@@ -230,6 +230,12 @@ typedef struct {
   /* Compact forms of the same results (fewer PCIe bytes per env-step); page-locked memory only. */
   uint32_t* state32;        /* HOST [E] out: the state word narrowed to 32 bits; networks with N <= 32 only */
   uint8_t* done;            /* HOST [E] out: terminated | truncated << 1 */
+  /* The smallest form, 6 bytes per env-step over PCIe (N <= 30, bins == 3; page-locked memory): */
+  uint32_t* packed;         /* HOST [E] out: state bits [N-1:0] | terminated << 30 | truncated << 31.  The reward is a
+                               function of (number of distinct non-zero actions of the env, terminated): the caller
+                               looks it up in pbn_reward_table instead of moving 4 more bytes per env */
+  const uint16_t* actions16; /* HOST [E] in, instead of `actions`: a0 | a1 << 5 | a2 << 10 (each action 0..N <= 30) */
+  uint16_t* actions16_dev;  /* DEVICE [E] staging buffer for actions16, caller-owned (actions_dev is needed as well) */
 } pbn_host_io;
 
 /* env.step(action) with HOST buffers, end to end: copies the actions to the device, steps all
@@ -241,6 +247,10 @@ typedef struct {
  * until the host outputs are complete (like the reference's env.step it returns values); it waits
  * on its own streams only, never on the whole device. */
 int pbn_step_host(pbn_handle* h, const pbn_step_args* args, const pbn_host_io* io, void* stream);
+
+/* reward = table[n_flips + (bins + 1) * terminated], n_flips = number of distinct action values in 1..N of the env
+ * (the fp32 values pbn_step writes): out[2 * (bins + 1)] (HOST). */
+int pbn_reward_table(const pbn_handle* h, float* out, int32_t n);
 
 /* Split launch (sliced kernel): the predictor-selection planes of a step depend only on (seed, env ids,
  * step counter), never on the state, so they can be drawn ahead of time -- pbn_predraw for step k+1 on a

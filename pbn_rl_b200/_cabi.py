@@ -34,7 +34,7 @@ EXPORTS = (
     "pbn_observe", "pbn_in_target", "pbn_rollout_track", "pbn_rollout_reduce",
     "pbn_visit_count", "pbn_successor_sets", "pbn_closure_expand", "pbn_closure_reach",
     "pbn_predraw", "pbn_planes_words", "pbn_rollout",
-    "pbn_resident_words", "pbn_resident_import", "pbn_resident_export",
+    "pbn_resident_words", "pbn_resident_import", "pbn_resident_export", "pbn_reward_table",
 )
 
 
@@ -113,6 +113,9 @@ class HostIO(C.Structure):
         ("reserved", C.c_int32),
         ("state32", C.c_void_p),
         ("done", C.c_void_p),
+        ("packed", C.c_void_p),
+        ("actions16", C.c_void_p),
+        ("actions16_dev", C.c_void_p),
     ]
 
 
@@ -180,6 +183,8 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_predraw.restype = C.c_int
     lib.pbn_planes_words.argtypes = [vp, i64]
     lib.pbn_planes_words.restype = i64
+    lib.pbn_reward_table.argtypes = [vp, vp, i32]
+    lib.pbn_reward_table.restype = C.c_int
     lib.pbn_resident_words.argtypes = [vp, i64]
     lib.pbn_resident_words.restype = i64
     lib.pbn_resident_import.argtypes = [vp, vp, vp, vp, vp, i64, vp]

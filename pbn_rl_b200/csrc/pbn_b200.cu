@@ -720,7 +720,10 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
   if (!h || !a || !io) return fail(PBN_ERR_INVALID, "null argument");
   if (a->n_envs < 0) return fail(PBN_ERR_INVALID, "n_envs=%lld", (long long)a->n_envs);
   if (a->n_envs == 0) return PBN_OK;
-  if (io->actions && !io->actions_dev) return fail(PBN_ERR_INVALID, "pbn_step_host: actions given without actions_dev staging buffer");
+  if ((io->actions || io->actions16) && !io->actions_dev) return fail(PBN_ERR_INVALID, "pbn_step_host: actions given without actions_dev staging buffer");
+  if (io->actions16 && (io->actions || !io->actions16_dev || h->net.bins != 3 || h->net.n_genes > 30))
+    return fail(PBN_ERR_INVALID, "pbn_step_host: actions16 needs actions16_dev, no `actions`, bins == 3 and N <= 30");
+  if (a->resident) return fail(PBN_ERR_UNSUPPORTED, "pbn_step_host works on the row-format arrays (export the resident block first)");
   if ((io->reward && !a->reward) || (io->terminated && !a->terminated) || (io->truncated && !a->truncated) || !a->state)
     return fail(PBN_ERR_INVALID, "pbn_step_host: a host output is requested whose device array is null");
   if (a->sel || a->pert_mask) return fail(PBN_ERR_INVALID, "pbn_step_host: sel/pert_mask must be null");
@@ -749,6 +752,15 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
         zero_copy = false;
       }
       zc[k] = static_cast<uint8_t*>(dp);
+    }
+  }
+  uint32_t* zc_packed = nullptr;
+  if (io->packed) {
+    void* dp = nullptr;
+    if (h->net.n_genes > 30 || !a->terminated || !a->truncated) return fail(PBN_ERR_INVALID, "pbn_step_host: packed needs N <= 30 and the terminated / truncated device arrays");
+    if (!zero_copy || cudaHostGetDevicePointer(&dp, io->packed, 0) != cudaSuccess || !(zc_packed = static_cast<uint32_t*>(dp))) {
+      cudaGetLastError();
+      return fail(PBN_ERR_INVALID, "pbn_step_host: packed needs page-locked host memory for every output");
     }
   }
   uint32_t* zc_state32 = nullptr;
@@ -780,10 +792,17 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
       PBN_CUDA(cudaMemcpyAsync(io->actions_dev + e0 * bins, io->actions + e0 * bins, (size_t)n * bins, cudaMemcpyHostToDevice, h->s_h2d));
       PBN_CUDA(cudaEventRecord(h->ev_in[c], h->s_h2d));
       PBN_CUDA(cudaStreamWaitEvent(stream, h->ev_in[c], 0));
+    } else if (io->actions16) {
+      PBN_CUDA(cudaMemcpyAsync(io->actions16_dev + e0, io->actions16 + e0, (size_t)n * 2, cudaMemcpyHostToDevice, h->s_h2d));
+      unpack_actions16_kernel<<<grid_for(h, n / 4 + 1, 256, 4), 256, 0, h->s_h2d>>>(io->actions16_dev + e0, io->actions_dev + e0 * bins, n);
+      PBN_CUDA(cudaGetLastError());
+      h->launches += 1;
+      PBN_CUDA(cudaEventRecord(h->ev_in[c], h->s_h2d));
+      PBN_CUDA(cudaStreamWaitEvent(stream, h->ev_in[c], 0));
     }
     pbn_step_args s = *a;
     s.state = a->state + e0 * W;
-    s.actions = io->actions ? io->actions_dev + e0 * bins : nullptr;
+    s.actions = (io->actions || io->actions16) ? io->actions_dev + e0 * bins : nullptr;
     if (a->target_id) s.target_id = a->target_id + e0;
     if (a->source_id) s.source_id = a->source_id + e0;
     if (a->t) s.t = a->t + e0;
@@ -818,6 +837,7 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
       x.term = a->terminated ? a->terminated + e0 : nullptr;
       x.trunc = a->truncated ? a->truncated + e0 : nullptr;
       x.done = zc_done ? zc_done + e0 : nullptr;
+      x.packed = zc_packed ? zc_packed + e0 : nullptr;
       x.n_envs = n;
       export_kernel<<<16, 256, 0, h->s_d2h>>>(x);
       PBN_CUDA(cudaGetLastError());
@@ -833,6 +853,19 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
   return PBN_OK;
 }
 int pbn_step_injected(pbn_handle* h, const pbn_step_args* a, void* stream) { return step_common(h, a, stream, true); }
+
+int pbn_reward_table(const pbn_handle* h, float* out, int32_t n) {
+  if (!h || !out) return fail(PBN_ERR_INVALID, "null argument");
+  const int bins = h->net.bins;
+  if (n < 2 * (bins + 1)) return fail(PBN_ERR_INVALID, "reward table has %d entries, buffer holds %d", 2 * (bins + 1), n);
+  for (int hit = 0; hit < 2; ++hit)
+    for (int nf = 0; nf <= bins; ++nf) {
+      volatile float base = h->net.r_action * (float)nf;   // two separately rounded fp32 operations, as on the device
+      base = h->net.r_step + base;
+      out[nf + (bins + 1) * hit] = hit ? (float)(base + h->net.r_success) : base;
+    }
+  return PBN_OK;
+}
 
 int pbn_reset(pbn_handle* h, uint64_t* state, int32_t* target_id, int32_t* source_id, uint16_t* t,
               const uint8_t* done_mask, uint64_t step_ctr, int64_t env_offset, int64_t n_envs, void* stream_) {

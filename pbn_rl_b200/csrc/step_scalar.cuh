@@ -299,8 +299,34 @@ struct ExportArgs {
   const uint8_t* term;
   const uint8_t* trunc;
   uint8_t* done;
+  uint32_t* packed;   // state | terminated << 30 | truncated << 31 (N <= 30)
   long long n_envs;
 };
+
+// actions16[e] = a0 | a1 << 5 | a2 << 10  ->  the 3 action bytes of env e (four envs per thread)
+__global__ void __launch_bounds__(256) unpack_actions16_kernel(const uint16_t* __restrict__ a16, uint8_t* __restrict__ out, long long n_envs) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = (size_t)n_envs >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(a16) & 7u) | (reinterpret_cast<uintptr_t>(out) & 3u)) == 0;
+  if (vec) {
+    for (size_t i = tid; i < n4; i += nth) {
+      const uint2 v = reinterpret_cast<const uint2*>(a16)[i];
+      uint32_t b[12];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t x = ((e < 2 ? v.x : v.y) >> (16 * (e & 1))) & 0xFFFFu;
+        b[3 * e] = x & 31u; b[3 * e + 1] = (x >> 5) & 31u; b[3 * e + 2] = (x >> 10) & 31u;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        reinterpret_cast<uint32_t*>(out)[3 * i + q] = b[4 * q] | (b[4 * q + 1] << 8) | (b[4 * q + 2] << 16) | (b[4 * q + 3] << 24);
+    }
+  }
+  for (size_t e = (vec ? (n4 << 2) : 0) + tid; e < (size_t)n_envs; e += nth) {
+    const uint32_t x = a16[e];
+    out[3 * e] = (uint8_t)(x & 31u); out[3 * e + 1] = (uint8_t)((x >> 5) & 31u); out[3 * e + 2] = (uint8_t)((x >> 10) & 31u);
+  }
+}
 
 __global__ void __launch_bounds__(256) export_kernel(ExportArgs x) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
@@ -329,6 +355,21 @@ __global__ void __launch_bounds__(256) export_kernel(ExportArgs x) {
       }
     }
     for (size_t e = (vec ? (n4 << 2) : 0) + tid; e < (size_t)x.n_envs; e += nth) x.state32[e] = (uint32_t)x.state64[e];
+  }
+  if (x.packed != nullptr) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(x.state64) | reinterpret_cast<uintptr_t>(x.packed)) & 15u) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x.term) | reinterpret_cast<uintptr_t>(x.trunc)) & 3u) == 0;
+    if (vec) {
+      for (size_t i = tid; i < n4; i += nth) {
+        const uint4 a = reinterpret_cast<const uint4*>(x.state64)[2 * i], b = reinterpret_cast<const uint4*>(x.state64)[2 * i + 1];
+        const uint32_t te = reinterpret_cast<const uint32_t*>(x.term)[i], tr = reinterpret_cast<const uint32_t*>(x.trunc)[i];
+        reinterpret_cast<uint4*>(x.packed)[i] =
+            make_uint4(a.x | ((te & 1u) << 30) | ((tr & 1u) << 31), a.z | (((te >> 8) & 1u) << 30) | (((tr >> 8) & 1u) << 31),
+                       b.x | (((te >> 16) & 1u) << 30) | (((tr >> 16) & 1u) << 31), b.z | (((te >> 24) & 1u) << 30) | (((tr >> 24) & 1u) << 31));
+      }
+    }
+    for (size_t e = (vec ? (n4 << 2) : 0) + tid; e < (size_t)x.n_envs; e += nth)
+      x.packed[e] = (uint32_t)x.state64[e] | ((uint32_t)(x.term[e] & 1u) << 30) | ((uint32_t)(x.trunc[e] & 1u) << 31);
   }
   if (x.done != nullptr) {
     const bool vec = ((reinterpret_cast<uintptr_t>(x.term) | reinterpret_cast<uintptr_t>(x.trunc) | reinterpret_cast<uintptr_t>(x.done)) & 3u) == 0;

@@ -490,22 +490,50 @@ class VecPBNEnv:
         tensor of that shape) go to the device without an intermediate host copy in :meth:`step_host`."""
         return torch.empty((self.num_envs, self.bins), dtype=torch.uint8, pin_memory=True)
 
-    def step_host(self, actions_host, chunks: int = 0, compact: bool = False) -> Dict[str, np.ndarray]:
+    def reward_table(self) -> np.ndarray:
+        """fp32 ``[2, bins + 1]``: ``reward = table[terminated, n_flips]`` with ``n_flips`` the number of distinct action
+        values in ``1..N`` of the env -- exactly the values :meth:`step` writes (``pbn_reward_table``).  Lets a host
+        caller of ``step_host(compact="packed")`` derive rewards without moving them over PCIe."""
+        out = np.zeros(2 * (self.bins + 1), dtype=np.float32)
+        check(self.lib.pbn_reward_table(self._h, out.ctypes.data, out.size))
+        return out.reshape(2, self.bins + 1)
+
+    def pinned_actions16(self) -> torch.Tensor:
+        """A page-locked int16 ``[E]`` host tensor for packed actions ``a0 | a1 << 5 | a2 << 10`` (bins = 3, N <= 30)."""
+        return torch.empty((self.num_envs,), dtype=torch.int16, pin_memory=True)
+
+    @staticmethod
+    def pack_actions16(actions) -> np.ndarray:
+        """uint8 ``[E, 3]`` actions -> the packed 16-bit form ``step_host`` takes as ``actions16``."""
+        a = np.asarray(actions, dtype=np.uint16).reshape(-1, 3)
+        return (a[:, 0] | (a[:, 1] << 5) | (a[:, 2] << 10)).astype(np.uint16)
+
+    def step_host(self, actions_host, chunks: int = 0, compact=False, actions16=None) -> Dict[str, np.ndarray]:
         """``step`` with HOST buffers, the call a user of the reference's CPU env makes per step
         (``pbn_step_host``): uploads ``actions_host`` (uint8 ``[E, bins]``: a pinned torch tensor is used
         in place, anything else is first copied into a pinned buffer; ``None`` = no interventions), steps,
         and streams state / reward / terminated / truncated into pinned host buffers returned as
         numpy views (valid until the next call).  ``compact=True`` returns the same information in
         fewer PCIe bytes: ``state32`` (uint32, networks with N <= 32), ``reward`` and ``done``
-        (``terminated | truncated << 1``).  The batch is processed in ``chunks`` ranges so that upload,
-        kernel and download overlap (0 = library default); blocks until the results are there."""
+        (``terminated | truncated << 1``); ``compact="packed"`` (N <= 30) returns one uint32 per env,
+        ``packed = state | terminated << 30 | truncated << 31`` -- the reward follows from the caller's own actions and
+        the terminated bit through :meth:`reward_table`.  ``actions16`` (instead of ``actions_host``): a pinned int16
+        ``[E]`` tensor of packed actions (:meth:`pack_actions16`), 2 instead of 3 bytes per env.  The batch is
+        processed in ``chunks`` ranges so that upload, kernel and download overlap (0 = library default); blocks
+        until the results are there."""
         hb = self._host_buffers()
-        key = "io_compact" if compact else "io"
+        key = "io_packed" if compact == "packed" else ("io_compact" if compact else "io")
         if key not in hb:
             io = _cabi.HostIO()
             io.actions_dev = hb["d_actions"].data_ptr()
-            io.reward = hb["reward"].data_ptr()
-            if compact:
+            if compact == "packed":
+                if self.n_genes > 30:
+                    raise ValueError("packed host results need N <= 30")
+                hb["packed"] = torch.empty((self.num_envs,), dtype=torch.int32, pin_memory=True)
+                io.packed = hb["packed"].data_ptr()
+                hb["views_packed"] = {"packed": hb["packed"].numpy().view(np.uint32)}
+            elif compact:
+                io.reward = hb["reward"].data_ptr()
                 if self.n_genes > 32:
                     raise ValueError("compact host results need N <= 32 (state32)")
                 hb["state32"] = torch.empty((self.num_envs,), dtype=torch.int32, pin_memory=True)
@@ -515,14 +543,24 @@ class VecPBNEnv:
                 hb["views_compact"] = {"state32": hb["state32"].numpy().view(np.uint32), "reward": hb["reward"].numpy(),
                                        "done": hb["done"].numpy()}
             else:
+                io.reward = hb["reward"].data_ptr()
                 io.state = hb["state"].data_ptr()
                 io.terminated = hb["terminated"].data_ptr()
                 io.truncated = hb["truncated"].data_ptr()
                 hb["views"] = {k: hb[k].numpy() for k in ("state", "reward", "terminated", "truncated")}
             hb[key] = io
         io = hb[key]
-        if actions_host is None:
-            io.actions = None
+        io.actions, io.actions16 = None, None
+        if actions16 is not None:
+            if not (isinstance(actions16, torch.Tensor) and actions16.is_pinned() and actions16.dtype == torch.int16
+                    and actions16.is_contiguous() and actions16.numel() == self.num_envs):
+                raise ValueError("actions16 must be a pinned contiguous int16 tensor with one entry per env")
+            if "d_actions16" not in hb:
+                hb["d_actions16"] = torch.empty((self.num_envs,), dtype=torch.int16, device=self.device)
+            io.actions16 = actions16.data_ptr()
+            io.actions16_dev = hb["d_actions16"].data_ptr()
+        elif actions_host is None:
+            pass
         elif isinstance(actions_host, torch.Tensor) and actions_host.is_pinned() and actions_host.dtype == torch.uint8 \
                 and actions_host.is_contiguous() and actions_host.numel() == self.num_envs * self.bins:
             io.actions = actions_host.data_ptr()
@@ -541,13 +579,19 @@ class VecPBNEnv:
             self.step_ctr += 1
         elif self.pdl:
             self._pos += 1
-        return hb["views_compact" if compact else "views"]
+        return hb["views_packed" if compact == "packed" else ("views_compact" if compact else "views")]
 
     @property
     def host_bytes_per_step(self) -> Tuple[int, int]:
         """(host->device, device->host) bytes moved by one :meth:`step_host`."""
         e = self.num_envs
         return e * self.bins, e * (8 * self.n_words + 4 + 1 + 1)
+
+    @property
+    def host_bytes_per_step_packed(self) -> Tuple[int, int]:
+        """The same for ``step_host(actions16=..., compact="packed")``: 2 bytes up, one uint32 down per env."""
+        e = self.num_envs
+        return e * 2, e * 4
 
     @property
     def host_bytes_per_step_compact(self) -> Tuple[int, int]:

@@ -60,3 +60,18 @@ def test_stats_allreduce_world2():
     assert stats[1] == 10 + 20 and stats[4] == 40 + 41
     assert ranges[0][0] == 0 and ranges[1][0] == ranges[0][1]
     assert sum(c for _, c in ranges) == total
+
+
+def test_parse_cpulist_and_numa_binding_is_harmless(tmp_path):
+    from pbn_rl_b200.dist import bind_to_gpu_numa, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    # a fake two-node sysfs tree: rank 1 of 2 lands on node 1 when the GPU's node is unknown (no CUDA device here)
+    for node, cpus in ((0, "0"), (1, "0")):
+        d = tmp_path / "devices" / "system" / "node" / ("node%d" % node)
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(cpus + "\n")
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa(0, rank=1, world=2, sysfs=str(tmp_path))
+    assert info["node"] in (None, 1)
+    os.sched_setaffinity(0, before)

@@ -191,3 +191,79 @@ def test_predraw_refused_where_it_cannot_be_exact():
     with pytest.raises(RuntimeError):
         env.predraw(env.planes_buffer())
     env.close()
+
+
+@pytest.mark.parametrize("name,e", [("pbn28", 5000), ("pbn10", 4096), ("pbn7", 1025)])
+@pytest.mark.parametrize("chunks", [0, 3])
+def test_packed_host_form_matches_oracle(name, e, chunks):
+    """step_host(actions16=..., compact="packed"): 2 bytes up, one uint32 down per env.  Compared with the ORACLE
+    (oracle.batched_step on the oracle's twin of the kernel's random streams), including the rewards the caller
+    derives from reward_table()."""
+    import torch
+    from oracle import pbn_oracle as O
+    from helpers import oracle_net
+    net, onet = product_net(name), oracle_net(name)
+    n = net.n_genes
+    attrs = attractor_set(name)
+    tables = O.attractor_tables(attrs.attractors, n)
+    kw = dict(horizon=6, r_success=5.0, r_step=-0.25, r_action=-1.0)
+    from pbn_rl_b200 import VecPBNEnv
+    env = VecPBNEnv(net, e, attrs, device="cuda:0", perturb_p=0.01, perturb_mode="A", seed=77, **kw)
+    _seed_env(env, name, e, 3)
+    state = env.state.cpu().numpy().astype(np.uint64)
+    target = env.target_id.cpu().numpy()
+    t = np.zeros(e, dtype=np.uint16)
+    rng = np.random.default_rng(4)
+    table = env.reward_table()
+    ids = np.arange(e, dtype=np.uint64)
+    for step in range(4):
+        act = rng.integers(0, n + 1, size=(e, 3), dtype=np.uint8)
+        a16 = env.pinned_actions16()
+        a16.numpy().view(np.uint16)[...] = env.pack_actions16(act)
+        out = env.step_host(None, chunks=chunks, compact="packed", actions16=a16)
+        if env.kernel == "sliced":
+            sel, pert = O.sliced_stream(onet, 0.01, ids, step, 77)
+        else:
+            sel, pert = O.scalar_stream_selection(onet, ids, step, 77), O.scalar_stream_perturbation(n, 0.01, ids, step, 77)
+        nxt, t, rew, term, trunc = O.batched_step(onet, tables, state, act, target, t, mode=O.PERT_A, sel=sel, pert=pert, **kw)
+        packed = out["packed"]
+        assert np.array_equal(packed & np.uint32((1 << 30) - 1), nxt[:, 0].astype(np.uint32)), f"state at step {step}"
+        assert np.array_equal((packed >> np.uint32(30)) & np.uint32(1), term.astype(np.uint32))
+        assert np.array_equal(packed >> np.uint32(31), trunc.astype(np.uint32))
+        # rewards from the caller's own actions + the terminated bit
+        nf = np.array([len({int(v) for v in row if 1 <= v <= n}) for row in act])
+        assert np.array_equal(table[term.astype(np.int64), nf].view(np.uint32), rew.view(np.uint32))
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), rew.view(np.uint32))
+        state = nxt
+    env.close()
+
+
+@pytest.mark.parametrize("name,e", [("pbn28", 3000), ("pbn70", 2048)])
+def test_step_host_matches_oracle(name, e):
+    """The full-width host form against the oracle (not only against pbn_step)."""
+    import torch
+    from oracle import pbn_oracle as O
+    from helpers import oracle_net
+    net, onet = product_net(name), oracle_net(name)
+    n = net.n_genes
+    attrs = attractor_set(name)
+    tables = O.attractor_tables(attrs.attractors, n)
+    kw = dict(horizon=6, r_success=5.0, r_step=-0.25, r_action=-1.0)
+    from pbn_rl_b200 import VecPBNEnv
+    env = VecPBNEnv(net, e, attrs, device="cuda:0", perturb_p=0.01, perturb_mode="B", seed=77, **kw)
+    _seed_env(env, name, e, 8)
+    state = env.state.cpu().numpy().astype(np.uint64)
+    target = env.target_id.cpu().numpy()
+    t = np.zeros(e, dtype=np.uint16)
+    rng = np.random.default_rng(6)
+    ids = np.arange(e, dtype=np.uint64)
+    for step in range(3):
+        act = rng.integers(0, n + 1, size=(e, 3), dtype=np.uint8)
+        out = env.step_host(act, chunks=2)
+        sel, pert = O.sliced_stream(onet, 0.01, ids, step, 77)
+        nxt, t, rew, term, trunc = O.batched_step(onet, tables, state, act, target, t, mode=O.PERT_B, sel=sel, pert=pert, **kw)
+        assert np.array_equal(out["state"].astype(np.uint64), nxt)
+        assert np.array_equal(out["reward"].view(np.uint32), rew.view(np.uint32))
+        assert np.array_equal(out["terminated"], term) and np.array_equal(out["truncated"], trunc)
+        state = nxt
+    env.close()
