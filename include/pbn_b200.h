@@ -189,6 +189,11 @@ typedef struct {
                                    When given, it replaces state / target_id / t (which must be NULL): the step
                                    reads and writes the env state in the resident block; the per-env results
                                    reward / terminated / truncated are produced as usual */
+  uint32_t* packed_out;         /* [E] or NULL (N <= 30, row-format state): per env one word = state bits [N-1:0] of
+                                   args->state after the step (after the auto-reset, if enabled) | terminated << 30 |
+                                   truncated << 31, written by the step kernel itself.  May be a device pointer to
+                                   mapped page-locked HOST memory: the results then cross PCIe as posted writes of
+                                   the step kernel, no export pass follows (pbn_step_host's packed form) */
 } pbn_step_args;
 
 /* gym.make(...) construction: upload truth tables and constants, pick the kernel. */

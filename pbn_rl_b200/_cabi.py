@@ -98,6 +98,7 @@ class StepArgs(C.Structure):
         ("reserved", C.c_uint32),
         ("sel_planes", C.c_void_p),
         ("resident", C.c_void_p),
+        ("packed_out", C.c_void_p),
     ]
 
 

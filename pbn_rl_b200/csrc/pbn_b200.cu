@@ -562,6 +562,8 @@ static int step_common(pbn_handle* h, const pbn_step_args* a, void* stream_, boo
   if (!h || !a) return fail(PBN_ERR_INVALID, "null argument");
   if (a->n_envs < 0) return fail(PBN_ERR_INVALID, "n_envs=%lld", (long long)a->n_envs);
   if (a->n_envs == 0) return PBN_OK;
+  if (a->packed_out && (h->net.n_genes > 30 || a->resident || (reinterpret_cast<uintptr_t>(a->packed_out) & 15u)))
+    return fail(PBN_ERR_INVALID, "packed_out needs N <= 30, row-format state and a 16-byte aligned array");
   if (a->resident) {
     if (a->state || a->target_id || a->t || a->final_state || a->sel_planes)
       return fail(PBN_ERR_INVALID, "plane-resident step: state / target_id / t / final_state / sel_planes must be null (the block holds them)");
@@ -775,6 +777,9 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
       return fail(PBN_ERR_INVALID, "pbn_step_host: state32/done need page-locked host memory for every output");
     }
   }
+  // only the packed word is wanted: the step kernel writes it straight into the mapped host buffer (no export pass)
+  const bool fused_packed = zc_packed && !io->state && !io->reward && !io->terminated && !io->truncated && !io->state32 && !io->done &&
+                            (reinterpret_cast<uintptr_t>(zc_packed) & 15u) == 0;
   const int64_t E = a->n_envs, tiles = (E + 1023) / 1024;
   int64_t nc = io->n_chunks > 0 ? io->n_chunks : (E >= (1 << 18) ? 2 : 1);  // measured best on B200 / PCIe Gen5 (scripts/host_path_probe.py)
   if (nc > pbn_handle::kMaxChunks) nc = pbn_handle::kMaxChunks;
@@ -814,8 +819,10 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
     s.n_envs = n;
     // the chunks are one logical step: one counter value; PDL only orders kernels, which the event waits already do
     s.flags = (a->flags & ~PBN_STEP_PDL) | ((last && !(a->flags & PBN_STEP_PDL)) ? 0u : PBN_STEP_NO_COUNT);
+    if (fused_packed) s.packed_out = zc_packed + e0;   // the step kernel writes the results over PCIe itself
     const int rc = step_common(h, &s, stream_, false);
     if (rc != PBN_OK) return rc;
+    if (fused_packed) continue;
     PBN_CUDA(cudaEventRecord(h->ev_k[c], stream));
     PBN_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_k[c], 0));
     if (zero_copy) {
@@ -848,6 +855,11 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
     if (io->reward) PBN_CUDA(cudaMemcpyAsync(io->reward + e0, a->reward + e0, (size_t)n * 4, cudaMemcpyDeviceToHost, h->s_d2h));
     if (io->terminated) PBN_CUDA(cudaMemcpyAsync(io->terminated + e0, a->terminated + e0, (size_t)n, cudaMemcpyDeviceToHost, h->s_d2h));
     if (io->truncated) PBN_CUDA(cudaMemcpyAsync(io->truncated + e0, a->truncated + e0, (size_t)n, cudaMemcpyDeviceToHost, h->s_d2h));
+  }
+  if (fused_packed) {
+    PBN_CUDA(cudaEventRecord(h->ev_k[0], stream));
+    PBN_CUDA(cudaEventSynchronize(h->ev_k[0]));
+    return PBN_OK;
   }
   PBN_CUDA(cudaStreamSynchronize(h->s_d2h));
   return PBN_OK;

@@ -712,6 +712,10 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
         for (int q = 0; q < 2 * kW64; ++q)
           fp[q] = make_ulonglong2(y[(2 * q) / kW64][(2 * q) % kW64], y[(2 * q + 1) / kW64][(2 * q + 1) % kW64]);
       }
+      if (a.packed_out != nullptr)   // (kW64 == 1: the host admits N <= 30 only)
+        *reinterpret_cast<uint4*>(a.packed_out + e) =
+            make_uint4((uint32_t)y[0][0] | ((hbits & 1u) << 30) | ((tbits & 1u) << 31), (uint32_t)y[1][0] | (((hbits >> 1) & 1u) << 30) | (((tbits >> 1) & 1u) << 31),
+                       (uint32_t)y[2][0] | (((hbits >> 2) & 1u) << 30) | (((tbits >> 2) & 1u) << 31), (uint32_t)y[3][0] | (((hbits >> 3) & 1u) << 30) | (((tbits >> 3) & 1u) << 31));
       if (a.reward != nullptr) *reinterpret_cast<float4*>(a.reward + e) = make_float4(rw[0], rw[1], rw[2], rw[3]);
       if (a.terminated != nullptr) *reinterpret_cast<uint32_t*>(a.terminated + e) = hbytes;
       if (a.truncated != nullptr) *reinterpret_cast<uint32_t*>(a.truncated + e) = tbytes;
@@ -727,6 +731,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
           a.state[(e + c) * kW64 + wd] = y[c][wd];
           if (a.final_state != nullptr) a.final_state[(e + c) * kW64 + wd] = y[c][wd];
         }
+        if (a.packed_out != nullptr) a.packed_out[e + c] = (uint32_t)y[c][0] | (((hbits >> c) & 1u) << 30) | (((tbits >> c) & 1u) << 31);
         if (a.reward != nullptr) a.reward[e + c] = rw[c];
         if (a.terminated != nullptr) a.terminated[e + c] = (uint8_t)((hbits >> c) & 1u);
         if (a.truncated != nullptr) a.truncated[e + c] = (uint8_t)((tbits >> c) & 1u);
@@ -749,7 +754,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     }
   }
   if (a.flags & PBN_STEP_AUTORESET) {
-    auto do_reset = [&](int64_t env, const Philox4& r) {
+    auto do_reset = [&](int64_t env, const Philox4& r, uint32_t flag_bits) {
       uint64_t s[kW64];
       int src, tgt;
       if (attr_in_smem) {
@@ -768,6 +773,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       a.target_id[env] = tgt;
       if (a.source_id != nullptr) a.source_id[env] = src;
       a.t[env] = 0;
+      if (a.packed_out != nullptr) a.packed_out[env] = (uint32_t)s[0] | flag_bits;   // the state after the reset, the flags of the step
     };
     // The finished envs of the warp (about 13 of its 256 per step) are dealt out over its lanes, one per lane and
     // trip: a single Philox pass instead of a per-lane serial loop that runs for as long as the unluckiest lane.
@@ -792,13 +798,14 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       L = min(L, 31u);
       const uint32_t eL = __shfl_sync(0xFFFFFFFFu, excl, (int)L);
       const uint32_t DL = __shfl_sync(0xFFFFFFFFu, D, (int)L);
+      const uint32_t HL = __shfl_sync(0xFFFFFFFFu, H, (int)L);
       if (j < total) {
         uint32_t m = DL;
         for (uint32_t k = j - eL; k != 0u; --k) m &= m - 1u;   // drop the k lowest finished envs of the owner
         const int i = __ffs(m) - 1;
         const int64_t env = tile * 1024 + 4 * (int64_t)L + 128 * (2 * (int)w + (i >> 2)) + (i & 3);
         const Philox4 r = philox_stream_rk((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.rk);
-        do_reset(env, r);
+        do_reset(env, r, ((HL >> i) & 1u) ? (1u << 30) : (1u << 31));
       }
     }
   }

@@ -23,7 +23,12 @@ E = 1 << 20
 env = VecPBNEnv(net, E, attrs, device=dev, auto_reset=True, **ENV_KW)
 env.reset()
 pa = env.pinned_actions(); pa.random_(0, 29)
-for compact in (False, True):
-    for ch in (1, 2, 4, 8):
-        t = timeit(lambda: env.step_host(pa, chunks=ch, compact=compact))
-        print("step_host compact=%d chunks=%2d: %.3f ms  %.3e env-steps/s" % (compact, ch, t * 1e3, E / t))
+import numpy as np
+a16 = env.pinned_actions16(); a16.numpy().view(np.uint16)[...] = env.pack_actions16(pa.numpy())
+for compact in (False, True, "packed"):
+    for ch in (1, 2, 3, 4, 6, 8):
+        if compact == "packed":
+            t = timeit(lambda: env.step_host(None, chunks=ch, compact="packed", actions16=a16))
+        else:
+            t = timeit(lambda: env.step_host(pa, chunks=ch, compact=compact))
+        print("step_host compact=%s chunks=%2d: %.3f ms  %.3e env-steps/s" % (compact, ch, t * 1e3, E / t))

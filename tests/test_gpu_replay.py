@@ -107,3 +107,41 @@ def test_insitu_bdq_loop_runs():
     out = mod.run("pbn28", envs=4096, iters=4, warmup=1, batch=64)
     assert out["value"] > 0 and out["episodes"] > 0 and np.isfinite(out["loss_last"])
     assert out["kernel"] == "sliced" and out["env_launches"] >= 5 * 3
+
+
+def test_device_ring_reproduces_reference_memory_fixture():
+    """The scripted store / overwrite / sample sequence of tests/golden/replay_expected.json (produced by running the
+    reference's ExperienceReplay and update_policy tensor code) through pbn_replay_observe / commit / sample."""
+    import ctypes as C
+    import json
+    from pathlib import Path
+
+    import torch
+    from pbn_rl_b200 import AttractorSet, PBNNetwork, VecPBNEnv, _cabi
+    from pbn_rl_b200.replay import DeviceReplay
+    fx = json.loads((Path(__file__).resolve().parent / "golden" / "replay_expected.json").read_text())
+    n, cap = fx["n"], fx["capacity"]
+    net = PBNNetwork.from_expressions(["g%d" % i for i in range(n)], [["g%d" % i] for i in range(n)])
+    targets = sorted({tuple(t["target"]) for t in fx["script"]})
+    attrs = AttractorSet([[t] for t in targets], n)
+    env = VecPBNEnv(net, 1, attrs, device="cuda:0", horizon=0, bins=fx["bins"])
+    ring = DeviceReplay(env, cap)
+    bits = lambda v: sum(int(b) << i for i, b in enumerate(v))
+    lib, dev = env.lib, env.device
+    for t in fx["script"]:      # one transition per store, exactly like memory.store(Transition(...))
+        env.set_state(torch.tensor([[bits(t["state"])]], dtype=torch.int64), packed=True)
+        env.set_target(targets.index(tuple(t["target"])))
+        ring.observe()
+        env.reward.fill_(t["reward"])
+        env.terminated.fill_(1 if t["done"] else 0)
+        env.truncated.fill_(0)
+        nxt = torch.tensor([[bits(t["next_state"])]], dtype=torch.int64, device=dev)
+        ring.commit(torch.tensor([t["action"]], dtype=torch.uint8, device=dev), nxt)
+    assert len(ring) == fx["len"] and ring.head == fx["current_index"]
+    for smp in fx["samples"]:
+        got = ring.sample(smp["batch"], index=torch.tensor(smp["index"]))
+        assert got["obs"][0].cpu().tolist() == smp["states"] and got["obs"][1].cpu().tolist() == smp["targets"]
+        assert got["next_obs"][0].cpu().tolist() == smp["next_states"] and got["next_obs"][1].cpu().tolist() == smp["targets"]
+        assert got["actions"].cpu().tolist() == smp["actions"] and list(got["actions"].shape) == smp["actions_shape"]
+        assert got["reward"].cpu().tolist() == smp["rewards"] and got["done"].cpu().tolist() == smp["masks"]
+    env.close()
