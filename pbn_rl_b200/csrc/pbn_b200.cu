@@ -777,10 +777,62 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
       return fail(PBN_ERR_INVALID, "pbn_step_host: state32/done need page-locked host memory for every output");
     }
   }
-  // only the packed word is wanted: the step kernel writes it straight into the mapped host buffer (no export pass)
-  const bool fused_packed = zc_packed && !io->state && !io->reward && !io->terminated && !io->truncated && !io->state32 && !io->done &&
-                            (reinterpret_cast<uintptr_t>(zc_packed) & 15u) == 0;
+  // only the packed word is wanted.  (Measured: letting the step kernel write it straight into the mapped host buffer
+  // through args->packed_out -- 1024 CTAs posting 16-byte writes -- is slower over PCIe, 0.200 ms per 2^20 envs, than
+  // the 16-CTA export kernel, 0.176 ms: PBN_B200_FUSED_PACKED=1 keeps that form available for experiments.)
+  const bool packed_only = zc_packed && !io->state && !io->reward && !io->terminated && !io->truncated && !io->state32 && !io->done;
+  const bool fused_packed = packed_only && (reinterpret_cast<uintptr_t>(zc_packed) & 15u) == 0 && getenv("PBN_B200_FUSED_PACKED") != nullptr;
   const int64_t E = a->n_envs, tiles = (E + 1023) / 1024;
+  // Two-lane form of the packed path: each half of the batch runs copy -> unpack -> step -> export in order on its own
+  // library stream, so nothing inside a lane needs an event, and PCIe (full duplex) carries lane 1's upload under
+  // lane 0's results.  The lanes' step kernels run concurrently, so the launch-counting update of a device step
+  // counter is not available here (host counter, or PDL sequences that advance it explicitly).
+  if (packed_only && !fused_packed && io->actions16 && io->n_chunks <= 0 && E >= (1 << 18) &&
+      (a->step_ctr_dev == nullptr || (a->flags & PBN_STEP_PDL))) {
+    const int64_t half = ((tiles + 1) / 2) * 1024;
+    PBN_CUDA(cudaEventRecord(h->ev_entry, stream));
+    cudaStream_t lane[2] = {h->s_h2d, h->s_d2h};
+    for (int c = 0; c < 2; ++c) {
+      const int64_t e0 = c * half, n = (c == 0) ? (E < half ? E : half) : E - half;
+      if (n <= 0) continue;
+      cudaStream_t S = lane[c];
+      PBN_CUDA(cudaStreamWaitEvent(S, h->ev_entry, 0));
+      PBN_CUDA(cudaMemcpyAsync(io->actions16_dev + e0, io->actions16 + e0, (size_t)n * 2, cudaMemcpyHostToDevice, S));
+      unpack_actions16_kernel<<<grid_for(h, n / 4 + 1, 256, 4), 256, 0, S>>>(io->actions16_dev + e0, io->actions_dev + e0 * h->net.bins, n);
+      PBN_CUDA(cudaGetLastError());
+      pbn_step_args s = *a;
+      s.state = a->state + e0 * h->W;
+      s.actions = io->actions_dev + e0 * h->net.bins;
+      if (a->target_id) s.target_id = a->target_id + e0;
+      if (a->source_id) s.source_id = a->source_id + e0;
+      if (a->t) s.t = a->t + e0;
+      if (a->reward) s.reward = a->reward + e0;
+      s.terminated = a->terminated + e0;
+      s.truncated = a->truncated + e0;
+      if (a->final_state) s.final_state = a->final_state + e0 * h->W;
+      s.env_offset = a->env_offset + e0;
+      s.n_envs = n;
+      s.flags = (a->flags & ~PBN_STEP_PDL) | PBN_STEP_NO_COUNT;
+      const int rc = step_common(h, &s, S, false);
+      if (rc != PBN_OK) return rc;
+      ExportArgs x{};
+      x.state64 = a->state + e0;
+      x.term = a->terminated + e0;
+      x.trunc = a->truncated + e0;
+      x.packed = zc_packed + e0;
+      x.n_envs = n;
+      export_kernel<<<16, 256, 0, S>>>(x);
+      PBN_CUDA(cudaGetLastError());
+      h->launches += 2;
+      PBN_CUDA(cudaEventRecord(h->ev_k[c], S));
+      PBN_CUDA(cudaStreamWaitEvent(stream, h->ev_k[c], 0));   // later work on the caller's stream sees the step
+    }
+    g_last_advance = nullptr;
+    if (a->step_ctr_dev && !(a->flags & PBN_STEP_PDL)) return fail(PBN_ERR_INVALID, "unreachable");
+    PBN_CUDA(cudaEventSynchronize(h->ev_k[0]));
+    if (E > half) PBN_CUDA(cudaEventSynchronize(h->ev_k[1]));
+    return PBN_OK;
+  }
   int64_t nc = io->n_chunks > 0 ? io->n_chunks : (E >= (1 << 18) ? 2 : 1);  // measured best on B200 / PCIe Gen5 (scripts/host_path_probe.py)
   if (nc > pbn_handle::kMaxChunks) nc = pbn_handle::kMaxChunks;
   if (nc > tiles) nc = tiles;

@@ -745,12 +745,20 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   // ---- G. auto-reset of finished envs (sparse: scattered writes after the vector stores) ----------
   uint32_t D = (H | TR) & VALID;
   if (a.stats != nullptr) {
-    const uint32_t v[7] = {(uint32_t)__popc(VALID), (uint32_t)__popc(D), (uint32_t)__popc(H & VALID),
-                           (uint32_t)__popc(TR & VALID), len_sum, flips, npert};
-#pragma unroll
-    for (int q = 0; q < 7; ++q) {
-      const uint32_t x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
-      if (lane == 0u && x != 0u) atomicAdd(&s_stat[q], x);
+    // the per-thread counts are small (8 envs): two 16-bit fields per warp reduction
+    const uint32_t x0 = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(VALID) | ((uint32_t)__popc(H & VALID) << 16));
+    const uint32_t x1 = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(TR & VALID) | (npert << 16));
+    const uint32_t x2 = __reduce_add_sync(0xFFFFFFFFu, flips);
+    const uint32_t x3 = __reduce_add_sync(0xFFFFFFFFu, len_sum);
+    if (lane == 0u) {
+      const uint32_t te = x0 >> 16, tr = x1 & 0xFFFFu;
+      atomicAdd(&s_stat[PBN_STAT_STEPS], x0 & 0xFFFFu);
+      if (te + tr) atomicAdd(&s_stat[PBN_STAT_EPISODES], te + tr);
+      if (te) atomicAdd(&s_stat[PBN_STAT_TERMINATED], te);
+      if (tr) atomicAdd(&s_stat[PBN_STAT_TRUNCATED], tr);
+      if (x3) atomicAdd(&s_stat[PBN_STAT_EP_LEN_SUM], x3);
+      if (x2) atomicAdd(&s_stat[PBN_STAT_FLIPS], x2);
+      if (x1 >> 16) atomicAdd(&s_stat[PBN_STAT_PERTURBED], x1 >> 16);
     }
   }
   if (a.flags & PBN_STEP_AUTORESET) {

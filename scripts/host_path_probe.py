@@ -26,7 +26,7 @@ pa = env.pinned_actions(); pa.random_(0, 29)
 import numpy as np
 a16 = env.pinned_actions16(); a16.numpy().view(np.uint16)[...] = env.pack_actions16(pa.numpy())
 for compact in (False, True, "packed"):
-    for ch in (1, 2, 3, 4, 6, 8):
+    for ch in (0, 1, 2, 3, 4, 6, 8):
         if compact == "packed":
             t = timeit(lambda: env.step_host(None, chunks=ch, compact="packed", actions16=a16))
         else:

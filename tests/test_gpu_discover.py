@@ -177,7 +177,7 @@ def test_bench_runs_on_a_small_configuration():
     from pathlib import Path
     root = Path(__file__).resolve().parent.parent
     out = subprocess.run([sys.executable, str(root / "bench.py"), "--envs", "8192", "--batches", "2", "--steps", "10", "--warmup", "3",
-                          "--no-cpu-baseline", "--e2e-steps", "2"], capture_output=True, text=True, timeout=600, cwd=str(root))
+                          "--no-cpu-baseline", "--no-configs", "--strong", "--e2e-steps", "2"], capture_output=True, text=True, timeout=600, cwd=str(root))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -186,4 +186,5 @@ def test_bench_runs_on_a_small_configuration():
                 "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in d, key
     assert d["steps"] == 10 and d["gpu_launches"] == 10 and d["value"] > 0 and d["roofline"]["bound"] == "hbm"
-    assert d["e2e"]["h2d_bytes_per_step"] == 8192 * 3
+    assert d["e2e"]["h2d_bytes_per_step"] == 8192 * 2 and d["e2e"]["d2h_bytes_per_step"] == 8192 * 4   # packed host form
+    assert d["strong"]["total_envs"] == 8192 and d["strong"]["value"] > 0 and d["configs"] is None
