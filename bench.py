@@ -577,6 +577,15 @@ def run_extra_configs(args, device, stream, peak):
         e.close()
     out["rollout_pbn28"] = {"value": (1 << 20) / us * 1e6, "unit": UNIT, "us_per_update": us,
                             "note": "pbn_rollout: 64 uncontrolled updates per launch (env.step([]) x 64), p = 1e-3"}
+    # ---- target membership through the hash set: the headline workload with a 15th attractor of 8192 states
+    from pbn_rl_b200 import AttractorSet
+    rng = np.random.default_rng(8192)
+    big = {tuple(int(v) for v in rng.integers(0, 2, size=28)) for _ in range(8300)}
+    attrs_big = AttractorSet(list(attrs28.attractors) + [sorted(big)[:8192]], 28)
+    us_h = short_run(a28, net28, attrs_big, 640, 8) * 1e3
+    out["membership_hashset_pbn28"] = {"us_per_step": us_h, "value": (1 << 20) / us_h * 1e6, "unit": UNIT, "attractors": 15, "largest_attractor": 8192,
+                                       "note": "targets uniform over 14 single-state attractors + one 8192-state attractor: every env's target test "
+                                               "is one probe of the L2-resident hash set over the 8206 states (pbn_update_attractors)"}
     # ---- the headline workload with plane-resident env state (same random streams, bit-identical results)
     if not (args.resident or args.chain):
         try:

@@ -37,7 +37,9 @@
  *   5. hit        = target_id in [0, A) and s' matches an entry (care, value) of that attractor
  *   6. t'         = min(t + 1, 65535); terminated = hit;
  *      truncated  = !hit && horizon > 0 && t' >= horizon
- *   7. reward     = (r_step + r_action * popcount(flip)) + (hit ? r_success : 0)   [fp32, no FMA]
+ *   7. reward     = (r_step + r_action * popcount(flip)) + (hit ? r_success : wrong ? r_wrong : 0)   [fp32, no FMA]
+ *                   wrong = !hit and s' lies in an attractor other than the target (only evaluated when r_wrong != 0;
+ *                   upstream gym-PBN's "wrong attractor" penalty)
  *   8. with PBN_STEP_AUTORESET, envs with terminated|truncated are re-initialised as by
  *      pbn_reset (new source state / target / t = 0) after their outputs were written.
  *
@@ -159,6 +161,8 @@ typedef struct {
   const uint8_t* wide_inputs;       /* [n_wide*16] gene index feeding bit j of the truth-table index */
   const int32_t* wide_lut_offset;   /* [n_wide+1] offsets into wide_lut, in 64-bit words */
   const uint64_t* wide_lut;         /* truth tables: bit a of table v = wide_lut[off[v] + a/64] >> (a%64) */
+  float r_wrong;                    /* reward term for ending a step in an attractor that is not the target; 0 = none */
+  float reserved1;
 } pbn_net_desc;
 
 /* Arguments of one step over n_envs instances (device pointers). */
@@ -407,6 +411,10 @@ int pbn_closure_reach(pbn_handle* h, const uint64_t* list, int64_t count, uint8_
 int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void* stream);
 
 /* Introspection. */
+/* Slots of the hash set pbn_update_attractors built over the fully specified attractor states (tables with an
+ * attractor of more than 8 states: env.in_target / env.is_attracting_state become one probe sequence, model_tester.py:
+ * 602-616), 0 if the table is small enough for the scan. */
+int pbn_attractor_hash_slots(const pbn_handle* h);
 int pbn_kernel_kind(const pbn_handle* h);            /* PBN_KERNEL_SCALAR or PBN_KERNEL_SLICED */
 int pbn_words_per_state(const pbn_handle* h);        /* W */
 int pbn_launch_count(const pbn_handle* h, uint64_t* out); /* kernels launched through this handle */

@@ -250,10 +250,13 @@ def flip_mask_from_actions(actions: Sequence[int], n: int) -> int:
     return m
 
 
-def reward_f32(n_flips: int, hit: bool, r_success: float, r_step: float, r_action: float) -> np.float32:
-    """reward = (r_step + r_action * n_flips) + (r_success if hit else 0), each op rounded to fp32."""
+def reward_f32(n_flips: int, hit: bool, r_success: float, r_step: float, r_action: float, wrong: bool = False,
+               r_wrong: float = 0.0) -> np.float32:
+    """reward = (r_step + r_action * n_flips) + (r_success if hit else r_wrong if wrong else 0), each op rounded to
+    fp32.  `wrong`: the step ended in an attractor that is not the target (upstream gym-PBN's penalty)."""
     base = np.float32(r_step) + np.float32(r_action) * np.float32(n_flips)
-    return np.float32(base + (np.float32(r_success) if hit else np.float32(0.0)))
+    bonus = np.float32(r_success) if hit else (np.float32(r_wrong) if wrong else np.float32(0.0))
+    return np.float32(base + bonus)
 
 
 class OraclePBNEnv:
@@ -261,14 +264,14 @@ class OraclePBNEnv:
 
     def __init__(self, network: OracleNetwork, attractors, horizon: int = 20, perturb_p: float = 0.0,
                  perturb_mode="A", r_success: float = 5.0, r_step: float = 0.0, r_action: float = -1.0,
-                 seed: Optional[int] = None):
+                 seed: Optional[int] = None, r_wrong: float = 0.0):
         self.net = network
         self.n = network.n
         self.all_attractors = [list(map(tuple, a)) for a in attractors]
         self.horizon = int(horizon)
         self.p = float(perturb_p)
         self.mode = PERT_MODES[perturb_mode] if self.p > 0 else PERT_NONE
-        self.r_success, self.r_step, self.r_action = r_success, r_step, r_action
+        self.r_success, self.r_step, self.r_action, self.r_wrong = r_success, r_step, r_action, r_wrong
         self.rng = random.Random(seed)
         self.state = 0
         self.target_attractor_id = 0
@@ -324,7 +327,9 @@ class OraclePBNEnv:
         state = self.render()
         hit = self.in_target(state)
         truncated = (not hit) and self.horizon > 0 and self.n_steps >= self.horizon
-        reward = float(reward_f32(bin(flip).count("1"), hit, self.r_success, self.r_step, self.r_action))
+        wrong = (not hit) and self.r_wrong != 0 and any(
+            a != self.target_attractor_id and attractor_contains(at, state) for a, at in enumerate(self.all_attractors))
+        reward = float(reward_f32(bin(flip).count("1"), hit, self.r_success, self.r_step, self.r_action, wrong, self.r_wrong))
         return state, reward, bool(hit), bool(truncated), {}
 
     # -- extras the reference calls ------------------------------
@@ -425,7 +430,7 @@ def scalar_stream_perturbation(n: int, p: float, env_ids: np.ndarray, step_ctr: 
 
 
 def batched_step(net: OracleNetwork, tables, words, actions, target_id, t, *, horizon, mode, sel, pert,
-                 r_success, r_step, r_action):
+                 r_success, r_step, r_action, r_wrong=0.0):
     """One env step for E instances given sel[E,N] and pert[E,W] (injected or stream-drawn).
     Returns (next_words, t_next, reward, terminated, truncated).  Mirrors include/pbn_b200.h."""
     offs, care, val = tables
@@ -459,7 +464,20 @@ def batched_step(net: OracleNetwork, tables, words, actions, target_id, t, *, ho
     t_next = np.minimum(np.asarray(t, dtype=np.int64) + 1, 65535).astype(np.uint16)
     trunc = (~hit) & (horizon > 0) & (t_next >= horizon)
     base = np.float32(r_step) + np.float32(r_action) * nflips.astype(np.float32)
-    reward = (base + np.where(hit, np.float32(r_success), np.float32(0.0))).astype(np.float32)
+    bonus = np.where(hit, np.float32(r_success), np.float32(0.0)).astype(np.float32)
+    if r_wrong != 0.0:
+        # the step ended in an attractor that is not the target ("wrong attractor")
+        other = np.zeros(e, dtype=bool)
+        for a in range(n_attr):
+            m = (~hit) & (target_id != a)
+            if not m.any():
+                continue
+            h = np.zeros(int(m.sum()), dtype=bool)
+            for s in range(offs[a], offs[a + 1]):
+                h |= ((nxt[m] & care[s]) == val[s]).all(axis=1)
+            other[m] |= h
+        bonus = np.where(other, np.float32(r_wrong), bonus).astype(np.float32)
+    reward = (base + bonus).astype(np.float32)
     return nxt, t_next, reward, hit.astype(np.uint8), trunc.astype(np.uint8)
 
 

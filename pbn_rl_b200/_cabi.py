@@ -34,7 +34,7 @@ EXPORTS = (
     "pbn_observe", "pbn_in_target", "pbn_rollout_track", "pbn_rollout_reduce",
     "pbn_visit_count", "pbn_successor_sets", "pbn_closure_expand", "pbn_closure_reach",
     "pbn_predraw", "pbn_planes_words", "pbn_rollout",
-    "pbn_resident_words", "pbn_resident_import", "pbn_resident_export", "pbn_reward_table",
+    "pbn_resident_words", "pbn_resident_import", "pbn_resident_export", "pbn_reward_table", "pbn_attractor_hash_slots",
 )
 
 
@@ -73,6 +73,8 @@ class NetDesc(C.Structure):
         ("wide_inputs", C.c_void_p),
         ("wide_lut_offset", C.c_void_p),
         ("wide_lut", C.c_void_p),
+        ("r_wrong", C.c_float),
+        ("reserved1", C.c_float),
     ]
 
 
@@ -184,6 +186,8 @@ def load_library(path: Optional[os.PathLike] = None) -> C.CDLL:
     lib.pbn_predraw.restype = C.c_int
     lib.pbn_planes_words.argtypes = [vp, i64]
     lib.pbn_planes_words.restype = i64
+    lib.pbn_attractor_hash_slots.argtypes = [vp]
+    lib.pbn_attractor_hash_slots.restype = C.c_int
     lib.pbn_reward_table.argtypes = [vp, vp, i32]
     lib.pbn_reward_table.restype = C.c_int
     lib.pbn_resident_words.argtypes = [vp, i64]

@@ -8,13 +8,6 @@
 
 namespace pbn {
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
-  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-  x ^= x >> 27; x *= 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return x;
-}
-
 // Key of a state in the tags[] column: never 0 (empty slot) and never 1 (kTagBusy).
 //   W == 1, N <= 63: tag = 2*state + 1  -- injective: distinct states never share a slot.
 //   otherwise      : a 64-bit splitmix64 fingerprint; a tag match is confirmed by comparing the state words in

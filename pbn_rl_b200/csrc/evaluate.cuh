@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) in_target_kernel(const __grid_constant__ 
 #pragma unroll
     for (int w = 0; w < W; ++w) s[w] = state[e * W + w];
     const int a = target_id[e];
-    out[e] = (a >= 0 && a < n.n_attr && in_attractor<W>(n.attr_offset, n.attr_care, n.attr_val, a, s)) ? 1 : 0;
+    out[e] = (a >= 0 && a < n.n_attr && (n.ahash_tags != nullptr ? in_attractor_hashed<W>(n, a, s) : in_attractor<W>(n.attr_offset, n.attr_care, n.attr_val, a, s))) ? 1 : 0;
   }
 }
 

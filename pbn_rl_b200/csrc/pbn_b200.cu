@@ -1,5 +1,6 @@
 // C-ABI of libpbn_b200.so (include/pbn_b200.h): handle management, table upload, launches.
 // The only translation unit; kernels live in the .cuh files next to it.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -101,6 +102,13 @@ struct pbn_handle {
   uint64_t* d_attr_val = nullptr;
   uint32_t* d_pair_cum = nullptr;
   size_t cap_attr_offset = 0, cap_attr_care = 0, cap_attr_val = 0, cap_pair_cum = 0;
+  // hash set over the fully specified attractor states + CSR of the wildcard entries (large attractors)
+  unsigned long long* d_ahash_tags = nullptr;
+  uint64_t* d_ahash_state = nullptr;
+  int32_t* d_ahash_attr = nullptr;
+  int32_t* d_awild_offset = nullptr;
+  int32_t* d_awild_entry = nullptr;
+  size_t cap_ahash_tags = 0, cap_ahash_state = 0, cap_ahash_attr = 0, cap_awild_offset = 0, cap_awild_entry = 0;
   unsigned int* d_ticket = nullptr;
   uint32_t* d_surv_sliced = nullptr;
   WideDesc* d_wide = nullptr;
@@ -231,6 +239,7 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
 static int resident_supported(const pbn_handle* h) {
   if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state needs the sliced kernel");
   if (h->net.n_attr > 254) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: %d attractors > 254", h->net.n_attr);
+  if (h->net.r_wrong != 0.0f) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: the wrong-attractor reward term (r_wrong) needs the row-format kernels");
   if (h->net.n_attr > 0 && !h->net.attr_simple && h->net.n_attr_states > 256)
     return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: attractor table with %d (care, value) entries > 256 and several states per attractor", h->net.n_attr_states);
   return PBN_OK;
@@ -327,6 +336,11 @@ void pbn_destroy(pbn_handle* h) {
     cudaFree(h->d_attr_care);
     cudaFree(h->d_attr_val);
     cudaFree(h->d_pair_cum);
+    cudaFree(h->d_ahash_tags);
+    cudaFree(h->d_ahash_state);
+    cudaFree(h->d_ahash_attr);
+    cudaFree(h->d_awild_offset);
+    cudaFree(h->d_awild_entry);
     cudaFree(h->d_ticket);
     cudaFree(h->d_surv_sliced);
     cudaFree(h->d_wide);
@@ -488,6 +502,7 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
   n.pert_rng = d->perturb_p > 0.0f ? 1u : 0u;
   n.pert_inv_log2 = d->perturb_p > 0.0 ? (float)(1.0 / std::log2(1.0 - d->perturb_p)) : 0.0f;
   n.r_success = d->r_success;
+  n.r_wrong = d->r_wrong;
   n.r_step = d->r_step;
   n.r_action = d->r_action;
   n.k0 = (uint32_t)d->seed;
@@ -547,8 +562,70 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
       if (care[(size_t)e * h->W + w] != full) simple = false;
     }
   n.attr_simple = simple ? 1u : 0u;
+
+  // Hash set for tables with large attractors (an attractor of more than kHashMinStates states): membership becomes
+  // one probe sequence instead of a scan over the attractor (pbn70 has an 8192-state attractor; model_tester.py:602-616).
+  constexpr int kHashMinStates = 8;
+  int largest = 0;
+  for (int a = 0; a < A; ++a) largest = std::max(largest, attr_offset[a + 1] - attr_offset[a]);
+  n.ahash_tags = nullptr;
+  n.ahash_state = nullptr;
+  n.ahash_attr = nullptr;
+  n.awild_offset = nullptr;
+  n.awild_entry = nullptr;
+  n.ahash_mask = 0;
+  if (!simple && largest > kHashMinStates) {
+    const int W = h->W;
+    std::vector<int32_t> wild_off(A + 1, 0), wild_entry;
+    std::vector<int> exact;   // entry indices
+    for (int a = 0; a < A; ++a) {
+      for (int e = attr_offset[a]; e < attr_offset[a + 1]; ++e) {
+        bool full = true;
+        for (int w = 0; w < W; ++w) {
+          const int nbits = n.n_genes - 64 * w;
+          const uint64_t m = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1ull);
+          if (care[(size_t)e * W + w] != m) full = false;
+        }
+        if (full) exact.push_back(e); else wild_entry.push_back(e);
+      }
+      wild_off[a + 1] = (int32_t)wild_entry.size();
+    }
+    size_t cap = 64;
+    while (cap < 2 * exact.size() + 2) cap *= 2;
+    std::vector<unsigned long long> tags(cap, 0ull);
+    std::vector<uint64_t> states(cap * W, 0ull);
+    std::vector<int32_t> owner(cap, -1);
+    std::vector<int32_t> attr_of(S);
+    for (int a = 0; a < A; ++a)
+      for (int e = attr_offset[a]; e < attr_offset[a + 1]; ++e) attr_of[e] = a;
+    for (int e : exact) {
+      const uint64_t* st = value + (size_t)e * W;
+      const uint64_t tag = attr_tag(st, W);
+      size_t slot = (size_t)(mix64(tag) & (cap - 1));
+      while (tags[slot] != 0ull) slot = (slot + 1) & (cap - 1);
+      tags[slot] = tag;
+      for (int w = 0; w < W; ++w) states[slot * W + w] = st[w];
+      owner[slot] = attr_of[e];
+    }
+    if (wild_entry.empty()) wild_entry.push_back(0);   // never an empty upload
+    if ((rc = update_table(&h->d_ahash_tags, &h->cap_ahash_tags, tags.data(), tags.size(), stream)) != PBN_OK ||
+        (rc = update_table(&h->d_ahash_state, &h->cap_ahash_state, states.data(), states.size(), stream)) != PBN_OK ||
+        (rc = update_table(&h->d_ahash_attr, &h->cap_ahash_attr, owner.data(), owner.size(), stream)) != PBN_OK ||
+        (rc = update_table(&h->d_awild_offset, &h->cap_awild_offset, wild_off.data(), wild_off.size(), stream)) != PBN_OK ||
+        (rc = update_table(&h->d_awild_entry, &h->cap_awild_entry, wild_entry.data(), wild_entry.size(), stream)) != PBN_OK)
+      return rc;
+    // (pageable sources: cudaMemcpyAsync has staged them before it returned, the local vectors may go)
+    n.ahash_tags = h->d_ahash_tags;
+    n.ahash_state = h->d_ahash_state;
+    n.ahash_attr = h->d_ahash_attr;
+    n.awild_offset = h->d_awild_offset;
+    n.awild_entry = h->d_awild_entry;
+    n.ahash_mask = (uint32_t)(cap - 1);
+  }
   return PBN_OK;
 }
+
+int pbn_attractor_hash_slots(const pbn_handle* h) { return h ? (h->net.ahash_tags ? (int)h->net.ahash_mask + 1 : 0) : PBN_ERR_INVALID; }
 
 static int grid_for(const pbn_handle* h, int64_t n, int block, int per_sm) {
   int64_t g = (n + block - 1) / block;
@@ -922,6 +999,7 @@ int pbn_reward_table(const pbn_handle* h, float* out, int32_t n) {
   if (!h || !out) return fail(PBN_ERR_INVALID, "null argument");
   const int bins = h->net.bins;
   if (n < 2 * (bins + 1)) return fail(PBN_ERR_INVALID, "reward table has %d entries, buffer holds %d", 2 * (bins + 1), n);
+  if (h->net.r_wrong != 0.0f) return fail(PBN_ERR_UNSUPPORTED, "with r_wrong != 0 the reward is not a function of (flips, terminated)");
   for (int hit = 0; hit < 2; ++hit)
     for (int nf = 0; nf <= bins; ++nf) {
       volatile float base = h->net.r_action * (float)nf;   // two separately rounded fp32 operations, as on the device

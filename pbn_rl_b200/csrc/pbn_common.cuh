@@ -51,6 +51,15 @@ struct NetParams {
   float pert_inv_log2;           // 1 / log2(1 - perturb_p) (negative): first guess of the geometric skip
   const WideDesc* wide;          // [n_wide] or nullptr
   const uint64_t* wide_lut;      // multi-word truth tables of the wide predictors
+  // Hash set over the fully specified attractor states (built by pbn_update_attractors for tables with large
+  // attractors): open addressing, linear probing, key = the state, payload = its attractor.  nullptr: not built.
+  const unsigned long long* ahash_tags;   // [mask + 1] fingerprint of the slot's state, 0 = empty
+  const uint64_t* ahash_state;            // [(mask + 1) * W]
+  const int32_t* ahash_attr;              // [mask + 1]
+  const int32_t* awild_offset;            // [A + 1] CSR over the entries with wildcards ('*'), by attractor
+  const int32_t* awild_entry;             // entry indices into attr_care / attr_val
+  uint32_t ahash_mask;
+  float r_wrong;                          // reward term for ending a step in a non-target attractor (0: not evaluated)
 };
 
 // Value of a wide predictor in state s (gather up to 16 state bits, look the bit up in global memory / L1).
@@ -187,6 +196,80 @@ __device__ __forceinline__ void reset_draw(const NetParams& n, const Philox4& r,
   for (int w = 0; w < W; ++w) s[w] = n.attr_val[(size_t)j * W + w];
 }
 
+// splitmix64 finaliser; shared by the attractor hash set and the visit-count table (discover.cuh)
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+
+// Fingerprint of a state in the attractor hash set: never 0 (an empty slot).  The host builds the table with the
+// same function (pbn_update_attractors).
+__host__ __device__ __forceinline__ uint64_t attr_tag(const uint64_t* s, int W) {
+  uint64_t h = mix64(s[0] + 0x9E3779B97F4A7C15ull);
+  if (W == 2) h = mix64(h ^ (s[1] + 0xD1B54A32D192ED03ull));
+  return h == 0ull ? 1ull : h;
+}
+
+// env.in_target(state) through the hash set: is `s` a state of attractor `a`?  O(1) expected: one probe sequence over
+// the fully specified states (tag match confirmed on the state words and the attractor id) + the attractor's few
+// wildcard entries.  model_tester.py:602-616; bdq_model/__init__.py:182-184 (attractor sets that grow).
+template <int W>
+__device__ __forceinline__ bool in_attractor_hashed(const NetParams& n, int a, const uint64_t (&s)[W]) {
+  const uint64_t tag = attr_tag(s, W);
+  uint32_t slot = (uint32_t)mix64(tag) & n.ahash_mask;
+  for (uint32_t probe = 0; probe <= n.ahash_mask; ++probe, slot = (slot + 1u) & n.ahash_mask) {
+    const unsigned long long cur = n.ahash_tags[slot];
+    if (cur == 0ull) break;
+    if (cur == tag && n.ahash_attr[slot] == a) {
+      bool same = true;
+#pragma unroll
+      for (int w = 0; w < W; ++w) same = same && n.ahash_state[(size_t)slot * W + w] == s[w];
+      if (same) return true;
+    }
+  }
+  for (int k = n.awild_offset[a]; k < n.awild_offset[a + 1]; ++k) {
+    const int e = n.awild_entry[k];
+    bool m = true;
+#pragma unroll
+    for (int w = 0; w < W; ++w) m = m && ((s[w] & n.attr_care[(size_t)e * W + w]) == n.attr_val[(size_t)e * W + w]);
+    if (m) return true;
+  }
+  return false;
+}
+
+// env.state_attractor_id through the hash set: the first (lowest-numbered) attractor containing `s`, or -1.
+template <int W>
+__device__ __forceinline__ int attractor_of_hashed(const NetParams& n, const uint64_t (&s)[W]) {
+  int best = n.n_attr;
+  const uint64_t tag = attr_tag(s, W);
+  uint32_t slot = (uint32_t)mix64(tag) & n.ahash_mask;
+  for (uint32_t probe = 0; probe <= n.ahash_mask; ++probe, slot = (slot + 1u) & n.ahash_mask) {
+    const unsigned long long cur = n.ahash_tags[slot];
+    if (cur == 0ull) break;
+    if (cur == tag && n.ahash_attr[slot] < best) {
+      bool same = true;
+#pragma unroll
+      for (int w = 0; w < W; ++w) same = same && n.ahash_state[(size_t)slot * W + w] == s[w];
+      if (same) best = n.ahash_attr[slot];
+    }
+  }
+  for (int a = 0; a < best; ++a)
+    for (int k = n.awild_offset[a]; k < n.awild_offset[a + 1]; ++k) {
+      const int e = n.awild_entry[k];
+      bool m = true;
+#pragma unroll
+      for (int w = 0; w < W; ++w) m = m && ((s[w] & n.attr_care[(size_t)e * W + w]) == n.attr_val[(size_t)e * W + w]);
+      if (m) { best = a; break; }
+    }
+  return best < n.n_attr ? best : -1;
+}
+
+// "wrong attractor" test of the reward (r_wrong != 0): s lies in some attractor other than `target`
+template <int W>
+__device__ __forceinline__ bool in_other_attractor(const NetParams& n, int target, const uint64_t (&s)[W]);
+
 template <int W>
 __device__ __forceinline__ bool in_attractor(const int32_t* offs, const uint64_t* care, const uint64_t* val,
                                              int a, const uint64_t (&s)[W]) {
@@ -199,6 +282,17 @@ __device__ __forceinline__ bool in_attractor(const int32_t* offs, const uint64_t
     hit = hit || m;
   }
   return hit;
+}
+
+template <int W>
+__device__ __forceinline__ bool in_other_attractor(const NetParams& n, int target, const uint64_t (&s)[W]) {
+  if (n.ahash_tags != nullptr) {
+    const int a = attractor_of_hashed<W>(n, s);   // the lowest-numbered attractor holding s; a state of the target is a hit, not a miss
+    return a >= 0 && a != target;
+  }
+  for (int a = 0; a < n.n_attr; ++a)
+    if (a != target && in_attractor<W>(n.attr_offset, n.attr_care, n.attr_val, a, s)) return true;
+  return false;
 }
 
 }  // namespace pbn

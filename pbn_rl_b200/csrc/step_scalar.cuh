@@ -206,13 +206,15 @@ __global__ void __launch_bounds__(256) step_scalar_kernel(const __grid_constant_
     int tgt = -1;
     if (a.target_id != nullptr) {
       tgt = a.target_id[e];
-      if (tgt >= 0 && tgt < n.n_attr) hit = in_attractor<W>(aoffs, acare, aval, tgt, nx);
+      if (tgt >= 0 && tgt < n.n_attr) hit = n.ahash_tags != nullptr ? in_attractor_hashed<W>(n, tgt, nx) : in_attractor<W>(aoffs, acare, aval, tgt, nx);
     }
     uint32_t tt = a.t != nullptr ? a.t[e] : 0u;
     tt = tt < 65535u ? tt + 1u : 65535u;
     const bool trunc = !hit && n.horizon > 0 && tt >= (uint32_t)n.horizon;
     const float base = __fadd_rn(n.r_step, __fmul_rn(n.r_action, (float)nflips));
-    const float rew = __fadd_rn(base, hit ? n.r_success : 0.0f);
+    float bonus = hit ? n.r_success : 0.0f;
+    if (!hit && n.r_wrong != 0.0f && n.n_attr > 0 && in_other_attractor<W>(n, tgt, nx)) bonus = n.r_wrong;
+    const float rew = __fadd_rn(base, bonus);
     if (a.reward != nullptr) a.reward[e] = rew;
     if (a.terminated != nullptr) a.terminated[e] = hit ? 1 : 0;
     if (a.truncated != nullptr) a.truncated[e] = trunc ? 1 : 0;
@@ -422,8 +424,12 @@ __global__ void __launch_bounds__(256) attractor_id_kernel(const __grid_constant
 #pragma unroll
     for (int w = 0; w < W; ++w) s[w] = state[e * W + w];
     int found = -1;
-    for (int a = 0; a < n.n_attr && found < 0; ++a)
-      if (in_attractor<W>(n.attr_offset, n.attr_care, n.attr_val, a, s)) found = a;
+    if (n.ahash_tags != nullptr) {
+      found = attractor_of_hashed<W>(n, s);
+    } else {
+      for (int a = 0; a < n.n_attr && found < 0; ++a)
+        if (in_attractor<W>(n.attr_offset, n.attr_care, n.attr_val, a, s)) found = a;
+    }
     attr_id[e] = found;
   }
 }

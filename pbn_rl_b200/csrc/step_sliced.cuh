@@ -642,6 +642,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   const uint32_t n_attr = (a.target_id != nullptr) ? (uint32_t)n.n_attr : 0u;
   const uint32_t horizon = n.horizon > 0 ? (uint32_t)n.horizon : 0xFFFFFFFFu;
   const bool simple = n.attr_simple != 0u;  // block-uniform
+  const bool use_hash = !simple && n.ahash_tags != nullptr;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int64_t e = e0 + 128 * (2 * (int)w + g);
@@ -652,7 +653,14 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       const int i = 4 * g + c;
       bool hit = false;
       if (tg[i] < n_attr) {  // unsigned compare: negative ids never match
-        if (attr_in_smem && simple) {
+        if (use_hash) {
+          // large attractors: O(1) through the hash set over their states (L2-resident) instead of a scan
+          uint64_t y64[kW64];
+#pragma unroll
+          for (int wd = 0; wd < kW64; ++wd)
+            y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
+          hit = in_attractor_hashed<kW64>(n, (int)tg[i], y64);
+        } else if (attr_in_smem && simple) {
           // one fully specified state per attractor: entry index == attractor id
           const uint32_t* ent = s_aent + tg[i] * (2 * kNW) + kNW;
           uint32_t diff = 0u;
@@ -682,6 +690,13 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       const bool trunc = !hit && t1 >= horizon;
       const uint32_t nf = (nfp >> (4 * i)) & 0xFu;
       rw[c] = s_rew[nf + (hit ? 9u : 0u)];
+      if (!hit && n.r_wrong != 0.0f && n_attr != 0u) {   // "wrong attractor" term (rare configuration: row-domain scan / hash)
+        uint64_t y64[kW64];
+#pragma unroll
+        for (int wd = 0; wd < kW64; ++wd)
+          y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
+        if (in_other_attractor<kW64>(n, (int)tg[i], y64)) rw[c] = __fadd_rn(s_rew[nf], n.r_wrong);
+      }
       const bool valid = FULL || (e + c < E);
       hbits |= (hit && valid ? 1u : 0u) << c;
       tbits |= (trunc && valid ? 1u : 0u) << c;

@@ -164,7 +164,7 @@ class PBNEnv:
                  N: Optional[int] = None, genes: Optional[Sequence[str]] = None, logic_functions=None,
                  horizon: int = 20, min_attractors: Optional[int] = None, device="cuda:0",
                  seed: Optional[int] = None, perturb_p: float = 0.0, perturb_mode: str = "A",
-                 r_success: float = 5.0, r_step: float = 0.0, r_action: float = -1.0, num_envs: int = 1,
+                 r_success: float = 5.0, r_step: float = 0.0, r_action: float = -1.0, r_wrong: float = 0.0, num_envs: int = 1,
                  kernel: str = "auto", name: str = ""):
         from .vec_env import VecPBNEnv  # needs torch + the CUDA extension; no CPU fallback
 
@@ -192,7 +192,7 @@ class PBNEnv:
         self._seed = 0x5EED if seed is None else int(seed)
         self.vec = VecPBNEnv(network, num_envs, attractors, device=device, seed=self._seed, horizon=horizon,
                              bins=MAX_ACTIONS, perturb_p=perturb_p, perturb_mode=perturb_mode,
-                             r_success=r_success, r_step=r_step, r_action=r_action, kernel=kernel)
+                             r_success=r_success, r_step=r_step, r_action=r_action, r_wrong=r_wrong, kernel=kernel)
         self._attractors = attractors
         self.observation_space = Box(0, 1, (self.N,), np.int8)
         self.action_space = Discrete(self.N + 1, seed)

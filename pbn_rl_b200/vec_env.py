@@ -45,7 +45,7 @@ def pair_thresholds(weights: np.ndarray) -> np.ndarray:
 
 def make_desc(network: PBNNetwork, bins: int = 3, horizon: int = 20, perturb_p: float = 0.0,
               perturb_mode: str = "A", r_success: float = 5.0, r_step: float = 0.0, r_action: float = -1.0,
-              seed: int = 0x5EED, device: int = 0, kernel: str = "auto"):
+              seed: int = 0x5EED, device: int = 0, kernel: str = "auto", r_wrong: float = 0.0):
     """Fill a ``pbn_net_desc`` for ``network``; returns ``(desc, keepalive)`` -- the host arrays the
     descriptor points into must outlive the C call."""
     arr = network.descriptor_arrays()
@@ -63,6 +63,7 @@ def make_desc(network: PBNNetwork, bins: int = 3, horizon: int = 20, perturb_p: 
     d.perturb_mode = _cabi.PERT_MODES[perturb_mode]
     d.perturb_p = float(perturb_p)
     d.r_success, d.r_step, d.r_action = float(r_success), float(r_step), float(r_action)
+    d.r_wrong = float(r_wrong)
     d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     d.device = int(device)
     d.kernel = _cabi.KERNEL_KINDS[kernel]
@@ -147,7 +148,9 @@ class VecPBNEnv:
     Parameters mirror the reference's ``gym.make`` kwargs where they exist (``horizon``,
     train_BDQ.py:50) and expose every constant the reference tree does not pin:
     ``perturb_p`` / ``perturb_mode`` (A: Shmulevich, a perturbed step skips the update; B:
-    update then flip; C: per-gene), the reward constants and the Philox ``seed``.
+    update then flip; C: per-gene), the reward constants (``r_success`` on reaching the target, ``r_step`` per
+    step, ``r_action`` per flipped gene, ``r_wrong`` for ending a step in an attractor that is not the target --
+    upstream gym-PBN's shape is +5 / -1 per action / -2) and the Philox ``seed``.
     ``env_offset`` is the global id of env 0 (a multiple of 1024): shards of one logical batch
     on several GPUs draw exactly the randomness the single-GPU batch would.
     ``device_counter=True`` keeps the Philox step counter in device memory (incremented by each
@@ -173,7 +176,8 @@ class VecPBNEnv:
                  bins: int = 3, perturb_p: float = 0.0, perturb_mode: str = "A", r_success: float = 5.0,
                  r_step: float = 0.0, r_action: float = -1.0, kernel: str = "auto", env_offset: int = 0,
                  auto_reset: bool = False, pair_weights: Optional[np.ndarray] = None,
-                 device_counter: bool = False, pdl: bool = False, resident: bool = False, chain: bool = False):
+                 device_counter: bool = False, pdl: bool = False, resident: bool = False, chain: bool = False,
+                 r_wrong: float = 0.0):
         self._h = None
         self.lib = _cabi.lib()  # raises if the CUDA extension is not built: no fallback
         if not torch.cuda.is_available():
@@ -198,7 +202,8 @@ class VecPBNEnv:
 
         d, self._keep = make_desc(network, bins=self.bins, horizon=self.horizon, perturb_p=self.perturb_p,
                                   perturb_mode=perturb_mode, r_success=r_success, r_step=r_step,
-                                  r_action=r_action, seed=self.seed, device=self.device.index, kernel=kernel)
+                                  r_action=r_action, seed=self.seed, device=self.device.index, kernel=kernel,
+                                  r_wrong=r_wrong)
         h = C.c_void_p()
         check(self.lib.pbn_create(C.byref(d), C.byref(h)))
         self._h = h

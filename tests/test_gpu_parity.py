@@ -312,3 +312,36 @@ def test_perturbation_stream_extremes(name, e, p):
         total += int(sum(bin(int(x)).count("1") for x in pert.reshape(-1)))
     assert total > 0, "no perturbation event in the sample: test is vacuous"
     assert env.stats()["perturbed"] == total
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", ["pbn10", "pbn7", "pbn28"])
+def test_wrong_attractor_reward_term(name, kernel):
+    """r_wrong (upstream's "-2 wrong attractor"): envs that end a step in an attractor other than their
+    target get r_wrong instead of r_success -- rewards bit-exact against the oracle, both kernels."""
+    import torch
+    e = 4096
+    case = random_case(name, e, seed=77)
+    attrs = attractor_set(name)
+    # start a third of the envs inside attractors so that hits and wrong-attractor endings both occur
+    rng = np.random.default_rng(1)
+    flat = [s for a in attrs.attractors for s in a]
+    for k in range(0, e, 3):
+        s = flat[int(rng.integers(0, len(flat)))]
+        case["state"][k, :] = 0
+        for i, b in enumerate(s):
+            if b != "*" and int(b):
+                case["state"][k, i >> 6] |= np.uint64(1) << np.uint64(i & 63)
+    case["actions"][::2] = 0
+    env = _env(name, e, mode="none", kernel=kernel, r_wrong=-2.0)
+    _load(env, case)
+    env.step_injected(torch.from_numpy(case["actions"]), torch.from_numpy(case["sel"]))
+    from oracle import pbn_oracle as O
+    onet = oracle_net(name)
+    tables = O.attractor_tables(attrs.attractors, onet.n)
+    exp = O.batched_step(onet, tables, case["state"], case["actions"], case["target"], case["t"], mode=0, sel=case["sel"],
+                         pert=np.zeros_like(case["pert"]), r_wrong=-2.0, **KW)
+    plain = O.batched_step(onet, tables, case["state"], case["actions"], case["target"], case["t"], mode=0, sel=case["sel"],
+                           pert=np.zeros_like(case["pert"]), **KW)
+    assert (exp[2] != plain[2]).sum() > 10          # the term fires
+    _compare(env, exp, f"{name}/{kernel}/r_wrong")
