@@ -584,7 +584,29 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
     slot_gene = [i for i, k in enumerate(ks) if k > 1]
     # SELECT: slot r (the r-th gene with K > 1) owns block (SELECT, r) = words x, y, z, w.  K=2: s0 = x; K=4: (s0, s1) =
     # (x, y); K=3: the pairs (x, y), (z, w) -- pair value 3 is rejected and replaced by the next pair.
+    weighted = {}
+    for i, k in enumerate(ks):
+        thr = selection_thresholds(net.probs[i])[:-1]
+        weighted[i] = any(abs(t - int(np.floor((j + 1) / k * 4294967296.0 + 0.5))) > 2 for j, t in enumerate(thr))
     for r, i in enumerate(slot_gene):
+        if weighted[i]:
+            # arbitrary probabilities: a 32-bit uniform per env, bit 31 - j of the column's envs = word j of the blocks
+            # (SELECT, 128 + 8 r + i'), compared with the 32-bit thresholds: sel = #{k : cum[k] <= u}
+            u32 = [np.zeros(ng, dtype=np.uint64) for _ in range(32)]   # per bit position b: the env's u
+            for blk in range(8):
+                words = philox4x32(*_ctr(groups, step_ctr, KIND_SELECT, 128 + 8 * r + blk), k0, k1)
+                for j in range(4):
+                    plane = words[j].astype(np.uint64)
+                    for b in range(32):
+                        u32[b] |= ((plane >> np.uint64(b)) & np.uint64(1)) << np.uint64(31 - (4 * blk + j))
+            thr = selection_thresholds(net.probs[i])[:-1]
+            for b in range(32):
+                sel_b = np.zeros(ng, dtype=np.uint64)
+                for t in thr:
+                    sel_b += (u32[b] >= np.uint64(t)).astype(np.uint64)
+                s0[:, i] |= (sel_b & np.uint64(1)) << np.uint64(b)
+                s1[:, i] |= ((sel_b >> np.uint64(1)) & np.uint64(1)) << np.uint64(b)
+            continue
         x, y, z, w = (v.astype(np.uint64) for v in philox4x32(*_ctr(groups, step_ctr, KIND_SELECT, r), k0, k1))
         if ks[i] == 2:
             s0[:, i] = x
@@ -601,7 +623,7 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
     # earlier slot of the group has claimed bit b of this plane.  Blocks are consumed until no slot of the group is
     # at 3 anywhere in the column (columns that are done ignore further blocks).
     for q in range(4):
-        slots_q = [i for r, i in enumerate(slot_gene) if r % 4 == q and ks[i] == 3]
+        slots_q = [i for r, i in enumerate(slot_gene) if r % 4 == q and ks[i] == 3 and not weighted[i]]
         if not slots_q:
             continue
         for it in range(1024):

@@ -64,4 +64,34 @@ __device__ __forceinline__ Philox4 philox_stream(uint64_t id, uint64_t step, uin
   return philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), (uint32_t)step, c3, k0, k1);
 }
 
+// Selection planes of a slot with arbitrary predictor probabilities (e.g. ASSA-format PBNs, train_assa_matlab_BQN.py:
+// 72-171): per env a 32-bit uniform u is compared with the gene's K-1 cumulative thresholds, sel = #{k : cum[k] <= u}
+// -- the same rule, with the same 32-bit thresholds, as the thread-per-env kernel.  Bit-sliced: u's bit 31 - j of the
+// column's 32 envs is plane j = word j of the slot's blocks (SELECT, 128 + 8 r + i), compared bit-serially from the
+// most significant bit; planes are drawn four at a time only while some env of the warp is still undecided against
+// some threshold (2^-j of them after j planes: four blocks in the typical case).  Returns lo + 2 hi = sel.
+__device__ __forceinline__ void draw_weighted(uint64_t gid, uint64_t step, const uint32_t (&rk)[20], uint32_t r, uint32_t K,
+                                              const uint32_t* cum, uint32_t& lo, uint32_t& hi) {
+  const uint32_t c0 = cum[0], c1 = cum[1], c2 = cum[2];
+  uint32_t eq0 = 0xFFFFFFFFu, eq1 = K > 2u ? 0xFFFFFFFFu : 0u, eq2 = K > 3u ? 0xFFFFFFFFu : 0u;   // still equal to the threshold
+  uint32_t lt0 = 0u, lt1 = K > 2u ? 0u : 0xFFFFFFFFu, lt2 = K > 3u ? 0u : 0xFFFFFFFFu;             // decided: u < threshold
+#pragma unroll 1
+  for (uint32_t i = 0; i < 8u; ++i) {
+    const Philox4 P = philox_stream_rk(gid, step, PBN_RNG_SELECT, 128u + 8u * r + i, rk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t u = j == 0 ? P.x : j == 1 ? P.y : j == 2 ? P.z : P.w;
+      const uint32_t sh = 4u * i + (uint32_t)j;
+      const uint32_t b0 = (uint32_t)((int32_t)(c0 << sh) >> 31), b1 = (uint32_t)((int32_t)(c1 << sh) >> 31), b2 = (uint32_t)((int32_t)(c2 << sh) >> 31);
+      lt0 |= eq0 & ~u & b0; eq0 &= ~(u ^ b0);
+      lt1 |= eq1 & ~u & b1; eq1 &= ~(u ^ b1);
+      lt2 |= eq2 & ~u & b2; eq2 &= ~(u ^ b2);
+    }
+    if (!__any_sync(0xFFFFFFFFu, (eq0 | eq1 | eq2) != 0u)) break;
+  }
+  const uint32_t g0 = ~lt0, g1 = ~lt1, g2 = ~lt2;   // u >= threshold (thermometer: g0 >= g1 >= g2)
+  lo = g0 ^ g1 ^ g2;
+  hi = g1;
+}
+
 }  // namespace pbn

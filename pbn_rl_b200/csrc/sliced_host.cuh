@@ -25,6 +25,7 @@ struct GenFunc {
   int arity;
   int in[PBN_MAX_ARITY];
   uint64_t lut;
+  uint32_t cum;   // cumulative selection threshold (2^-32 units) of this predictor within its gene
 };
 
 struct GenNet {
@@ -34,7 +35,8 @@ struct GenNet {
 };
 
 // ---- eligibility ---------------------------------------------------------------------------
-// The sliced kernel draws uniform selections among K in {1,2,3,4} predictors per gene.
+// The sliced kernels take K in {1,2,3,4} predictors per gene: uniform selection from 2-bit pairs (exact 1-of-3 by
+// rejection), any other probabilities by a bit-serial comparison of a 32-bit uniform with the gene's thresholds.
 inline bool eligible(const pbn_net_desc* d, std::string* why) {
   if (d->n_genes > 96) {
     if (why) *why = "more than 96 genes";
@@ -51,13 +53,11 @@ inline bool eligible(const pbn_net_desc* d, std::string* why) {
         if (why) *why = "predictor with more than 6 inputs";
         return false;
       }
-    for (int k = 0; k + 1 < K; ++k) {
-      const double want = std::floor((double)(k + 1) / K * 4294967296.0 + 0.5);
-      if (std::fabs((double)d->func_cum[f0 + k] - want) > 2.0) {
-        if (why) *why = "non-uniform predictor selection probabilities";
+    for (int k = 0; k + 2 < K; ++k)
+      if (d->func_cum[f0 + k] > d->func_cum[f0 + k + 1]) {
+        if (why) *why = "selection thresholds of a gene are not non-decreasing";
         return false;
       }
-    }
   }
   return true;
 }
@@ -75,6 +75,7 @@ inline GenNet gen_net_from_desc(const pbn_net_desc* d) {
       gf.arity = d->func_arity[f];
       for (int j = 0; j < gf.arity; ++j) gf.in[j] = d->func_inputs[f * PBN_FUNC_INPUT_STRIDE + j];
       gf.lut = gf.arity >= 6 ? d->func_lut[f] : (d->func_lut[f] & ((1ull << (1u << gf.arity)) - 1ull));
+      gf.cum = d->func_cum[f];
       g.funcs[i].push_back(gf);
     }
   return g;
@@ -177,6 +178,17 @@ inline int sliced_min_blocks(const GenNet& g) {
 // pair-planes for the 1/16 of the 1-of-3 draws that are still rejected -- see step_sliced.cuh "Random streams"); a
 // part evaluates its genes (pbn_eval_part, plane-resident kernel).  Single-predictor genes are spread over the
 // parts by load.
+// A gene's selection is "uniform" when its thresholds are those of 1/K each (what ISPL networks give): the cheap
+// pair-plane draw applies.  Anything else is "weighted".
+inline bool uniform_selection(const std::vector<GenFunc>& fs) {
+  const int K = (int)fs.size();
+  for (int k = 0; k + 1 < K; ++k) {
+    const double want = std::floor((double)(k + 1) / K * 4294967296.0 + 0.5);
+    if (std::fabs((double)fs[k].cum - want) > 2.0) return false;
+  }
+  return true;
+}
+
 inline void generate_parts(const GenNet& g, std::string& u) {
   const int N = g.n_genes;
   char buf[320];
@@ -205,22 +217,45 @@ inline void generate_parts(const GenNet& g, std::string& u) {
   const int MAXS4 = (NSEL + 3) / 4 > 0 ? (NSEL + 3) / 4 : 1;
   u += "\n#define PBN_CLAIM(k, m3, px, py) { const uint32_t rj_ = lo[k] & hi[k] & (m3); const uint32_t tk_ = rj_ & av; av &= ~rj_; "
        "lo[k] = bmux(tk_, px, lo[k]); hi[k] = bmux(tk_, py, hi[k]); }\n";
+  {
+    std::string tw, tc;
+    int slot_i = 0;
+    for (int i = 0; i < N; ++i)
+      if (g.funcs[i].size() > 1) {
+        tw += (uniform_selection(g.funcs[i]) ? "0, " : "1, ");
+        for (int k = 0; k < 3; ++k) {
+          snprintf(buf, sizeof(buf), "0x%08Xu, ", k + 1 < (int)g.funcs[i].size() ? g.funcs[i][k].cum : 0xFFFFFFFFu);
+          tc += buf;
+        }
+        ++slot_i;
+      }
+    if (slot_i == 0) { tw = "0"; tc = "0u"; }
+    u += "// slot r draws by threshold comparison (kSelWeighted[r] != 0) against kSelCum[3r .. 3r+K-2]\n";
+    u += "__device__ __constant__ unsigned char kSelWeighted[] = {" + tw + "};\n";
+    u += "__device__ __constant__ uint32_t kSelCum[] = {" + tc + "};\n";
+  }
   u += "// selection planes of group q (slots r = q + 4k): lo[k] + 2*hi[k] = predictor index, bit-sliced over the column's 32 envs\n";
   u += "__device__ __forceinline__ void pbn_draw_group(uint32_t q, uint64_t gid, uint64_t step, const uint32_t (&rk)[20],\n"
        "                                               uint32_t (&lo)[PBN_MAXS4], uint32_t (&hi)[PBN_MAXS4]) {\n";
-  std::vector<int> kof(NSEL, 1);
+  std::vector<int> kof(NSEL, 1), wof(NSEL, 0);
+  std::vector<uint32_t> cumof(3 * (NSEL > 0 ? NSEL : 1), 0xFFFFFFFFu);
   for (int i = 0; i < N; ++i)
-    if (slot_of[i] >= 0) kof[slot_of[i]] = (int)g.funcs[i].size();
+    if (slot_of[i] >= 0) {
+      kof[slot_of[i]] = (int)g.funcs[i].size();
+      wof[slot_of[i]] = uniform_selection(g.funcs[i]) ? 0 : 1;
+      for (int k = 0; k + 1 < (int)g.funcs[i].size() && k < 3; ++k) cumof[3 * slot_of[i] + k] = g.funcs[i][k].cum;
+    }
   std::string any;
   std::vector<std::string> m3(MAXS4);
   for (int k = 0; k < MAXS4; ++k) {
     int Kq[4];
-    bool same = true, some3 = false;
+    bool same = true, some3 = false, anyw = false;
     for (int q = 0; q < 4; ++q) {
       const int r = q + 4 * k;
       Kq[q] = r < NSEL ? kof[r] : 1;
       same = same && Kq[q] == Kq[0];
-      some3 = some3 || Kq[q] == 3;
+      some3 = some3 || (Kq[q] == 3 && !(r < NSEL && wof[r]));
+      anyw = anyw || (r < NSEL && wof[r]);
     }
     snprintf(buf, sizeof(buf), "  lo[%d] = 0u; hi[%d] = 0u;\n", k, k);
     u += buf;
@@ -228,7 +263,7 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       m3[k] = "";
       continue;
     }
-    if (same) {
+    if (same && !anyw) {
       snprintf(buf, sizeof(buf), "  { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, q + %du, rk);  // K = %d in every group\n", 4 * k, Kq[0]);
       u += buf;
       if (Kq[0] == 2) snprintf(buf, sizeof(buf), "    lo[%d] = A.x; }\n", k);
@@ -239,14 +274,23 @@ inline void generate_parts(const GenNet& g, std::string& u) {
     } else {
       snprintf(buf, sizeof(buf), "  const uint32_t K%d = (q + %du < %du) ? kSelK[q + %du] : 1u;\n", k, 4 * k, NSEL, 4 * k);
       u += buf;
-      snprintf(buf, sizeof(buf), "  if (K%d > 1u) { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, q + %du, rk);\n", k, 4 * k);
+      if (anyw) {
+        snprintf(buf, sizeof(buf), "  const bool W%d = (q + %du < %du) && kSelWeighted[q + %du] != 0;\n", k, 4 * k, NSEL, 4 * k);
+        u += buf;
+        snprintf(buf, sizeof(buf), "  if (W%d) draw_weighted(gid, step, rk, q + %du, K%d, kSelCum + 3u * (q + %du), lo[%d], hi[%d]);\n  else ", k, 4 * k, k, 4 * k, k, k);
+        u += buf;
+      } else {
+        u += "  ";
+      }
+      snprintf(buf, sizeof(buf), "if (K%d > 1u) { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, q + %du, rk);\n", k, 4 * k);
       u += buf;
       snprintf(buf, sizeof(buf), "    lo[%d] = A.x; if (K%d == 4u) hi[%d] = A.y;\n", k, k, k);
       u += buf;
       snprintf(buf, sizeof(buf), "    if (K%d == 3u) { const uint32_t rj = A.x & A.y; lo[%d] = bmux(rj, A.z, A.x); hi[%d] = bmux(rj, A.w, A.y); } }\n", k, k, k);
       u += buf;
       if (some3) {
-        snprintf(buf, sizeof(buf), "  const uint32_t m3_%d = K%d == 3u ? 0xFFFFFFFFu : 0u;\n", k, k);
+        if (anyw) snprintf(buf, sizeof(buf), "  const uint32_t m3_%d = (K%d == 3u && !W%d) ? 0xFFFFFFFFu : 0u;\n", k, k, k);
+        else snprintf(buf, sizeof(buf), "  const uint32_t m3_%d = K%d == 3u ? 0xFFFFFFFFu : 0u;\n", k, k);
         u += buf;
         snprintf(buf, sizeof(buf), "m3_%d", k);
         m3[k] = buf;

@@ -92,9 +92,7 @@ def test_sliced_eligibility():
     from pbn_rl_b200.vec_env import jit_source
     assert "pbn_update_part" in jit_source(product_net("pbn28"))
     nonuniform = PBNNetwork.from_expressions(["a", "b"], [[("a | b", 0.9), ("a & b", 0.1)], ["a"]])
-    with pytest.raises(_cabi.PbnError) as ei:
-        jit_source(nonuniform)
-    assert ei.value.code == -3
+    assert "draw_weighted" in jit_source(nonuniform)   # arbitrary probabilities: threshold comparison, still bit-sliced
     five = PBNNetwork.from_expressions(["a", "b"], [["a", "b", "a|b", "a&b", "~a"], ["a"]])
     with pytest.raises(_cabi.PbnError):
         jit_source(five)
@@ -107,12 +105,13 @@ HOST_HARNESS = r"""
 #define __device__
 #define __forceinline__ inline
 #define __constant__ const
-#include "philox.cuh"
-using pbn::Philox4;
-using pbn::philox_stream_rk;
 #define PBN_RNG_SELECT 0u
 #define PBN_RNG_FIX 3u
 static inline bool __any_sync(unsigned, bool p) { return p; }   // one column = one lane
+#include "philox.cuh"
+using pbn::Philox4;
+using pbn::philox_stream_rk;
+using pbn::draw_weighted;
 template <int IMM> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r = 0;
   for (int i = 0; i < 32; ++i) {
@@ -172,7 +171,26 @@ int main(int argc, char** argv) {
 """
 
 
-@pytest.mark.parametrize("name", NETS)
+def _mixed_network():
+    """K in {1,2,3,4}, uniform and weighted selection mixed, so that every branch of the generated draw runs."""
+    genes = ["g%d" % i for i in range(11)]
+    fs = [
+        [("g1 | g2", 0.9), ("g1 & g2", 0.1)],                       # K=2 weighted
+        ["g0"],                                                      # K=1
+        ["g3 & g4", "g3 | g4", "~g5"],                               # K=3 uniform
+        [("g0", 0.25), ("g1", 0.25), ("g2 & ~g3", 0.5)],              # K=3 weighted
+        ["g4", "~g4"],                                               # K=2 uniform
+        ["g1", "g2", "g3", "g4 & g0"],                               # K=4 uniform
+        [("g6", 0.1), ("g7", 0.2), ("g8", 0.3), ("g9", 0.4)],        # K=4 weighted
+        ["g7 | g8", "g9", "g10"],                                    # K=3 uniform
+        ["g8"],                                                      # K=1
+        [("g9 & g10", 0.999), ("g0", 0.001)],                        # K=2 weighted, extreme
+        ["g10", "g5", "g6 & g7"],                                    # K=3 uniform
+    ]
+    return genes, fs
+
+
+@pytest.mark.parametrize("name", NETS + ("mixed",))
 def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     """Compile the generated net_gen.cuh / net_update.inc with g++: the predictor trees of both kernels against the
     truth tables on random bit-planes, and the generated selection draw (pbn_draw_group, with csrc/philox.cuh compiled
@@ -181,7 +199,12 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     from oracle import pbn_oracle as O
     from helpers import oracle_net
     from pbn_rl_b200.vec_env import jit_source
-    net = product_net(name)
+    if name == "mixed":
+        genes, fs = _mixed_network()
+        net = PBNNetwork.from_expressions(genes, fs)
+        onet = O.OracleNetwork(genes, [[(f, 1.0 / len(g)) if isinstance(f, str) else f for f in g] for g in fs])
+    else:
+        net, onet = product_net(name), oracle_net(name)
     src = jit_source(net)
     gen, upd = src.split("// ---- net_gen.cuh\n")[1].split("// ---- net_update.inc\n")
     (tmp_path / "net_gen.cuh").write_text(gen)
@@ -224,7 +247,6 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
         for i in range(n):
             diff |= got2[i] ^ int(x[(i + 1) % n])
         assert got2[n] == diff  # OR of (next state XOR target planes)
-    onet = oracle_net(name)
     for (gid, step, seed), got in zip(draws, rows[2 * cases:]):
         tile, lane = gid >> 5, gid & 31
         ids = np.array([tile * 1024 + 128 * (b >> 2) + 4 * lane + (b & 3) for b in range(32)], dtype=np.uint64)

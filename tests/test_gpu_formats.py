@@ -61,9 +61,12 @@ def test_wide_predictor_known_answer():
     assert [[str(a), str(b)] for a, b in zip(_inputs(14)[:8], out[:8])] == want["first_rows"]
 
 
-def test_assa_network_rollout_bit_exact_with_selection_probabilities():
+@pytest.mark.parametrize("kernel", ["auto", "scalar"])
+def test_assa_network_rollout_bit_exact_with_selection_probabilities(kernel):
     """Product: truth tables from the ASSA file.  Oracle: the python expressions + probabilities the REFERENCE
-    parser made of the same file.  Own-RNG rollout (non-uniform predictor selection) must agree bit for bit."""
+    parser made of the same file.  Own-RNG rollout (non-uniform predictor selection) must agree bit for bit -- on the
+    bit-sliced kernel (threshold comparison of a bit-sliced 32-bit uniform, train_assa_matlab_BQN.py:72-171) and on
+    the thread-per-env kernel -- and the selection frequencies must follow the file's probabilities (chi-square)."""
     import torch
     from oracle import pbn_oracle as O
     from pbn_rl_b200 import VecPBNEnv
@@ -71,9 +74,9 @@ def test_assa_network_rollout_bit_exact_with_selection_probabilities():
     want = _golden("assa_example_expected.json")
     net, rate = network_from_assa_matlab(GOLD / "assa_example.txt")
     onet = O.OracleNetwork(want["genes"], [[(e, p) for e, p in want["logic_functions"][str(g)]] for g in range(5)])
-    e, seed, p = 4096, 1234, 0.05
-    env = VecPBNEnv(net, e, None, device="cuda:0", perturb_p=p, perturb_mode="A", seed=seed)
-    assert env.kernel == "scalar"
+    e, seed, p = 8192, 1234, 0.05
+    env = VecPBNEnv(net, e, None, device="cuda:0", perturb_p=p, perturb_mode="A", seed=seed, kernel=kernel)
+    assert env.kernel == ("sliced" if kernel == "auto" else "scalar")
     rng = np.random.default_rng(0)
     state = rng.integers(0, 32, size=(e, 1)).astype(np.uint64)
     env.set_state(torch.from_numpy(state.astype(np.int64)), packed=True)
@@ -83,16 +86,48 @@ def test_assa_network_rollout_bit_exact_with_selection_probabilities():
     for step in range(6):
         act = rng.integers(0, 6, size=(e, 3), dtype=np.uint8)
         env.step(torch.from_numpy(act).cuda())
-        sel = O.scalar_stream_selection(onet, ids, step, seed)
-        pert = O.scalar_stream_perturbation(5, p, ids, step, seed)
+        if env.kernel == "sliced":
+            sel, pert = O.sliced_stream(onet, p, ids, step, seed)
+        else:
+            sel = O.scalar_stream_selection(onet, ids, step, seed)
+            pert = O.scalar_stream_perturbation(5, p, ids, step, seed)
         state, *_ = O.batched_step(onet, tables, state, act, np.full(e, -1), np.zeros(e, np.uint16), horizon=0,
                                    mode=O.PERT_A, sel=sel, pert=pert, r_success=5.0, r_step=0.0, r_action=-1.0)
         assert np.array_equal(env.state.cpu().numpy().astype(np.uint64), state), step
         counts += np.bincount(sel[:, 2], minlength=3)
-    freq = counts / counts.sum()                 # gene 2: probabilities 0.3 / 0.2 / 0.5
-    assert np.allclose(freq, [0.3, 0.2, 0.5], atol=0.02)
+    probs = np.array([0.3, 0.2, 0.5])               # gene 2 of the file
+    chi2 = float((((counts - counts.sum() * probs) ** 2) / (counts.sum() * probs)).sum())
+    assert chi2 < 18.4, (chi2, counts)              # 2 degrees of freedom, p = 1e-4
     assert abs(rate - 0.0025) < 1e-12
     env.close()
+
+
+def test_weighted_network_resident_equals_rows():
+    """A network mixing K = 1..4 with uniform and weighted selection: plane-resident steps == row-format steps."""
+    import torch
+    from pbn_rl_b200 import AttractorSet, PBNNetwork, VecPBNEnv
+    genes = ["g%d" % i for i in range(6)]
+    fs = [[("g1 | g2", 0.9), ("g1 & g2", 0.1)], ["g0"], ["g3 & g4", "g3 | g4", "~g5"],
+          [("g0", 0.25), ("g1", 0.25), ("g2 & ~g3", 0.5)], ["g4", "~g4"], [("g0", 0.1), ("g1", 0.2), ("g2", 0.3), ("g3", 0.4)]]
+    net = PBNNetwork.from_expressions(genes, fs)
+    attrs = AttractorSet([[(1, 1, 1, 1, 1, 1)], [(0, 0, 0, 0, 0, 0)], [(1, 0, 1, 0, 1, 0)]], 6)
+    e = 2048 + 100
+    envs = [VecPBNEnv(net, e, attrs, device="cuda:0", perturb_p=0.01, perturb_mode="B", seed=5, horizon=4, auto_reset=True,
+                      kernel="sliced", resident=r) for r in (False, True)]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    st = torch.randint(0, 64, (e, 1), generator=g, device="cuda", dtype=torch.int64)
+    tg = torch.randint(0, 3, (e,), generator=g, device="cuda", dtype=torch.int32)
+    for env in envs:
+        env.set_state(st, packed=True)
+        env.set_target(tg)
+    for step in range(10):
+        a = torch.randint(0, 7, (e, 3), generator=g, device="cuda", dtype=torch.uint8)
+        for env in envs:
+            env.step(a)
+        assert torch.equal(envs[0].reward, envs[1].reward) and torch.equal(envs[0].terminated, envs[1].terminated)
+    assert torch.equal(envs[0].state, envs[1].state) and envs[0].stats() == envs[1].stats()
+    for env in envs:
+        env.close()
 
 
 def test_control_env_protocol():
