@@ -168,7 +168,9 @@ static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W, int warps,
   L.rew_off = o;
   o += 80u;
   const uint32_t abytes = (uint32_t)(n.n_attr + 1) * 4u + (uint32_t)n.n_attr_states * W * 16u + 32u;
-  L.attractors_in_smem = (n.n_attr > 0 && abytes <= 32u * 1024u) ? 1u : 0u;
+  // (large attractors go through the hash set, the wrong-attractor reward term through the table scan: both live in
+  //  the kernel's out-of-line membership path, selected by clearing this flag)
+  L.attractors_in_smem = (n.n_attr > 0 && abytes <= 32u * 1024u && !(n.attr_simple == 0u && n.ahash_tags != nullptr) && n.r_wrong == 0.0f) ? 1u : 0u;
   if (L.attractors_in_smem) {
     L.acare_off = o;
     o += (uint32_t)n.n_attr_states * W * 8u;

@@ -336,6 +336,22 @@ __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, co
 #endif
 }
 
+// The uncommon membership tests of phase F, out of line so that they cost the common path neither registers nor
+// instruction-cache space: state in attractor a through the hash set (large attractors) or by the scan over the table
+// in global memory (bit 0 of the result), and, with r_wrong != 0, state in an attractor OTHER than a (bit 1).
+// (the row travels by value: a reference would force the caller's row registers into local memory)
+__device__ __noinline__ uint32_t rare_membership(const NetParams& n, int a, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  const uint32_t row[4] = {r0, r1, r2, r3};
+  uint64_t y64[kW64];
+#pragma unroll
+  for (int wd = 0; wd < kW64; ++wd)
+    y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? row[(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | row[2 * wd];
+  const bool hit = (n.attr_simple == 0u && n.ahash_tags != nullptr) ? in_attractor_hashed<kW64>(n, a, y64)
+                                                                     : in_attractor<kW64>(n.attr_offset, n.attr_care, n.attr_val, a, y64);
+  const bool wrong = !hit && n.r_wrong != 0.0f && in_other_attractor<kW64>(n, a, y64);
+  return (hit ? 1u : 0u) | (wrong ? 2u : 0u);
+}
+
 // FULL: the tile has all 1024 envs (vector loads/stores); otherwise every access is guarded.
 // ASMEM: the attractor table was staged into shared memory (the usual case).
 template <bool FULL, bool ASMEM>
@@ -642,7 +658,9 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   const uint32_t n_attr = (a.target_id != nullptr) ? (uint32_t)n.n_attr : 0u;
   const uint32_t horizon = n.horizon > 0 ? (uint32_t)n.horizon : 0xFFFFFFFFu;
   const bool simple = n.attr_simple != 0u;  // block-uniform
-  const bool use_hash = !simple && n.ahash_tags != nullptr;
+  // ASMEM (compile time): the table sits in shared memory and neither the hash set nor the wrong-attractor term is in
+  // play (the host clears the flag otherwise): the out-of-line test below is then not even compiled in
+  constexpr bool fast_attr = ASMEM;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int64_t e = e0 + 128 * (2 * (int)w + g);
@@ -652,22 +670,21 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     for (int c = 0; c < 4; ++c) {
       const int i = 4 * g + c;
       bool hit = false;
+      bool wrong = false;
       if (tg[i] < n_attr) {  // unsigned compare: negative ids never match
-        if (use_hash) {
-          // large attractors: O(1) through the hash set over their states (L2-resident) instead of a scan
-          uint64_t y64[kW64];
-#pragma unroll
-          for (int wd = 0; wd < kW64; ++wd)
-            y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
-          hit = in_attractor_hashed<kW64>(n, (int)tg[i], y64);
-        } else if (attr_in_smem && simple) {
+        if (!fast_attr) {
+          // large attractors (hash set), tables too large for shared memory, or the wrong-attractor reward term
+          const uint32_t hw = rare_membership(n, (int)tg[i], o[i][0], o[i][kNW > 1 ? 1 : 0], o[i][kNW > 2 ? 2 : 0], o[i][kNW > 3 ? 3 : 0]);
+          hit = (hw & 1u) != 0u;
+          wrong = (hw & 2u) != 0u;
+        } else if (simple) {
           // one fully specified state per attractor: entry index == attractor id
           const uint32_t* ent = s_aent + tg[i] * (2 * kNW) + kNW;
           uint32_t diff = 0u;
 #pragma unroll
           for (int wd = 0; wd < kNW; ++wd) diff |= o[i][wd] ^ ent[wd];
           hit = diff == 0u;
-        } else if (attr_in_smem) {
+        } else {
           int en = s_aoffs[tg[i]];
           const int en1 = s_aoffs[tg[i] + 1];
 #pragma unroll 1
@@ -678,25 +695,13 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
             for (int wd = 0; wd < kNW; ++wd) diff |= (o[i][wd] & ent[wd]) ^ ent[kNW + wd];
             hit = hit || diff == 0u;
           } while (++en < en1);
-        } else {
-          uint64_t y64[kW64];
-#pragma unroll
-          for (int wd = 0; wd < kW64; ++wd)
-            y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
-          hit = in_attractor<kW64>(n.attr_offset, n.attr_care, n.attr_val, (int)tg[i], y64);
         }
       }
       const uint32_t t1 = min(tt[i] + 1u, 65535u);
       const bool trunc = !hit && t1 >= horizon;
       const uint32_t nf = (nfp >> (4 * i)) & 0xFu;
       rw[c] = s_rew[nf + (hit ? 9u : 0u)];
-      if (!hit && n.r_wrong != 0.0f && n_attr != 0u) {   // "wrong attractor" term (rare configuration: row-domain scan / hash)
-        uint64_t y64[kW64];
-#pragma unroll
-        for (int wd = 0; wd < kW64; ++wd)
-          y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
-        if (in_other_attractor<kW64>(n, (int)tg[i], y64)) rw[c] = __fadd_rn(s_rew[nf], n.r_wrong);
-      }
+      if (wrong) rw[c] = __fadd_rn(s_rew[nf], n.r_wrong);
       const bool valid = FULL || (e + c < E);
       hbits |= (hit && valid ? 1u : 0u) << c;
       tbits |= (trunc && valid ? 1u : 0u) << c;
@@ -727,7 +732,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
         for (int q = 0; q < 2 * kW64; ++q)
           fp[q] = make_ulonglong2(y[(2 * q) / kW64][(2 * q) % kW64], y[(2 * q + 1) / kW64][(2 * q + 1) % kW64]);
       }
-      if (a.packed_out != nullptr)   // (kW64 == 1: the host admits N <= 30 only)
+      if (PBN_EXP != 7 && a.packed_out != nullptr)   // (kW64 == 1: the host admits N <= 30 only)
         *reinterpret_cast<uint4*>(a.packed_out + e) =
             make_uint4((uint32_t)y[0][0] | ((hbits & 1u) << 30) | ((tbits & 1u) << 31), (uint32_t)y[1][0] | (((hbits >> 1) & 1u) << 30) | (((tbits >> 1) & 1u) << 31),
                        (uint32_t)y[2][0] | (((hbits >> 2) & 1u) << 30) | (((tbits >> 2) & 1u) << 31), (uint32_t)y[3][0] | (((hbits >> 3) & 1u) << 30) | (((tbits >> 3) & 1u) << 31));
@@ -746,7 +751,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
           a.state[(e + c) * kW64 + wd] = y[c][wd];
           if (a.final_state != nullptr) a.final_state[(e + c) * kW64 + wd] = y[c][wd];
         }
-        if (a.packed_out != nullptr) a.packed_out[e + c] = (uint32_t)y[c][0] | (((hbits >> c) & 1u) << 30) | (((tbits >> c) & 1u) << 31);
+        if (PBN_EXP != 7 && a.packed_out != nullptr) a.packed_out[e + c] = (uint32_t)y[c][0] | (((hbits >> c) & 1u) << 30) | (((tbits >> c) & 1u) << 31);
         if (a.reward != nullptr) a.reward[e + c] = rw[c];
         if (a.terminated != nullptr) a.terminated[e + c] = (uint8_t)((hbits >> c) & 1u);
         if (a.truncated != nullptr) a.truncated[e + c] = (uint8_t)((tbits >> c) & 1u);
@@ -760,6 +765,15 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   // ---- G. auto-reset of finished envs (sparse: scattered writes after the vector stores) ----------
   uint32_t D = (H | TR) & VALID;
   if (a.stats != nullptr) {
+#if PBN_EXP == 8
+    const uint32_t v[7] = {(uint32_t)__popc(VALID), (uint32_t)__popc(D), (uint32_t)__popc(H & VALID),
+                           (uint32_t)__popc(TR & VALID), len_sum, flips, npert};
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const uint32_t x = __reduce_add_sync(0xFFFFFFFFu, v[q]);
+      if (lane == 0u && x != 0u) atomicAdd(&s_stat[q], x);
+    }
+#else
     // the per-thread counts are small (8 envs): two 16-bit fields per warp reduction
     const uint32_t x0 = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(VALID) | ((uint32_t)__popc(H & VALID) << 16));
     const uint32_t x1 = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(TR & VALID) | (npert << 16));
@@ -775,6 +789,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       if (x2) atomicAdd(&s_stat[PBN_STAT_FLIPS], x2);
       if (x1 >> 16) atomicAdd(&s_stat[PBN_STAT_PERTURBED], x1 >> 16);
     }
+#endif
   }
   if (a.flags & PBN_STEP_AUTORESET) {
     auto do_reset = [&](int64_t env, const Philox4& r, uint32_t flag_bits) {
@@ -796,7 +811,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       a.target_id[env] = tgt;
       if (a.source_id != nullptr) a.source_id[env] = src;
       a.t[env] = 0;
-      if (a.packed_out != nullptr) a.packed_out[env] = (uint32_t)s[0] | flag_bits;   // the state after the reset, the flags of the step
+      if (PBN_EXP != 7 && a.packed_out != nullptr) a.packed_out[env] = (uint32_t)s[0] | flag_bits;   // the state after the reset, the flags of the step
     };
     // The finished envs of the warp (about 13 of its 256 per step) are dealt out over its lanes, one per lane and
     // trip: a single Philox pass instead of a per-lane serial loop that runs for as long as the unluckiest lane.
@@ -821,7 +836,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       L = min(L, 31u);
       const uint32_t eL = __shfl_sync(0xFFFFFFFFu, excl, (int)L);
       const uint32_t DL = __shfl_sync(0xFFFFFFFFu, D, (int)L);
-      const uint32_t HL = __shfl_sync(0xFFFFFFFFu, H, (int)L);
+      const uint32_t HL = PBN_EXP != 7 ? __shfl_sync(0xFFFFFFFFu, H, (int)L) : 0u;
       if (j < total) {
         uint32_t m = DL;
         for (uint32_t k = j - eL; k != 0u; --k) m &= m - 1u;   // drop the k lowest finished envs of the owner
@@ -896,7 +911,8 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
       if (full) tile_step<true, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
       else tile_step<false, true>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
     } else {
-      tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
+      if (full) tile_step<true, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
+      else tile_step<false, false>(p, L, scr, s_surv, s_rew, s_aoffs, s_aent, tile, step_ctr, stage, st_state, st_act, mbar, tma_parity, pre_drawn, ev_drawn);
     }
     stage = false;
     pre_drawn = false;
