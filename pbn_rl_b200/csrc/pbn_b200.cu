@@ -116,6 +116,7 @@ struct pbn_handle {
   // sliced kernel: [0] = own-RNG specialisation, [1] = injected-randomness one (compiled on first use)
   jit::GenNet gen;
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
+  cudaLibrary_t jit_lib_planes[2] = {nullptr, nullptr};   // the plane-resident kernels' program, loaded on first use
   cudaKernel_t jit_kernel[2] = {nullptr, nullptr};
   cudaKernel_t planes_kernel[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [injected][0: 4 warps, 1: 8 warps] pbn_step_planes_w*
   uint32_t planes_smem_opt_in[2][2] = {{48u * 1024u, 48u * 1024u}, {48u * 1024u, 48u * 1024u}};
@@ -138,11 +139,9 @@ static int load_sliced(pbn_handle* h, int injected) {
   if (h->jit_kernel[injected]) return PBN_OK;
   std::vector<char> cubin;
   std::string err;
-  if (jit::compile(h->gen, injected != 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
+  if (jit::compile(h->gen, injected != 0, 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
   PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
-  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][0], h->jit_lib[injected], "pbn_step_planes_w4"));
-  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][1], h->jit_lib[injected], "pbn_step_planes_w8"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->predraw_kernel, h->jit_lib[0], "pbn_predraw_sliced"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->rollout_kernel, h->jit_lib[0], "pbn_rollout_sliced"));
   if (!injected) {  // the survival table of the perturbation sub-streams lives in the specialisation's constant memory
@@ -154,6 +153,25 @@ static int load_sliced(pbn_handle* h, int injected) {
   }
   h->sliced_threads = jit::sliced_threads(h->gen);
   h->sliced_min_blocks = jit::sliced_min_blocks(h->gen);
+  return PBN_OK;
+}
+
+// The plane-resident kernels' specialisation (own program, compiled / loaded on first use).
+static int load_planes(pbn_handle* h, int injected) {
+  if (h->planes_kernel[injected][0]) return PBN_OK;
+  std::vector<char> cubin;
+  std::string err;
+  if (jit::compile(h->gen, injected != 0, 1, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
+  PBN_CUDA(cudaLibraryLoadData(&h->jit_lib_planes[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][1], h->jit_lib_planes[injected], "pbn_step_planes_w8"));
+  if (!injected) {
+    void* dptr = nullptr;
+    size_t bytes = 0;
+    PBN_CUDA(cudaLibraryGetGlobal(&dptr, &bytes, h->jit_lib_planes[injected], "_ZN3pbn10kSurvTableE"));
+    if (bytes != h->surv_sliced_host.size() * sizeof(uint32_t)) return fail(PBN_ERR_JIT, "kSurvTable has %zu bytes, expected %zu", bytes, h->surv_sliced_host.size() * sizeof(uint32_t));
+    PBN_CUDA(cudaMemcpy(dptr, h->surv_sliced_host.data(), bytes, cudaMemcpyHostToDevice));
+  }
+  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][0], h->jit_lib_planes[injected], "pbn_step_planes_w4"));
   return PBN_OK;
 }
 
@@ -253,7 +271,7 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
   if (rc != PBN_OK) return rc;
   if (!aligned_to(a.resident, 128) || !aligned_to(a.reward, 16) || !aligned_to(a.actions, 4) || !aligned_to(a.terminated, 4) || !aligned_to(a.truncated, 4))
     return fail(PBN_ERR_INVALID, "plane-resident step needs a 128-byte aligned block, 16-byte aligned reward, 4-byte aligned actions / flags");
-  if ((rc = load_sliced(h, injected ? 1 : 0)) != PBN_OK) return rc;
+  if ((rc = load_planes(h, injected ? 1 : 0)) != PBN_OK) return rc;
   const NetParams& n = h->net;
   const int N = n.n_genes, NW = (N + 31) / 32;
   const int64_t tiles = (a.n_envs + 1023) / 1024;
@@ -347,8 +365,10 @@ void pbn_destroy(pbn_handle* h) {
     cudaFree(h->d_surv_sliced);
     cudaFree(h->d_wide);
     cudaFree(h->d_wide_lut);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
       if (h->jit_lib[i]) cudaLibraryUnload(h->jit_lib[i]);
+      if (h->jit_lib_planes[i]) cudaLibraryUnload(h->jit_lib_planes[i]);
+    }
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
@@ -725,7 +745,8 @@ int pbn_jit_precompile(const pbn_net_desc* d) {
   for (int inj = 0; inj < 2; ++inj) {
     std::vector<char> cubin;
     std::string err;
-    if (jit::compile(g, inj != 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
+    for (int part = 0; part < 2; ++part)
+      if (jit::compile(g, inj != 0, part, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
   }
   return PBN_OK;
 }

@@ -619,7 +619,10 @@ inline bool profile_build() {
 }
 
 // Compile (or fetch from the cache) the specialisation; returns 0 or PBN_ERR_JIT with *err set.
-inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std::string* err) {
+// part 0: the row-format kernels (pbn_step_sliced, pbn_rollout_sliced, pbn_predraw_sliced); part 1: the plane-resident
+// kernels (pbn_step_planes_w4 / _w8), compiled and loaded on first use -- two programs, so that an env that never
+// uses one family never pays its compile time.
+inline int compile(const GenNet& g, bool injected, int part, std::vector<char>* cubin, std::string* err) {
   std::string gen_h, upd;
   generate(g, injected, &gen_h, &upd);
   const std::string main_src = main_source();
@@ -627,8 +630,9 @@ inline int compile(const GenNet& g, bool injected, std::vector<char>* cubin, std
   // PBN_B200_EXP=<n>: development experiments compiled into the kernels (never set in production)
   std::string exp_opt = "-DPBN_EXP=0";
   if (const char* env = getenv("PBN_B200_EXP")) exp_opt = std::string("-DPBN_EXP=") + env;
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", exp_opt.c_str(), "-DPBN_PROFILE=1"};
-  const int n_opts = profile ? 6 : 5;
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", exp_opt.c_str(),
+                        part ? "-DPBN_BUILD=1" : "-DPBN_BUILD=0", "-DPBN_PROFILE=1"};
+  const int n_opts = profile ? 7 : 6;
   std::string key = gen_h + upd + main_src + kSrc_step_sliced + kSrc_step_planes + kSrc_pbn_common + kSrc_philox + kSrc_pbn_b200_h;
   for (int i = 0; i < n_opts; ++i) key += opts[i];
   char name[64];

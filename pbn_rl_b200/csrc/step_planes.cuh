@@ -613,10 +613,12 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
   bump_device_step(a, p.ticket);
 }
 
+#if PBN_BUILD == 1   // the plane-resident kernels' program (sliced_host.cuh: compile part 1)
 extern "C" __global__ void __launch_bounds__(128, PBN_PLANES_MIN_BLOCKS_W4)
 pbn_step_planes_w4(const __grid_constant__ StepParams p, const PlanesLayout L) { step_planes_body<4>(p, L); }
 
 extern "C" __global__ void __launch_bounds__(256, PBN_PLANES_MIN_BLOCKS_W8)
 pbn_step_planes_w8(const __grid_constant__ StepParams p, const PlanesLayout L) { step_planes_body<8>(p, L); }
+#endif  // PBN_BUILD == 1
 
 }  // namespace pbn

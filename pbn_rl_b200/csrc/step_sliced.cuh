@@ -849,6 +849,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 }
 
+#if PBN_BUILD == 0   // the row-format kernels' program (sliced_host.cuh: compile part 0)
 extern "C" __global__ void __launch_bounds__(PBN_THREADS, PBN_MIN_BLOCKS)
 pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -931,7 +932,9 @@ pbn_step_sliced(const __grid_constant__ StepParams p, const SlicedSmemLayout L) 
   phase_stamp(a, 14);
 }
 
-#if !PBN_INJECTED
+#endif  // PBN_BUILD == 0
+
+#if !PBN_INJECTED && PBN_BUILD == 0
 // ---- pbn_rollout: S uncontrolled updates (env.step([]) S times, graph_classifier/__init__.py:148; the burn-in of
 // the attractor search; compute_ssd_hist's long runs) in ONE launch.  The tile's 1024 states are loaded and
 // bit-transposed once, then stay in shared memory as bit-planes: per update only the Philox selection
