@@ -412,7 +412,7 @@ int pbn_advance_counter(pbn_handle* h, uint64_t* step_ctr_dev, uint64_t n, void*
 
 /* Introspection. */
 /* Slots of the hash set pbn_update_attractors built over the fully specified attractor states (tables with an
- * attractor of more than 8 states: env.in_target / env.is_attracting_state become one probe sequence, model_tester.py:
+ * attractor of more than 64 states: env.in_target / env.is_attracting_state become one probe sequence, model_tester.py:
  * 602-616), 0 if the table is small enough for the scan. */
 int pbn_attractor_hash_slots(const pbn_handle* h);
 int pbn_kernel_kind(const pbn_handle* h);            /* PBN_KERNEL_SCALAR or PBN_KERNEL_SLICED */

@@ -585,9 +585,9 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
     }
   n.attr_simple = simple ? 1u : 0u;
 
-  // Hash set for tables with large attractors (an attractor of more than kHashMinStates states): membership becomes
+  // Hash set for tables with large attractors (an attractor of more than kHashMinStates = 64 states): membership becomes
   // one probe sequence instead of a scan over the attractor (pbn70 has an 8192-state attractor; model_tester.py:602-616).
-  constexpr int kHashMinStates = 8;
+  constexpr int kHashMinStates = 64;   // below that the scan over the attractor in shared memory is the faster test
   int largest = 0;
   for (int a = 0; a < A; ++a) largest = std::max(largest, attr_offset[a + 1] - attr_offset[a]);
   n.ahash_tags = nullptr;
