@@ -596,6 +596,7 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
   n.awild_offset = nullptr;
   n.awild_entry = nullptr;
   n.ahash_mask = 0;
+  n.awild_any = 0;
   if (!simple && largest > kHashMinStates) {
     const int W = h->W;
     std::vector<int32_t> wild_off(A + 1, 0), wild_entry;
@@ -613,7 +614,7 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
       wild_off[a + 1] = (int32_t)wild_entry.size();
     }
     size_t cap = 64;
-    while (cap < 2 * exact.size() + 2) cap *= 2;
+    while (cap < 4 * exact.size() + 2) cap *= 2;   // at most a quarter full: the first probe usually decides
     std::vector<unsigned long long> tags(cap, 0ull);
     std::vector<uint64_t> states(cap * W, 0ull);
     std::vector<int32_t> owner(cap, -1);
@@ -643,6 +644,7 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
     n.awild_offset = h->d_awild_offset;
     n.awild_entry = h->d_awild_entry;
     n.ahash_mask = (uint32_t)(cap - 1);
+    n.awild_any = wild_off[A] > 0 ? 1u : 0u;
   }
   return PBN_OK;
 }

@@ -59,6 +59,7 @@ struct NetParams {
   const int32_t* awild_offset;            // [A + 1] CSR over the entries with wildcards ('*'), by attractor
   const int32_t* awild_entry;             // entry indices into attr_care / attr_val
   uint32_t ahash_mask;
+  uint32_t awild_any;                     // some attractor has entries with wildcards (else the hash set alone decides)
   float r_wrong;                          // reward term for ending a step in a non-target attractor (0: not evaluated)
 };
 

@@ -661,6 +661,22 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   // ASMEM (compile time): the table sits in shared memory and neither the hash set nor the wrong-attractor term is in
   // play (the host clears the flag otherwise): the out-of-line test below is then not even compiled in
   constexpr bool fast_attr = ASMEM;
+  // hash set without wildcard entries and without the wrong-attractor term: first probes of the 8 envs up front
+  const bool hash_first = !fast_attr && !simple && n.ahash_tags != nullptr && n.awild_any == 0u && n.r_wrong == 0.0f;
+  unsigned long long htag[8], hcur[8];
+  uint32_t hslot[8];
+  if (hash_first) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint64_t y64[kW64];
+#pragma unroll
+      for (int wd = 0; wd < kW64; ++wd)
+        y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
+      htag[i] = attr_tag(y64, kW64);
+      hslot[i] = (uint32_t)mix64(htag[i]) & n.ahash_mask;
+      hcur[i] = n.ahash_tags[hslot[i]];
+    }
+  }
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int64_t e = e0 + 128 * (2 * (int)w + g);
@@ -673,10 +689,30 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       bool wrong = false;
       if (tg[i] < n_attr) {  // unsigned compare: negative ids never match
         if (!fast_attr) {
-          // large attractors (hash set), tables too large for shared memory, or the wrong-attractor reward term
+          // large attractors (hash set), tables too large for shared memory, or the wrong-attractor reward term.
+          // The hash set's first probe was issued for all 8 envs of the thread before this loop (independent L2
+          // round trips in flight together): an empty slot is a miss, a slot holding this state under this target
+          // is a hit, anything else goes through the full probe sequence out of line.
+          bool decided = false;
+          if (hash_first) {
+            if (hcur[i] == 0ull) {
+              decided = true;
+            } else if (hcur[i] == htag[i] && n.ahash_attr[hslot[i]] == (int)tg[i]) {
+              bool same = true;
+#pragma unroll
+              for (int wd = 0; wd < kW64; ++wd) {
+                const uint64_t y = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
+                same = same && n.ahash_state[(size_t)hslot[i] * kW64 + wd] == y;
+              }
+              hit = same;
+              decided = same;
+            }
+          }
+          if (!decided) {
           const uint32_t hw = rare_membership(n, (int)tg[i], o[i][0], o[i][kNW > 1 ? 1 : 0], o[i][kNW > 2 ? 2 : 0], o[i][kNW > 3 ? 3 : 0]);
           hit = (hw & 1u) != 0u;
           wrong = (hw & 2u) != 0u;
+          }
         } else if (simple) {
           // one fully specified state per attractor: entry index == attractor id
           const uint32_t* ent = s_aent + tg[i] * (2 * kNW) + kNW;
