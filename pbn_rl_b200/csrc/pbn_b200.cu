@@ -117,7 +117,8 @@ struct pbn_handle {
   jit::GenNet gen;
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
   cudaLibrary_t jit_lib_planes[2] = {nullptr, nullptr};   // the plane-resident kernels' program, loaded on first use
-  cudaKernel_t jit_kernel[2] = {nullptr, nullptr};
+  cudaKernel_t jit_kernel[2] = {nullptr, nullptr};      // pbn_step_sliced (attractor table in shared memory)
+  cudaKernel_t jit_kernel_gen[2] = {nullptr, nullptr};  // pbn_step_sliced_gen (hash set / global table / r_wrong)
   cudaKernel_t planes_kernel[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [injected][0: 4 warps, 1: 8 warps] pbn_step_planes_w*
   uint32_t planes_smem_opt_in[2][2] = {{48u * 1024u, 48u * 1024u}, {48u * 1024u, 48u * 1024u}};
   cudaKernel_t predraw_kernel = nullptr;  // pbn_predraw_sliced of the own-RNG specialisation
@@ -125,7 +126,7 @@ struct pbn_handle {
   uint32_t rollout_smem_opt_in = 48u * 1024u;
   std::vector<uint32_t> surv_sliced_host;  // copied into every loaded specialisation's constant memory
   int sliced_threads = 128, sliced_min_blocks = 1;
-  uint32_t jit_smem_opt_in[2] = {48u * 1024u, 48u * 1024u};
+  uint32_t jit_smem_opt_in[2][2] = {{48u * 1024u, 48u * 1024u}, {48u * 1024u, 48u * 1024u}};  // [injected][gen]
   uint64_t launches = 0;
   bool scalar_smem_opted = false;
   // pbn_step_host: two copy streams + per-chunk events (created on first use)
@@ -142,6 +143,7 @@ static int load_sliced(pbn_handle* h, int injected) {
   if (jit::compile(h->gen, injected != 0, 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
   PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
+  PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel_gen[injected], h->jit_lib[injected], "pbn_step_sliced_gen"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->predraw_kernel, h->jit_lib[0], "pbn_predraw_sliced"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->rollout_kernel, h->jit_lib[0], "pbn_rollout_sliced"));
   if (!injected) {  // the survival table of the perturbation sub-streams lives in the specialisation's constant memory
@@ -224,10 +226,11 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
   if (rc != PBN_OK) return rc;
   SlicedSmemLayout L = sliced_smem_layout(h->net, h->W, h->sliced_threads / 32, jit::scratch_words(h->gen));
   if (L.total > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "sliced kernel needs %u B of shared memory", L.total);
-  cudaKernel_t k = h->jit_kernel[injected ? 1 : 0];
-  if (L.total > h->jit_smem_opt_in[injected ? 1 : 0]) {
+  const int gen = L.attractors_in_smem ? 0 : 1;
+  cudaKernel_t k = gen ? h->jit_kernel_gen[injected ? 1 : 0] : h->jit_kernel[injected ? 1 : 0];
+  if (L.total > h->jit_smem_opt_in[injected ? 1 : 0][gen]) {
     PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    h->jit_smem_opt_in[injected ? 1 : 0] = L.total;
+    h->jit_smem_opt_in[injected ? 1 : 0][gen] = L.total;
   }
   // one CTA per 1024-env tile; beyond a few waves the CTAs loop over tiles
   int64_t grid = (a.n_envs + 1023) / 1024;
