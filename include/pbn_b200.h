@@ -75,7 +75,7 @@ extern "C" {
 
 #define PBN_MAX_GENES 128
 #define PBN_MAX_ARITY 6        /* predictors with a 64-bit truth table (func_lut) */
-#define PBN_MAX_WIDE_ARITY 16  /* "wide" predictors: multi-word truth tables (wide_lut), scalar kernel only */
+#define PBN_MAX_WIDE_ARITY 16  /* "wide" predictors: multi-word truth tables (wide_lut); up to 12 inputs bit-sliced, beyond: scalar kernel */
 #define PBN_MAX_BINS 8
 #define PBN_FUNC_INPUT_STRIDE 8
 

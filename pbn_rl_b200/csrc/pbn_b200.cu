@@ -457,10 +457,6 @@ int pbn_create(const pbn_net_desc* d, pbn_handle** out) {
 
   std::string why;
   bool can_slice = jit::eligible(d, &why);
-  if (max_arity > PBN_MAX_ARITY) {
-    can_slice = false;
-    why = "predictor with more than 6 inputs";
-  }
   int kernel = d->kernel;
   if (kernel == PBN_KERNEL_AUTO) kernel = can_slice ? PBN_KERNEL_SLICED : PBN_KERNEL_SCALAR;
   if (kernel != PBN_KERNEL_SCALAR && kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_INVALID, "kernel kind %d unknown", d->kernel);

@@ -21,12 +21,25 @@ namespace jit {
 // sources embedded at build time (csrc/Makefile -> embedded_src.inc)
 #include "embedded_src.inc"
 
+// Truth table of a predictor over its (ordered) inputs: bit a of the table = value for the input assignment a
+// (input j = bit j of a); 2^arity bits in 64-bit words (one word up to 6 inputs).
+using Table = std::vector<uint64_t>;
+
+inline bool tab_bit(const Table& t, unsigned a) { return (t[a >> 6] >> (a & 63u)) & 1ull; }
+inline void tab_set(Table& t, unsigned a, bool v) {
+  if (v) t[a >> 6] |= 1ull << (a & 63u);
+}
+inline Table tab_make(int k) { return Table((size_t)(k <= 6 ? 1 : (1u << (k - 6))), 0ull); }
+
 struct GenFunc {
   int arity;
-  int in[PBN_MAX_ARITY];
-  uint64_t lut;
+  std::vector<int> in;
+  Table lut;
   uint32_t cum;   // cumulative selection threshold (2^-32 units) of this predictor within its gene
 };
+
+// widest predictor the generated LOP3 trees take (wider ones: thread-per-env kernel)
+constexpr int kSlicedMaxArity = 12;
 
 struct GenNet {
   int n_genes = 0, bins = 3, pert_mode = 0;
@@ -37,6 +50,7 @@ struct GenNet {
 // ---- eligibility ---------------------------------------------------------------------------
 // The sliced kernels take K in {1,2,3,4} predictors per gene: uniform selection from 2-bit pairs (exact 1-of-3 by
 // rejection), any other probabilities by a bit-serial comparison of a 32-bit uniform with the gene's thresholds.
+// Predictors of up to kSlicedMaxArity inputs (7 and more: the multi-word tables of pbn_net_desc::wide_lut).
 inline bool eligible(const pbn_net_desc* d, std::string* why) {
   if (d->n_genes > 96) {
     if (why) *why = "more than 96 genes";
@@ -48,11 +62,17 @@ inline bool eligible(const pbn_net_desc* d, std::string* why) {
       if (why) *why = "gene with more than 4 predictors";
       return false;
     }
-    for (int k = 0; k < K; ++k)
-      if (d->func_arity[f0 + k] > PBN_MAX_ARITY) {
-        if (why) *why = "predictor with more than 6 inputs";
+    for (int k = 0; k < K; ++k) {
+      if (d->func_arity[f0 + k] > PBN_MAX_ARITY &&
+          (d->n_wide <= 0 || !d->wide_inputs || !d->wide_lut_offset || !d->wide_lut || d->func_lut[f0 + k] >= (uint64_t)d->n_wide)) {
+        if (why) *why = "wide predictor without its tables";
         return false;
       }
+      if (d->func_arity[f0 + k] > kSlicedMaxArity) {
+        if (why) *why = "predictor with more than 12 inputs";
+        return false;
+      }
+    }
     for (int k = 0; k + 2 < K; ++k)
       if (d->func_cum[f0 + k] > d->func_cum[f0 + k + 1]) {
         if (why) *why = "selection thresholds of a gene are not non-decreasing";
@@ -73,8 +93,15 @@ inline GenNet gen_net_from_desc(const pbn_net_desc* d) {
     for (int f = d->func_offset[i]; f < d->func_offset[i + 1]; ++f) {
       GenFunc gf{};
       gf.arity = d->func_arity[f];
-      for (int j = 0; j < gf.arity; ++j) gf.in[j] = d->func_inputs[f * PBN_FUNC_INPUT_STRIDE + j];
-      gf.lut = gf.arity >= 6 ? d->func_lut[f] : (d->func_lut[f] & ((1ull << (1u << gf.arity)) - 1ull));
+      gf.lut = tab_make(gf.arity);
+      if (gf.arity > PBN_MAX_ARITY) {  // wide predictor: func_lut holds its index into the wide tables
+        const uint64_t v = d->func_lut[f];
+        for (int j = 0; j < gf.arity; ++j) gf.in.push_back(d->wide_inputs[v * 16 + j]);
+        for (size_t wd = 0; wd < gf.lut.size(); ++wd) gf.lut[wd] = d->wide_lut[d->wide_lut_offset[v] + (int64_t)wd];
+      } else {
+        for (int j = 0; j < gf.arity; ++j) gf.in.push_back(d->func_inputs[f * PBN_FUNC_INPUT_STRIDE + j]);
+        gf.lut[0] = gf.arity >= 6 ? d->func_lut[f] : (d->func_lut[f] & ((1ull << (1u << gf.arity)) - 1ull));
+      }
       gf.cum = d->func_cum[f];
       g.funcs[i].push_back(gf);
     }
@@ -89,60 +116,86 @@ struct Expr {
 
 inline std::string plane(int gene) { return "x" + std::to_string(gene); }
 
+// cofactor of t (k variables) with variable j fixed to v: a table over the remaining k - 1 variables
+inline Table tab_cofactor(const Table& t, int k, int j, bool v) {
+  Table r = tab_make(k - 1);
+  unsigned na = 0;
+  for (unsigned a = 0; a < (1u << k); ++a) {
+    if ((((a >> j) & 1u) != 0u) != v) continue;
+    tab_set(r, na, tab_bit(t, a));
+    ++na;
+  }
+  return r;
+}
+
 // drop variables the table does not depend on; returns the reduced table, edits vars
-inline uint64_t reduce_support(uint64_t lut, std::vector<int>& vars) {
+inline Table reduce_support(Table lut, std::vector<int>& vars) {
   for (int j = (int)vars.size() - 1; j >= 0; --j) {
     const int k = (int)vars.size();
-    bool depends = false;
-    for (unsigned a = 0; a < (1u << k); ++a)
-      if (!((a >> j) & 1u) && (((lut >> a) ^ (lut >> (a | (1u << j)))) & 1ull)) depends = true;
-    if (depends) continue;
-    uint64_t nl = 0;
-    unsigned na = 0;
-    for (unsigned a = 0; a < (1u << k); ++a) {
-      if ((a >> j) & 1u) continue;
-      nl |= ((lut >> a) & 1ull) << na;
-      ++na;
-    }
-    lut = nl;
+    Table c0 = tab_cofactor(lut, k, j, false);
+    if (c0 != tab_cofactor(lut, k, j, true)) continue;
+    lut = c0;
     vars.erase(vars.begin() + j);
   }
   return lut;
 }
 
-inline Expr synth(uint64_t lut, std::vector<int> vars) {
+inline bool tab_complementary(const Table& a, const Table& b, int k) {
+  for (unsigned x = 0; x < (1u << k); ++x)
+    if (tab_bit(a, x) == tab_bit(b, x)) return false;
+  return true;
+}
+
+inline Expr synth(Table lut, std::vector<int> vars) {
   lut = reduce_support(lut, vars);
   const int k = (int)vars.size();
-  if (k == 0) return {(lut & 1ull) ? "0xFFFFFFFFu" : "0u", 0};
-  if (k == 1) return (lut & 3ull) == 2ull ? Expr{plane(vars[0]), 0} : Expr{"(~" + plane(vars[0]) + ")", 1};
+  if (k == 0) return {(lut[0] & 1ull) ? "0xFFFFFFFFu" : "0u", 0};
+  if (k == 1) return (lut[0] & 3ull) == 2ull ? Expr{plane(vars[0]), 0} : Expr{"(~" + plane(vars[0]) + ")", 1};
   if (k <= 3) {
     unsigned imm = 0;
     for (unsigned t = 0; t < 8; ++t) {
       const unsigned a = (t >> 2) & 1u, b = (t >> 1) & 1u, c = t & 1u;
       const unsigned idx = a | (b << 1) | (k >= 3 ? (c << 2) : 0u);
-      imm |= (unsigned)((lut >> idx) & 1ull) << t;
+      imm |= (unsigned)((lut[0] >> idx) & 1ull) << t;
     }
     char buf[160];
     snprintf(buf, sizeof(buf), "lop3<0x%02X>(%s, %s, %s)", imm, plane(vars[0]).c_str(), plane(vars[1]).c_str(),
              plane(vars[k >= 3 ? 2 : 0]).c_str());
     return {buf, 1};
   }
-  // Shannon expansion on the variable that gives the cheapest pair of cofactors
-  Expr best{"", 1 << 30};
-  for (int j = 0; j < k; ++j) {
-    uint64_t lo = 0, hi = 0;
-    unsigned na = 0;
-    for (unsigned a = 0; a < (1u << k); ++a) {
-      if ((a >> j) & 1u) continue;
-      lo |= ((lut >> a) & 1ull) << na;
-      hi |= ((lut >> (a | (1u << j))) & 1ull) << na;
-      ++na;
+  // Shannon expansion.  Up to 6 variables: on the variable that gives the cheapest pair of cofactors (exhaustive).
+  // Beyond: on the variable whose cofactors depend on the fewest variables together (an XOR decomposition first),
+  // no search -- the cofactors of real rule tables (sums of products) lose variables quickly.
+  std::vector<int> cands;
+  if (k <= 6) {
+    for (int j = 0; j < k; ++j) cands.push_back(j);
+  } else {
+    int best_j = 0, best_score = 1 << 30;
+    for (int j = 0; j < k; ++j) {
+      std::vector<int> r0(vars), r1(vars);
+      r0.erase(r0.begin() + j);
+      r1.erase(r1.begin() + j);
+      const Table c0 = tab_cofactor(lut, k, j, false), c1 = tab_cofactor(lut, k, j, true);
+      int score;
+      if (tab_complementary(c0, c1, k - 1)) {
+        reduce_support(c0, r0);
+        score = (int)r0.size() - k;  // one subtree instead of two
+      } else {
+        reduce_support(c0, r0);
+        reduce_support(c1, r1);
+        score = (int)r0.size() + (int)r1.size();
+      }
+      if (score < best_score) best_score = score, best_j = j;
     }
+    cands.push_back(best_j);
+  }
+  Expr best{"", 1 << 30};
+  for (int j : cands) {
+    const Table lo = tab_cofactor(lut, k, j, false), hi = tab_cofactor(lut, k, j, true);
     std::vector<int> rest(vars);
     rest.erase(rest.begin() + j);
-    const uint64_t full = (k - 1 >= 6) ? ~0ull : ((1ull << (1u << (k - 1))) - 1ull);
     Expr cand;
-    if ((lo ^ hi) == full) {
+    if (tab_complementary(lo, hi, k - 1)) {
       const Expr e0 = synth(lo, rest);
       cand = {"(" + e0.s + " ^ " + plane(vars[j]) + ")", e0.cost + 1};
     } else {
@@ -345,7 +398,7 @@ inline void generate_parts(const GenNet& g, std::string& u) {
     for (int i = 0; i < N; ++i) {
       if (part[i] != q) continue;
       for (const GenFunc& f : g.funcs[i]) {
-        std::vector<int> vars(f.in, f.in + f.arity);
+        std::vector<int> vars(f.in);
         reduce_support(f.lut, vars);
         for (int v : vars)
           if (std::find(used.begin(), used.end(), v) == used.end()) used.push_back(v);
@@ -362,11 +415,11 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       snprintf(buf, sizeof(buf), "    {  // gene %d: %d predictor(s)\n", i, K);
       u += buf;
       std::vector<std::string> names;
-      std::vector<std::pair<uint64_t, std::vector<int>>> seen;
+      std::vector<std::pair<Table, std::vector<int>>> seen;
       for (int k = 0; k < K; ++k) {
         const GenFunc& f = g.funcs[i][k];
-        std::vector<int> vars(f.in, f.in + f.arity);
-        const uint64_t red = reduce_support(f.lut, vars);
+        std::vector<int> vars(f.in);
+        const Table red = reduce_support(f.lut, vars);
         int same = -1;
         for (size_t z = 0; z < seen.size(); ++z)
           if (seen[z].first == red && seen[z].second == vars) same = (int)z;
@@ -377,7 +430,7 @@ inline void generate_parts(const GenNet& g, std::string& u) {
           continue;
         }
         names.push_back(buf);
-        const Expr e = synth(f.lut, std::vector<int>(f.in, f.in + f.arity));
+        const Expr e = synth(f.lut, f.in);
         u += "      const uint32_t " + std::string(buf) + " = " + e.s + ";\n";
       }
       std::string val;
@@ -467,7 +520,7 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
     for (int i = 0; i < N; ++i) {
       if (owner[i] != q) continue;
       for (const GenFunc& f : g.funcs[i]) {
-        std::vector<int> vars(f.in, f.in + f.arity);
+        std::vector<int> vars(f.in);
         reduce_support(f.lut, vars);
         for (int v : vars)
           if (std::find(used.begin(), used.end(), v) == used.end()) used.push_back(v);
@@ -484,11 +537,11 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
       snprintf(buf, sizeof(buf), "    {  // gene %d: %d predictor(s)\n", i, K);
       u += buf;
       std::vector<std::string> names;
-      std::vector<std::pair<uint64_t, std::vector<int>>> seen;
+      std::vector<std::pair<Table, std::vector<int>>> seen;
       for (int k = 0; k < K; ++k) {
         const GenFunc& f = g.funcs[i][k];
-        std::vector<int> vars(f.in, f.in + f.arity);
-        const uint64_t red = reduce_support(f.lut, vars);
+        std::vector<int> vars(f.in);
+        const Table red = reduce_support(f.lut, vars);
         int same = -1;
         for (size_t z = 0; z < seen.size(); ++z)
           if (seen[z].first == red && seen[z].second == vars) same = (int)z;
@@ -499,7 +552,7 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
           continue;
         }
         names.push_back(buf);
-        const Expr e = synth(f.lut, std::vector<int>(f.in, f.in + f.arity));
+        const Expr e = synth(f.lut, f.in);
         u += "      const uint32_t " + std::string(buf) + " = " + e.s + ";\n";
       }
       const std::string dst = "o[" + std::to_string(i * 32) + "]";

@@ -190,7 +190,35 @@ def _mixed_network():
     return genes, fs
 
 
-@pytest.mark.parametrize("name", NETS + ("mixed",))
+def _wide_network():
+    """Predictors of 7..12 inputs (multi-word truth tables, Shannon-expanded LOP3 trees): rule-like sums of products,
+    a parity (XOR decomposition), a dense random table, next to narrow ones."""
+    rng = np.random.default_rng(77)
+    genes = ["w%d" % i for i in range(14)]
+
+    def sop(ins, minterms):
+        return " | ".join("( " + " & ".join(("%s" if (a >> j) & 1 else "~ %s") % genes[ins[j]] for j in range(len(ins))) + " )"
+                          for a in minterms)
+
+    fs = []
+    for i in range(14):
+        ar = [7, 8, 9, 10, 11, 12, 3, 7, 12, 2, 8, 9, 10, 1][i]
+        ins = sorted(rng.choice(14, size=ar, replace=False).tolist())
+        if i == 7:     # parity of 7 inputs
+            fs.append([sop(ins, [a for a in range(128) if bin(a).count("1") & 1])])
+        elif i == 10:  # dense random table of 8 inputs
+            fs.append([sop(ins, [a for a in range(256) if rng.integers(0, 2)])])
+        elif i == 11:  # two wide predictors under one selection slot
+            fs.append([sop(ins, rng.integers(0, 1 << ar, size=6).tolist()), " & ".join(genes[j] for j in ins[:8])])
+        elif i == 12:  # an OR of 10 inputs, an AND of 3, a wide sum of products
+            fs.append([" | ".join(genes[j] for j in ins), " & ".join(genes[j] for j in ins[:3]),
+                       sop(ins, rng.integers(0, 1 << ar, size=4).tolist())])
+        else:
+            fs.append([sop(ins, rng.integers(0, 1 << ar, size=7).tolist())])
+    return genes, fs
+
+
+@pytest.mark.parametrize("name", NETS + ("mixed", "wide"))
 def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     """Compile the generated net_gen.cuh / net_update.inc with g++: the predictor trees of both kernels against the
     truth tables on random bit-planes, and the generated selection draw (pbn_draw_group, with csrc/philox.cuh compiled
@@ -199,8 +227,8 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     from oracle import pbn_oracle as O
     from helpers import oracle_net
     from pbn_rl_b200.vec_env import jit_source
-    if name == "mixed":
-        genes, fs = _mixed_network()
+    if name in ("mixed", "wide"):
+        genes, fs = _mixed_network() if name == "mixed" else _wide_network()
         net = PBNNetwork.from_expressions(genes, fs)
         onet = O.OracleNetwork(genes, [[(f, 1.0 / len(g)) if isinstance(f, str) else f for f in g] for g in fs])
     else:

@@ -51,12 +51,13 @@ def test_bb33_bnet_known_answer(kernel):
     assert _digest(out, 33) == want["sha256"]
 
 
-def test_wide_predictor_known_answer():
+@pytest.mark.parametrize("kernel", ["auto", "scalar"])
+def test_wide_predictor_known_answer(kernel):
     from pbn_rl_b200 import PBNNetwork
     want = _golden("control14.json")
     net = PBNNetwork.from_logic_functions(want["genes"], want["logic_functions"])
-    out, k = _step_fixed_inputs(net, "auto")
-    assert k == "scalar"                      # wide predictors run on the general kernel
+    out, k = _step_fixed_inputs(net, kernel)
+    assert k == ("sliced" if kernel == "auto" else "scalar")   # 8-input predictor: Shannon-expanded LOP3 tree
     assert _digest(out, 14) == want["sha256"]
     assert [[str(a), str(b)] for a, b in zip(_inputs(14)[:8], out[:8])] == want["first_rows"]
 

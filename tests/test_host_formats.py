@@ -95,12 +95,18 @@ def test_control_network_with_wide_predictor():
     assert int(arr["func_arity"].max()) == 8 and arr["wide_lut"].shape == (4,)
 
 
-def test_wide_networks_are_not_sliced_but_build():
-    """The C library accepts wide predictors (scalar kernel) and refuses to specialise them."""
+def test_wide_networks_specialise_up_to_12_inputs():
+    """Predictors of 7..12 inputs get Shannon-expanded LOP3 trees in the generated source (bit-sliced kernels);
+    beyond 12 inputs the library refuses to specialise (thread-per-env kernel only)."""
     from pbn_rl_b200 import PBNNetwork, _cabi
-    from pbn_rl_b200.vec_env import precompile
+    from pbn_rl_b200.vec_env import jit_source
     want = _golden("control14.json")
     net = PBNNetwork.from_logic_functions(want["genes"], want["logic_functions"])
+    src = jit_source(net)
+    assert "pbn_update_part" in src and "bmux(" in src
+    genes = ["v%d" % i for i in range(14)]
+    big = PBNNetwork.from_expressions(genes, [[" & ".join(genes[:13])]] + [[g] for g in genes[1:]])
+    assert big.max_arity == 13
     with pytest.raises(_cabi.PbnError) as ei:
-        precompile(net)
-    assert "6 inputs" in str(ei.value)
+        jit_source(big)
+    assert "12 inputs" in str(ei.value)
