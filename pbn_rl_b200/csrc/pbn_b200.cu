@@ -199,6 +199,15 @@ static SlicedSmemLayout sliced_smem_layout(const NetParams& n, int W, int warps,
     L.aoffs_off = o;
     o += (uint32_t)(n.n_attr + 1) * 4u;
     o = (o + 15u) & ~15u;
+  } else if (n.n_attr > 0 && n.attr_simple == 0u && n.ahash_tags != nullptr && n.awild_any == 0u && n.r_wrong == 0.0f &&
+             (uint32_t)n.n_attr * ((uint32_t)W * 16u + 4u) <= 16u * 1024u) {
+    L.singles_in_smem = 1u;
+    L.acare_off = o;
+    o += (uint32_t)n.n_attr * W * 16u;
+    L.aval_off = o;
+    L.aoffs_off = o;
+    o += (uint32_t)n.n_attr * 4u;
+    o = (o + 15u) & ~15u;
   }
   L.scratch_off = o;
   (void)warps;
@@ -613,7 +622,9 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
       wild_off[a + 1] = (int32_t)wild_entry.size();
     }
     size_t cap = 64;
-    while (cap < 4 * exact.size() + 2) cap *= 2;   // at most a quarter full: the first probe usually decides
+    // at most 1/16 full (1/4 beyond 4 M slots): the step kernels decide a membership test inline when the first
+    // probe finds an empty slot, and every occupied one sends the whole warp through the out-of-line probe loop
+    while (cap < 4 * exact.size() + 2 || (cap < 16 * exact.size() + 2 && cap < (1u << 22))) cap *= 2;
     std::vector<unsigned long long> tags(cap, 0ull);
     std::vector<uint64_t> states(cap * W, 0ull);
     std::vector<int32_t> owner(cap, -1);

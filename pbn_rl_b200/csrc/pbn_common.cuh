@@ -119,6 +119,10 @@ struct SlicedSmemLayout {
   uint32_t surv_off, rew_off, aoffs_off, acare_off, aval_off, scratch_off, total;
   uint32_t stage_state_off, stage_act_off, mbar_off;  // TMA staging of a tile's state / action bytes
   uint32_t attractors_in_smem;
+  // pbn_step_sliced_gen with the hash set: per attractor its FIRST entry ([care | value] at acare_off, as in the
+  // single-state layout) and its number of entries (at aoffs_off) -- single-state targets are then tested in shared
+  // memory and only the envs whose target is a larger attractor probe the hash set
+  uint32_t singles_in_smem;
 };
 
 // Dynamic shared-memory layout of the plane-resident kernel's attractor tables (byte offsets; the fixed part of

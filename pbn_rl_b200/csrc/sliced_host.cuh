@@ -216,13 +216,17 @@ inline int n_sel_slots(const GenNet& g) {
 inline int scratch_words(const GenNet& g) {
   const int NW = (g.n_genes + 31) / 32;
   // + pre-drawn perturbation events: one packed word per thread (8 N < 255 slots), else two
-  return 2 * NW * 32 * 32 + 2 * n_sel_slots(g) * 32 + 8 + 128 * (8 * g.n_genes < 255 ? 1 : 2);
+  // + the model-A event mask of the column (32 words)
+  return 2 * NW * 32 * 32 + 2 * n_sel_slots(g) * 32 + 8 + 128 * (8 * g.n_genes < 255 ? 1 : 2) + 32;
 }
 
 inline int sliced_threads(const GenNet&) { return 128; }  // four warps per 1024-env tile
 inline int sliced_min_blocks(const GenNet& g) {
   if (const char* env = getenv("PBN_B200_MIN_BLOCKS")) return atoi(env);  // tuning experiments
-  return g.n_genes <= 32 ? 8 : (g.n_genes <= 64 ? 4 : 2);
+  // one-word states: 7 CTAs per SM (72 registers) -- a 2^20-env step is 1024 tiles on 148 SMs, 6.9 per SM: with 8 slots
+  // the CTAs of the next launch pile up on the SMs that finish first (5..8 per SM) and the slowest SM sets the period
+  // (measured 16.5 -> 16.1 us per step)
+  return g.n_genes <= 32 ? 7 : (g.n_genes <= 64 ? 4 : 2);
 }
 
 
@@ -509,8 +513,9 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
   u += "__device__ __constant__ unsigned char kSelGene[] = {" + tg + "};\n";
   u += "__device__ __constant__ unsigned char kSelK[] = {" + tk + "};\n\n";
   u += "// x: input planes, o: out planes, sel0/sel1: selection planes; all [row][lane], lane folded in\n";
+  u += "// keep: envs of the column (bits) that take their input value instead of the update (perturbation model A)\n";
   u += "__device__ __forceinline__ void pbn_update_part(uint32_t w, const uint32_t* x, uint32_t* o,\n"
-       "                                                const uint32_t* sel0, const uint32_t* sel1) {\n";
+       "                                                const uint32_t* sel0, const uint32_t* sel1, uint32_t keep = 0u) {\n";
   u += "#define X(g) x[(g) * 32]\n";
   for (int q = 0; q < 4; ++q) {
     snprintf(buf, sizeof(buf), "  %sif (w == %du) {\n", q ? "else " : "", q);
@@ -519,6 +524,7 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
     std::vector<int> used;
     for (int i = 0; i < N; ++i) {
       if (owner[i] != q) continue;
+      if (std::find(used.begin(), used.end(), i) == used.end()) used.push_back(i);   // the gene's own plane: keep-mux
       for (const GenFunc& f : g.funcs[i]) {
         std::vector<int> vars(f.in);
         reduce_support(f.lut, vars);
@@ -555,18 +561,18 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
         const Expr e = synth(f.lut, f.in);
         u += "      const uint32_t " + std::string(buf) + " = " + e.s + ";\n";
       }
-      const std::string dst = "o[" + std::to_string(i * 32) + "]";
+      const std::string dst = "o[" + std::to_string(i * 32) + "] = bmux(keep, " + plane(i) + ", ";
       if (K == 1) {
-        u += "      " + dst + " = " + names[0] + ";\n    }\n";
+        u += "      " + dst + names[0] + ");\n    }\n";
         continue;
       }
       snprintf(buf, sizeof(buf), "      const uint32_t s0 = sel0[%d], s1 = sel1[%d];\n", slot_of[i] * 32, slot_of[i] * 32);
       u += buf;
-      if (K == 2) u += "      (void)s1;\n      " + dst + " = bmux(s0, " + names[1] + ", " + names[0] + ");\n";
-      if (K == 3) u += "      " + dst + " = bmux(s1, " + names[2] + ", bmux(s0, " + names[1] + ", " + names[0] + "));\n";
+      if (K == 2) u += "      (void)s1;\n      " + dst + "bmux(s0, " + names[1] + ", " + names[0] + "));\n";
+      if (K == 3) u += "      " + dst + "bmux(s1, " + names[2] + ", bmux(s0, " + names[1] + ", " + names[0] + ")));\n";
       if (K == 4)
-        u += "      " + dst + " = bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " +
-             names[0] + "));\n";
+        u += "      " + dst + "bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " +
+             names[0] + ")));\n";
       u += "    }\n";
     }
     if (q == 0)

@@ -67,7 +67,8 @@ constexpr int kScrSel1 = kScrSel0 + PBN_NSEL * 32;   // selection planes s1     
 constexpr int kScrStat = kScrSel1 + PBN_NSEL * 32;   // 8 block-level statistics counters
 constexpr int kEvWords = (8 * PBN_N < 255) ? 1 : 2;  // packed words of pre-drawn perturbation events per thread
 constexpr int kScrEv = kScrStat + 8;                 // pre-drawn perturbation events              [kEvWords][128]
-constexpr int kScrWords = kScrEv + 128 * kEvWords;   // total (must equal PBN_SCRATCH_WORDS)
+constexpr int kScrPm = kScrEv + 128 * kEvWords;      // model A: envs with a perturbation event, byte w of word [lane] = rows 8w..8w+7
+constexpr int kScrWords = kScrPm + 32;               // total (must equal PBN_SCRATCH_WORDS)
 // Pre-drawn perturbation events of a thread: ascending slot positions, kEvBits each, packed into kEvWords words;
 // all-ones = no event; an all-zero first word (never a valid ascending list) = more than kEvCap events: phase D
 // redoes the walk.
@@ -241,30 +242,38 @@ namespace pbn {
 // programmatic dependent launch, else behind the tile's TMA copy -- and phase D only applies them: the
 // Philox block and the dependent table look-ups of the geometric skip are a pure latency chain
 // (≈2 us per tile when it sat in D).  One packed word per thread (see kEvBits).
-__device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* ev, uint64_t gid, uint64_t step_ctr, uint32_t w) {
+// rows8 (step kernel, perturbation model A): receives the 8-bit mask of this thread's rows with at least one event --
+// complete even when the packed list overflows (the walk then goes on for the mask alone).
+__device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* ev, uint64_t gid, uint64_t step_ctr, uint32_t w,
+                                                 unsigned char* rows8 = nullptr) {
   uint32_t word[kEvWords];
 #pragma unroll
   for (int q = 0; q < kEvWords; ++q) word[q] = 0xFFFFFFFFu;   // no event
+  uint32_t m8 = 0u;
   if (n.pert_rng && n.pert_mode != PBN_PERT_NONE) {
+    const bool whole_walk = rows8 != nullptr && n.pert_mode == PBN_PERT_A;
     const uint32_t s_last = kSurvTable[kSlots];
     Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
     int pos = -1;
-    bool done = false;
 #pragma unroll 1
-    for (uint32_t k = 0; k <= kEvCap; ++k) {   // up to kEvCap events + the terminating draw
-      if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + (k >> 2), n.rk);   // rare
+    for (uint32_t k = 0;; ++k) {   // up to kEvCap events are packed
+      if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((k >> 2) & 63u), n.rk);   // rare
       const uint32_t u = pick4(blk, k & 3u);
       pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
-      if (pos >= kSlots) { done = true; break; }
+      if (pos >= kSlots) break;
+      m8 |= 1u << ((uint32_t)pos & 7u);
       if (k < kEvCap) {
         const uint32_t sh = kEvBits * (k % kEvPerWord);
 #pragma unroll
         for (int q = 0; q < kEvWords; ++q)
           if ((uint32_t)q == k / kEvPerWord) word[q] = (word[q] & ~(kEvMask << sh)) | ((uint32_t)pos << sh);
+      } else {
+        word[0] = kPreEvOverflow;              // more than kEvCap events: the consumer redoes the walk
+        if (!whole_walk) break;
       }
     }
-    if (!done) word[0] = kPreEvOverflow;       // more than kEvCap events: phase D redoes the walk
   }
+  if (rows8 != nullptr) *rows8 = (unsigned char)m8;
 #pragma unroll
   for (int q = 0; q < kEvWords; ++q) ev[128 * q] = word[q];
 }
@@ -272,6 +281,7 @@ __device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* e
 
 // Stage the small read-only tables into shared memory (first tile of a CTA, after its global loads
 // were issued; everything staged here is first read after block barrier (1)).
+template <bool ASMEM>
 __device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSmemLayout& L, uint32_t* s_surv,
                                              float* s_rew, int32_t* s_aoffs, uint32_t* s_aent, uint32_t* s_stat) {
   (void)s_surv;  // the survival table is read through the read-only path where needed
@@ -289,6 +299,13 @@ __device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSme
       s_aent[en * 2 * kNW + kNW + wd] = (uint32_t)(n.attr_val[en * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
     }
     for (int i = threadIdx.x; i <= n.n_attr; i += blockDim.x) s_aoffs[i] = n.attr_offset[i];
+  } else if (!ASMEM && L.singles_in_smem) {   // first entry + entry count of every attractor (see SlicedSmemLayout)
+    for (int i = threadIdx.x; i < n.n_attr * kNW; i += blockDim.x) {
+      const int at = i / kNW, wd = i - at * kNW, en = n.attr_offset[at];
+      s_aent[at * 2 * kNW + wd] = (uint32_t)(n.attr_care[en * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+      s_aent[at * 2 * kNW + kNW + wd] = (uint32_t)(n.attr_val[en * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
+    }
+    for (int i = threadIdx.x; i < n.n_attr; i += blockDim.x) s_aoffs[i] = n.attr_offset[i + 1] - n.attr_offset[i];
   }
 }
 
@@ -427,17 +444,18 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   unsigned int nsm;
   asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
   const bool c1_first = !pre_drawn && !planes_given && ((tile / (int64_t)nsm) & 1) == 0;
-  if (stage && !c1_first) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);
+  if (stage && !c1_first) stage_tables<ASMEM>(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);
   phase_stamp(a, 2);
   const uint64_t gid = (uint64_t)(((a.env_offset >> 10) + tile) * 32 + lane);
 #if !PBN_INJECTED
-  if (!ev_drawn) draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w);  // behind the TMA copy
+  if (!ev_drawn)   // behind the TMA copy
+    draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w, reinterpret_cast<unsigned char*>(scr + kScrPm) + 4u * lane + w);
 #endif
   // ---- C1 (even tiles: here, hiding the load latency; odd tiles: after B, so that neighbouring
   //      CTAs of the single wave are in different phases and share the SM's issue slots better)
   if (c1_first) {
     draw_selection_planes<FULL>(a, n, sel0, sel1, gid, step_ctr, e0, w);
-    if (stage) stage_tables(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);  // first read after barrier (1)
+    if (stage) stage_tables<ASMEM>(n, L, s_surv, s_rew, s_aoffs, s_aent, s_stat);  // first read after barrier (1)
   }
 
   phase_stamp(a, 3);
@@ -492,6 +510,51 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       }
     }
   }
+  uint32_t npert = 0u;
+#if !PBN_INJECTED
+  // Perturbation model A with the kernel's own events (a perturbed env keeps s1 and gets its flips, the update does
+  // not apply to it): the flips go into this thread's own s1 rows right here -- the predictors see them only in envs
+  // whose function values phase C discards again (pbn_update_part's mux on the event mask) -- so the next state comes
+  // out of the ordinary plane pipeline and phase D has nothing to do.
+  const bool pert_in_rows = n.pert_rng && n.pert_mode == PBN_PERT_A;   // block-uniform
+  if (pert_in_rows) {
+    auto flip_row = [&](uint32_t pos) {
+      const uint32_t g = pos >> 3, ib = pos & 7u;
+      rows[((g >> 5) * 32u + 8u * w + ib) * 32u] ^= 1u << (g & 31u);
+      if (FULL || e0 + 128 * (2 * (int)w + (int)(ib >> 2)) + (int)(ib & 3u) < E) ++npert;   // statistics count real envs only
+    };
+    uint32_t evw[kEvWords];
+#pragma unroll
+    for (int q = 0; q < kEvWords; ++q) evw[q] = scr[kScrEv + 128 * q + threadIdx.x];
+    if (evw[0] != kPreEvOverflow) {
+#pragma unroll
+      for (int q = 0; q < kEvWords; ++q) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < kEvPerWord; ++k) {
+          const uint32_t pos = (evw[q] >> (kEvBits * k)) & kEvMask;
+          if (pos == kEvMask) break;
+          flip_row(pos);
+        }
+      }
+    } else {   // more events than the packed list holds (large p): walk the sub-stream again
+      const uint32_t s_last = kSurvTable[kSlots];
+      uint32_t pert_next = 0u;
+      Philox4 pert_blk = {0u, 0u, 0u, 0u};
+      int pos = -1;
+      while (true) {
+        if ((pert_next & 3u) == 0u)
+          pert_blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((pert_next >> 2) & 63u), n.rk);
+        const uint32_t u = pick4(pert_blk, pert_next & 3u);
+        ++pert_next;
+        pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
+        if (pos >= kSlots) break;
+        flip_row((uint32_t)pos);
+      }
+    }
+  }
+#else
+  constexpr bool pert_in_rows = false;
+#endif
   phase_stamp(a, 4);
   __syncthreads();  // (1) all 32 s1 rows of the column are in scratch
   phase_stamp(a, 5);
@@ -518,7 +581,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   __syncthreads();  // (2) all input planes (and selection planes) are in scratch; S1 rows are dead
 
   // ---- C2. synchronous update of this warp's genes: generated LOP3 trees -> OPL planes ----------
-  pbn_update_part(w, pl, opl, sel0, sel1);
+  pbn_update_part(w, pl, opl, sel0, sel1, pert_in_rows ? scr[kScrPm + lane] : 0u);
   phase_stamp(a, 7);
   __syncthreads();  // (3) all out planes are in scratch
   phase_stamp(a, 8);
@@ -564,11 +627,9 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 9);
-  cta_stamp(a, 3);
   // ---- D. perturbation (row domain, sparse) ---------------------------------------------------------
-  uint32_t npert = 0u;
   const int pert_mode = n.pert_mode;  // block-uniform
-  if (pert_mode != PBN_PERT_NONE) {
+  if (pert_mode != PBN_PERT_NONE && !pert_in_rows) {
 #if PBN_INJECTED
     if (a.pert_mask != nullptr) {
 #pragma unroll
@@ -595,12 +656,9 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
 #else
     if (n.pert_rng) {
       // this warp's own event sub-stream: slots gene*8 + row over its 8 rows
-      uint32_t M = 0u;
-      auto apply_event = [&](uint32_t pos) {
+      auto apply_event = [&](uint32_t pos) {   // models B and C (model A: see A1)
         const uint32_t g = pos >> 3, ib = pos & 7u;
         const uint32_t m = 1u << (g & 31u), gw = g >> 5;
-        const bool first = !((M >> ib) & 1u);
-        M |= 1u << ib;
         if (FULL || e0 + 128 * (2 * (int)w + (int)(ib >> 2)) + (int)(ib & 3u) < E) ++npert;   // statistics count real envs only
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -608,10 +666,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
           for (int wd = 0; wd < kNW; ++wd) {
             const bool here = (uint32_t)i == ib;
             const uint32_t mm = (here && (uint32_t)wd == gw) ? m : 0u;
-            if (pert_mode == PBN_PERT_A) {
-              if (here && first) o[i][wd] = rows[(wd * 32 + 8 * (int)w + i) * 32];
-              o[i][wd] ^= mm;
-            } else if (pert_mode == PBN_PERT_B) {
+            if (pert_mode == PBN_PERT_B) {
               o[i][wd] ^= mm;
             } else if (here) {
               o[i][wd] = bmux(mm, ~rows[(wd * 32 + 8 * (int)w + i) * 32], o[i][wd]);
@@ -663,11 +718,21 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   constexpr bool fast_attr = ASMEM;
   // hash set without wildcard entries and without the wrong-attractor term: first probes of the 8 envs up front
   const bool hash_first = !fast_attr && !simple && n.ahash_tags != nullptr && n.awild_any == 0u && n.r_wrong == 0.0f;
+  // ... and single-state targets are tested against their entry in shared memory, no probe at all
+  const bool singles = !fast_attr && L.singles_in_smem != 0u;
   unsigned long long htag[8], hcur[8];
   uint32_t hslot[8];
+  uint32_t single = 0u;   // bit i: env i's target is a single-state attractor
+  if (singles) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (tg[i] < n_attr && s_aoffs[tg[i]] == 1) single |= 1u << i;
+  }
   if (hash_first) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      htag[i] = 0ull; hcur[i] = 0ull; hslot[i] = 0u;
+      if ((single >> i) & 1u) continue;
       uint64_t y64[kW64];
 #pragma unroll
       for (int wd = 0; wd < kW64; ++wd)
@@ -694,7 +759,14 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
           // round trips in flight together): an empty slot is a miss, a slot holding this state under this target
           // is a hit, anything else goes through the full probe sequence out of line.
           bool decided = false;
-          if (hash_first) {
+          if ((single >> i) & 1u) {
+            const uint32_t* ent = s_aent + tg[i] * (2 * kNW);
+            uint32_t diff = 0u;
+#pragma unroll
+            for (int wd = 0; wd < kNW; ++wd) diff |= (o[i][wd] & ent[wd]) ^ ent[kNW + wd];
+            hit = diff == 0u;
+            decided = true;
+          } else if (hash_first) {
             if (hcur[i] == 0ull) {
               decided = true;
             } else if (hcur[i] == htag[i] && n.ahash_attr[hslot[i]] == (int)tg[i]) {
@@ -797,7 +869,6 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   }
 
   phase_stamp(a, 11);
-  cta_stamp(a, 5);
   // ---- G. auto-reset of finished envs (sparse: scattered writes after the vector stores) ----------
   uint32_t D = (H | TR) & VALID;
   if (a.stats != nullptr) {
@@ -939,11 +1010,13 @@ __device__ __forceinline__ void step_sliced_body(const StepParams& p, const Slic
         pre_drawn = true;
       }
 #if !PBN_INJECTED
-      draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w);
+      draw_pert_events(n, scr + kScrEv + threadIdx.x, gid, step_ctr, w, reinterpret_cast<unsigned char*>(scr + kScrPm) + 4u * lane + w);
       ev_drawn = true;
 #endif
     }
+    cta_stamp(a, 5);   // (profile builds) pre-wait work done
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    cta_stamp(a, 3);   // (profile builds) the previous launch has completed
   }
   for (int64_t tile = first_tile; tile < n_tiles; tile += gridDim.x) {
     const bool full = (tile + 1) * 1024 <= a.n_envs;
