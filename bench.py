@@ -458,7 +458,8 @@ def run_gpu(args):
         "full_width_value": e2e_full, "full_width_d2h_bytes_per_step": e2e_env.host_bytes_per_step[1],
         "compact_value": e2e_compact, "compact_d2h_bytes_per_step": e2e_env.host_bytes_per_step_compact[1] if compact_ok else None,
         "transfer": "pbn_step_host: actions uploaded from pinned memory by the copy engine, results written "
-                    "by an export kernel straight into pinned host memory (zero-copy over PCIe), 2 chunks pipelined",
+                    "by an export kernel straight into pinned host memory (zero-copy over PCIe); packed form: 4 lanes "
+                    "(upload -> unpack -> step -> export per quarter of the batch), the whole step replayed as one captured CUDA graph",
         "numa": numa,
     }
     os.sched_setaffinity(0, affinity0)   # the CPU legs below use every host core again

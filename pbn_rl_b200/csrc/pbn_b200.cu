@@ -132,6 +132,22 @@ struct pbn_handle {
   // pbn_step_host: two copy streams + per-chunk events (created on first use)
   static constexpr int kMaxChunks = 16;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  static constexpr int kMaxLanes = 8;
+  cudaStream_t s_lane[kMaxLanes] = {};   // lanes 2.. of the packed path (lanes 0 and 1 are s_h2d and s_d2h)
+  // packed path with a device step counter: the whole step (uploads, unpack, step, export kernels of all lanes, counter
+  // update) is captured once per distinct argument set and replayed as one CUDA graph launch afterwards
+  struct HostGraph {
+    pbn_step_args a;
+    pbn_host_io io;
+    int lanes = 0, seen = 0;
+    uint64_t launches = 0, last_use = 0;
+    cudaGraphExec_t exec = nullptr;
+  };
+  static constexpr int kHostGraphs = 8;
+  HostGraph host_graph[kHostGraphs];
+  uint64_t host_graph_clock = 0;
+  cudaStream_t s_origin = nullptr;
+  cudaEvent_t ev_done = nullptr, ev_fork = nullptr;
   cudaEvent_t ev_entry = nullptr, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
 };
 
@@ -383,6 +399,13 @@ void pbn_destroy(pbn_handle* h) {
     }
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    for (cudaStream_t ls : h->s_lane)
+      if (ls) cudaStreamDestroy(ls);
+    for (auto& g : h->host_graph)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->s_origin) cudaStreamDestroy(h->s_origin);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
     for (int i = 0; i < pbn_handle::kMaxChunks; ++i) {
       if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -634,7 +657,7 @@ int pbn_update_attractors(pbn_handle* h, const int32_t* attr_offset, const uint6
     for (int e : exact) {
       const uint64_t* st = value + (size_t)e * W;
       const uint64_t tag = attr_tag(st, W);
-      size_t slot = (size_t)(mix64(tag) & (cap - 1));
+      size_t slot = attr_slot(tag, (uint32_t)(cap - 1));
       while (tags[slot] != 0ull) slot = (slot + 1) & (cap - 1);
       tags[slot] = tag;
       for (int w = 0; w < W; ++w) states[slot * W + w] = st[w];
@@ -899,50 +922,121 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
   // library stream, so nothing inside a lane needs an event, and PCIe (full duplex) carries lane 1's upload under
   // lane 0's results.  The lanes' step kernels run concurrently, so the launch-counting update of a device step
   // counter is not available here (host counter, or PDL sequences that advance it explicitly).
-  if (packed_only && !fused_packed && io->actions16 && io->n_chunks <= 0 && E >= (1 << 18) &&
-      (a->step_ctr_dev == nullptr || (a->flags & PBN_STEP_PDL))) {
-    const int64_t half = ((tiles + 1) / 2) * 1024;
-    PBN_CUDA(cudaEventRecord(h->ev_entry, stream));
-    cudaStream_t lane[2] = {h->s_h2d, h->s_d2h};
-    for (int c = 0; c < 2; ++c) {
-      const int64_t e0 = c * half, n = (c == 0) ? (E < half ? E : half) : E - half;
-      if (n <= 0) continue;
-      cudaStream_t S = lane[c];
-      PBN_CUDA(cudaStreamWaitEvent(S, h->ev_entry, 0));
-      PBN_CUDA(cudaMemcpyAsync(io->actions16_dev + e0, io->actions16 + e0, (size_t)n * 2, cudaMemcpyHostToDevice, S));
-      unpack_actions16_kernel<<<grid_for(h, n / 4 + 1, 256, 4), 256, 0, S>>>(io->actions16_dev + e0, io->actions_dev + e0 * h->net.bins, n);
-      PBN_CUDA(cudaGetLastError());
-      pbn_step_args s = *a;
-      s.state = a->state + e0 * h->W;
-      s.actions = io->actions_dev + e0 * h->net.bins;
-      if (a->target_id) s.target_id = a->target_id + e0;
-      if (a->source_id) s.source_id = a->source_id + e0;
-      if (a->t) s.t = a->t + e0;
-      if (a->reward) s.reward = a->reward + e0;
-      s.terminated = a->terminated + e0;
-      s.truncated = a->truncated + e0;
-      if (a->final_state) s.final_state = a->final_state + e0 * h->W;
-      s.env_offset = a->env_offset + e0;
-      s.n_envs = n;
-      s.flags = (a->flags & ~PBN_STEP_PDL) | PBN_STEP_NO_COUNT;
-      const int rc = step_common(h, &s, S, false);
-      if (rc != PBN_OK) return rc;
-      ExportArgs x{};
-      x.state64 = a->state + e0;
-      x.term = a->terminated + e0;
-      x.trunc = a->truncated + e0;
-      x.packed = zc_packed + e0;
-      x.n_envs = n;
-      export_kernel<<<16, 256, 0, S>>>(x);
-      PBN_CUDA(cudaGetLastError());
-      h->launches += 2;
-      PBN_CUDA(cudaEventRecord(h->ev_k[c], S));
-      PBN_CUDA(cudaStreamWaitEvent(stream, h->ev_k[c], 0));   // later work on the caller's stream sees the step
+  if (packed_only && !fused_packed && io->actions16 && io->n_chunks <= 0 && E >= (1 << 18)) {
+    // graph replay needs call-invariant arguments: a device counter (the host part of the step counter constant)
+    const bool graphable = a->step_ctr_dev != nullptr && getenv("PBN_B200_NO_HOST_GRAPH") == nullptr;
+    // measured on B200 / PCIe Gen5, 2^20 envs (scripts/host_lanes_probe.py): replayed graph 0.166 / 0.158 / 0.161 /
+    // 0.148 / 0.158 ms with 1 / 2 / 3 / 4 / 6 lanes; stream launches 0.175 / 0.169 / 0.167 / 0.173 / 0.189 ms
+    int lanes = graphable ? 4 : 2;
+    if (const char* env = getenv("PBN_B200_HOST_LANES")) lanes = atoi(env);
+    lanes = lanes < 1 ? 1 : (lanes > pbn_handle::kMaxLanes ? pbn_handle::kMaxLanes : lanes);
+    const int64_t per = ((tiles + lanes - 1) / lanes) * 1024;   // envs per lane: whole tiles
+    // a device step counter that the steps themselves advance (no PDL sequence): the lanes share one counter value
+    // (PBN_STEP_NO_COUNT) and one small launch adds 1 after they have joined
+    const bool own_count = a->step_ctr_dev != nullptr && !(a->flags & PBN_STEP_PDL) && !(a->flags & PBN_STEP_NO_COUNT);
+    if (!h->s_origin) {
+      PBN_CUDA(cudaStreamCreateWithFlags(&h->s_origin, cudaStreamNonBlocking));
+      PBN_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+      PBN_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     }
-    g_last_advance = nullptr;
-    if (a->step_ctr_dev && !(a->flags & PBN_STEP_PDL)) return fail(PBN_ERR_INVALID, "unreachable");
-    PBN_CUDA(cudaEventSynchronize(h->ev_k[0]));
-    if (E > half) PBN_CUDA(cudaEventSynchronize(h->ev_k[1]));
+    for (int c = 2; c < lanes; ++c)
+      if (!h->s_lane[c]) PBN_CUDA(cudaStreamCreateWithFlags(&h->s_lane[c], cudaStreamNonBlocking));
+    // everything of one step on the library's streams, forked from and joined into s_origin
+    auto enqueue = [&]() -> int {
+      PBN_CUDA(cudaEventRecord(h->ev_fork, h->s_origin));
+      for (int c = 0; c < lanes; ++c) {
+        const int64_t e0 = c * per, n = (E - e0 < per) ? E - e0 : per;
+        if (n <= 0) continue;
+        cudaStream_t S = c == 0 ? h->s_h2d : (c == 1 ? h->s_d2h : h->s_lane[c]);
+        PBN_CUDA(cudaStreamWaitEvent(S, h->ev_fork, 0));
+        PBN_CUDA(cudaMemcpyAsync(io->actions16_dev + e0, io->actions16 + e0, (size_t)n * 2, cudaMemcpyHostToDevice, S));
+        unpack_actions16_kernel<<<grid_for(h, n / 4 + 1, 256, 4), 256, 0, S>>>(io->actions16_dev + e0, io->actions_dev + e0 * h->net.bins, n);
+        PBN_CUDA(cudaGetLastError());
+        pbn_step_args s = *a;
+        s.state = a->state + e0 * h->W;
+        s.actions = io->actions_dev + e0 * h->net.bins;
+        if (a->target_id) s.target_id = a->target_id + e0;
+        if (a->source_id) s.source_id = a->source_id + e0;
+        if (a->t) s.t = a->t + e0;
+        if (a->reward) s.reward = a->reward + e0;
+        s.terminated = a->terminated + e0;
+        s.truncated = a->truncated + e0;
+        if (a->final_state) s.final_state = a->final_state + e0 * h->W;
+        s.env_offset = a->env_offset + e0;
+        s.n_envs = n;
+        s.flags = (a->flags & ~PBN_STEP_PDL) | PBN_STEP_NO_COUNT;
+        const int rc = step_common(h, &s, S, false);
+        if (rc != PBN_OK) return rc;
+        ExportArgs x{};
+        x.state64 = a->state + e0;
+        x.term = a->terminated + e0;
+        x.trunc = a->truncated + e0;
+        x.packed = zc_packed + e0;
+        x.n_envs = n;
+        export_kernel<<<16, 256, 0, S>>>(x);
+        PBN_CUDA(cudaGetLastError());
+        h->launches += 2;   // (+ the step kernel, counted by step_common)
+        PBN_CUDA(cudaEventRecord(h->ev_k[c], S));
+        PBN_CUDA(cudaStreamWaitEvent(h->s_origin, h->ev_k[c], 0));
+      }
+      if (own_count) {
+        advance_counter_kernel<<<1, 1, 0, h->s_origin>>>(a->step_ctr_dev, 1ull);
+        PBN_CUDA(cudaGetLastError());
+        h->launches += 1;
+      }
+      return PBN_OK;
+    };
+    PBN_CUDA(cudaEventRecord(h->ev_entry, stream));
+    PBN_CUDA(cudaStreamWaitEvent(h->s_origin, h->ev_entry, 0));
+    pbn_handle::HostGraph* slot = nullptr;
+    if (graphable) {
+      pbn_handle::HostGraph* lru = &h->host_graph[0];
+      for (auto& g : h->host_graph) {
+        if (g.seen && g.lanes == lanes && memcmp(&g.a, a, sizeof(*a)) == 0 && memcmp(&g.io, io, sizeof(*io)) == 0) slot = &g;
+        if (g.last_use < lru->last_use) lru = &g;
+      }
+      if (!slot) {
+        slot = lru;
+        if (slot->exec) cudaGraphExecDestroy(slot->exec);
+        *slot = pbn_handle::HostGraph{};
+        memcpy(&slot->a, a, sizeof(*a));
+        memcpy(&slot->io, io, sizeof(*io));
+        slot->lanes = lanes;
+      }
+      slot->last_use = ++h->host_graph_clock;
+    }
+    const uint64_t launches_before = h->launches;
+    if (slot && slot->exec) {
+      PBN_CUDA(cudaGraphLaunch(slot->exec, h->s_origin));
+      h->launches += slot->launches;
+    } else if (slot && slot->seen >= 1) {
+      // second call with these arguments (the first ran eagerly, so every kernel it needs is loaded): capture
+      cudaGraph_t graph = nullptr;
+      PBN_CUDA(cudaStreamBeginCapture(h->s_origin, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue();
+      const cudaError_t ce = cudaStreamEndCapture(h->s_origin, &graph);
+      if (rc != PBN_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess) return fail(PBN_ERR_CUDA, "pbn_step_host: graph capture failed: %s", cudaGetErrorString(ce));
+      const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        slot->exec = nullptr;
+        return fail(PBN_ERR_CUDA, "pbn_step_host: graph instantiation failed: %s", cudaGetErrorString(ie));
+      }
+      slot->launches = h->launches - launches_before;
+      PBN_CUDA(cudaGraphLaunch(slot->exec, h->s_origin));
+    } else {
+      const int rc = enqueue();
+      if (rc != PBN_OK) return rc;
+    }
+    if (slot) slot->seen += 1;
+    g_last_advance = own_count ? h : nullptr;
+    PBN_CUDA(cudaEventRecord(h->ev_done, h->s_origin));
+    PBN_CUDA(cudaStreamWaitEvent(stream, h->ev_done, 0));   // later work on the caller's stream sees the step
+    PBN_CUDA(cudaEventSynchronize(h->ev_done));
     return PBN_OK;
   }
   int64_t nc = io->n_chunks > 0 ? io->n_chunks : (E >= (1 << 18) ? 2 : 1);  // measured best on B200 / PCIe Gen5 (scripts/host_path_probe.py)

@@ -217,13 +217,17 @@ __host__ __device__ __forceinline__ uint64_t attr_tag(const uint64_t* s, int W) 
   return h == 0ull ? 1ull : h;
 }
 
+// Home slot of a fingerprint: its upper half (the fingerprint is a splitmix64 output -- mixing it a second time bought
+// nothing and cost the step kernels as much as the fingerprint itself).
+__host__ __device__ __forceinline__ uint32_t attr_slot(uint64_t tag, uint32_t mask) { return (uint32_t)(tag >> 32) & mask; }
+
 // env.in_target(state) through the hash set: is `s` a state of attractor `a`?  O(1) expected: one probe sequence over
 // the fully specified states (tag match confirmed on the state words and the attractor id) + the attractor's few
 // wildcard entries.  model_tester.py:602-616; bdq_model/__init__.py:182-184 (attractor sets that grow).
 template <int W>
 __device__ __forceinline__ bool in_attractor_hashed(const NetParams& n, int a, const uint64_t (&s)[W]) {
   const uint64_t tag = attr_tag(s, W);
-  uint32_t slot = (uint32_t)mix64(tag) & n.ahash_mask;
+  uint32_t slot = attr_slot(tag, n.ahash_mask);
   for (uint32_t probe = 0; probe <= n.ahash_mask; ++probe, slot = (slot + 1u) & n.ahash_mask) {
     const unsigned long long cur = n.ahash_tags[slot];
     if (cur == 0ull) break;
@@ -249,7 +253,7 @@ template <int W>
 __device__ __forceinline__ int attractor_of_hashed(const NetParams& n, const uint64_t (&s)[W]) {
   int best = n.n_attr;
   const uint64_t tag = attr_tag(s, W);
-  uint32_t slot = (uint32_t)mix64(tag) & n.ahash_mask;
+  uint32_t slot = attr_slot(tag, n.ahash_mask);
   for (uint32_t probe = 0; probe <= n.ahash_mask; ++probe, slot = (slot + 1u) & n.ahash_mask) {
     const unsigned long long cur = n.ahash_tags[slot];
     if (cur == 0ull) break;

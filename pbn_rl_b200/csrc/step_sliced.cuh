@@ -738,7 +738,7 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       for (int wd = 0; wd < kW64; ++wd)
         y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
       htag[i] = attr_tag(y64, kW64);
-      hslot[i] = (uint32_t)mix64(htag[i]) & n.ahash_mask;
+      hslot[i] = attr_slot(htag[i], n.ahash_mask);
       hcur[i] = n.ahash_tags[hslot[i]];
     }
   }

@@ -578,12 +578,24 @@ class VecPBNEnv:
         a = hb.get("args")
         if a is None:
             a = hb["args"] = self._args(None, None, True, rows=True)
-        a.step_ctr = self._pos if self.pdl else self.step_ctr
-        check(self.lib.pbn_step_host(self._h, C.byref(a), C.byref(io), self._stream()))
-        if self.step_ctr_dev is None:
-            self.step_ctr += 1
-        elif self.pdl:
-            self._pos += 1
+        if compact == "packed" and actions16 is not None and self.step_ctr_dev is not None and int(chunks) <= 0 \
+                and self.num_envs >= (1 << 18):
+            # lane form with a device counter: the library advances the counter itself and, the arguments being the
+            # same from call to call, replays the whole step as one captured graph
+            if self._pos:
+                self.advance_counter()
+            a.flags &= ~_cabi.STEP_PDL
+            a.step_ctr = self.step_ctr
+            check(self.lib.pbn_step_host(self._h, C.byref(a), C.byref(io), self._stream()))
+            if self.pdl:
+                a.flags |= _cabi.STEP_PDL
+        else:
+            a.step_ctr = self._pos if self.pdl else self.step_ctr
+            check(self.lib.pbn_step_host(self._h, C.byref(a), C.byref(io), self._stream()))
+            if self.step_ctr_dev is None:
+                self.step_ctr += 1
+            elif self.pdl:
+                self._pos += 1
         return hb["views_packed" if compact == "packed" else ("views_compact" if compact else "views")]
 
     @property

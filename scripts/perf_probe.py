@@ -74,6 +74,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--kernels", default="sliced")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--big-attractor", type=int, default=0, help="add one attractor of this many random states (hash-set membership)")
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--split", default="", help="'pipe': pbn_predraw on a side stream + pbn_step with pre-drawn planes; 'main' / 'draw': either kernel alone")
     ap.add_argument("--graph-steps", type=int, default=32)
@@ -83,6 +84,12 @@ def main():
     ap.add_argument("--p", type=float, default=0.001, help="perturbation probability of the 'full' row")
     args = ap.parse_args()
     net, attrs = bench.load_workload(args.net)
+    if args.big_attractor:
+        import numpy as np
+        from pbn_rl_b200 import AttractorSet
+        rng = np.random.default_rng(8192)
+        big = {tuple(int(v) for v in rng.integers(0, 2, size=net.n_genes)) for _ in range(args.big_attractor + 200)}
+        attrs = AttractorSet(list(attrs.attractors) + [sorted(big)[:args.big_attractor]], net.n_genes)
     W = net.n_words
     rows = [("full (p=%g, reset, stats)" % args.p, args.p, True, True, True),
             ("no perturbation", 0.0, True, True, True),

@@ -267,3 +267,44 @@ def test_step_host_matches_oracle(name, e):
         assert np.array_equal(out["terminated"], term) and np.array_equal(out["truncated"], trunc)
         state = nxt
     env.close()
+
+
+@pytest.mark.parametrize("mode", ["host_counter", "device_counter", "pdl"])
+def test_packed_lane_form_and_graph_replay_equal_step(mode):
+    """Large batches take the lane form of the packed path (each lane: upload -> unpack -> step -> export on its own
+    stream); with a device step counter the whole step is captured on the second call with the same arguments and
+    replayed as one graph launch from the third on.  Seven steps alternating two pinned action buffers must equal
+    pbn_step on a twin env, step for step (eager, capture and replay calls all occur)."""
+    import torch
+    name, e = "pbn28", (1 << 18) + 1024 + 7
+    kw = dict(auto_reset=True)
+    if mode != "host_counter":
+        kw.update(device_counter=True, pdl=(mode == "pdl"))
+    ref, dut = _mk(name, e, **kw), _mk(name, e, **kw)
+    for env in (ref, dut):
+        _seed_env(env, name, e, 11)
+    rng = np.random.default_rng(12)
+    bufs, acts = [], []
+    for k in range(2):
+        act = rng.integers(0, 29, size=(e, 3), dtype=np.uint8)
+        b = torch.empty((e,), dtype=torch.int16, pin_memory=True)
+        b.numpy().view(np.uint16)[...] = dut.pack_actions16(act)
+        bufs.append(b)
+        acts.append(torch.from_numpy(act).cuda())
+    launches0 = dut.launches
+    for step in range(7):
+        out = dut.step_host(None, compact="packed", actions16=bufs[step % 2])
+        ref.step(acts[step % 2])
+        if mode == "pdl":
+            ref.advance_counter()
+        torch.cuda.synchronize()
+        want = ref.state.cpu().numpy().astype(np.uint64)[:, 0].astype(np.uint32)
+        packed = out["packed"]
+        assert np.array_equal(packed & np.uint32((1 << 30) - 1), want), f"state at step {step}"
+        assert np.array_equal((packed >> np.uint32(30)) & np.uint32(1), ref.terminated.cpu().numpy().astype(np.uint32))
+        assert np.array_equal(packed >> np.uint32(31), ref.truncated.cpu().numpy().astype(np.uint32))
+    per_step = (dut.launches - launches0) / 7
+    # host counter: 2 lanes x (unpack, step, export); device counter: 4 lanes + the counter update
+    assert per_step == (13 if mode != "host_counter" else 6)
+    assert np.array_equal(dut.state.cpu().numpy(), ref.state.cpu().numpy())
+    ref.close(); dut.close()
