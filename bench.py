@@ -418,7 +418,7 @@ def run_gpu(args):
             if compact == "packed":
                 return e2e_env.step_host(None, compact="packed", actions16=host_actions16[i % 4])
             return e2e_env.step_host(host_actions[i % 4], compact=compact)
-        for i in range(3):
+        for i in range(12):   # warm-up: each of the 4 host buffers is seen three times (eager call, graph capture, replay)
             one(i)
         if world > 1:
             dist.barrier()
@@ -459,7 +459,7 @@ def run_gpu(args):
         "compact_value": e2e_compact, "compact_d2h_bytes_per_step": e2e_env.host_bytes_per_step_compact[1] if compact_ok else None,
         "transfer": "pbn_step_host: actions uploaded from pinned memory by the copy engine, results written "
                     "by an export kernel straight into pinned host memory (zero-copy over PCIe); packed form: 4 lanes "
-                    "(upload -> unpack -> step -> export per quarter of the batch), the whole step replayed as one captured CUDA graph",
+                    "(upload -> unpack -> step -> export per quarter of the batch), the whole step replayed as one CUDA graph (captured per host buffer during the warm-up calls)",
         "numa": numa,
     }
     os.sched_setaffinity(0, affinity0)   # the CPU legs below use every host core again

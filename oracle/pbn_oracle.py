@@ -581,13 +581,15 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
     full = np.uint64(0xFFFFFFFF)
     s0 = np.zeros((ng, n), dtype=np.uint64)
     s1 = np.zeros((ng, n), dtype=np.uint64)
+    s2 = np.zeros((ng, n), dtype=np.uint64)   # third selection plane: genes with 5..8 predictors
     slot_gene = [i for i, k in enumerate(ks) if k > 1]
     # SELECT: slot r (the r-th gene with K > 1) owns block (SELECT, r) = words x, y, z, w.  K=2: s0 = x; K=4: (s0, s1) =
     # (x, y); K=3: the pairs (x, y), (z, w) -- pair value 3 is rejected and replaced by the next pair.
     weighted = {}
     for i, k in enumerate(ks):
         thr = selection_thresholds(net.probs[i])[:-1]
-        weighted[i] = any(abs(t - int(np.floor((j + 1) / k * 4294967296.0 + 0.5))) > 2 for j, t in enumerate(thr))
+        # more than 4 predictors: always by threshold comparison (the pair-plane draw covers 2, 3 and 4)
+        weighted[i] = k > 4 or any(abs(t - int(np.floor((j + 1) / k * 4294967296.0 + 0.5))) > 2 for j, t in enumerate(thr))
     for r, i in enumerate(slot_gene):
         if weighted[i]:
             # arbitrary probabilities: a 32-bit uniform per env, bit 31 - j of the column's envs = word j of the blocks
@@ -606,6 +608,7 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
                     sel_b += (u32[b] >= np.uint64(t)).astype(np.uint64)
                 s0[:, i] |= (sel_b & np.uint64(1)) << np.uint64(b)
                 s1[:, i] |= ((sel_b >> np.uint64(1)) & np.uint64(1)) << np.uint64(b)
+                s2[:, i] |= ((sel_b >> np.uint64(2)) & np.uint64(1)) << np.uint64(b)
             continue
         x, y, z, w = (v.astype(np.uint64) for v in philox4x32(*_ctr(groups, step_ctr, KIND_SELECT, r), k0, k1))
         if ks[i] == 2:
@@ -617,7 +620,7 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
             s0[:, i] = (x & ~rj & full) | (z & rj)
             s1[:, i] = (y & ~rj & full) | (w & rj)
         else:
-            raise ValueError("the sliced kernel takes 1..4 predictors per gene")
+            raise ValueError("the sliced kernel takes 1..8 predictors per gene")
     # Pool of group q = r mod 4: blocks (FIX, 1024 q + i), i = 0, 1, ...; each block is two pair-planes (x, y), (z, w).
     # Per pair-plane the group's K=3 slots, in slot order, take bit b if they are still at value 3 there and no
     # earlier slot of the group has claimed bit b of this plane.  Blocks are consumed until no slot of the group is
@@ -643,7 +646,7 @@ def sliced_stream(net: OracleNetwork, p: float, env_ids: np.ndarray, step_ctr: i
                     s0[act, i] = (s0[act, i] & ~tk & full) | (px & tk)
                     s1[act, i] = (s1[act, i] & ~tk & full) | (py & tk)
     sh = bit.astype(np.uint64)[:, None]
-    sel = (((s0[inv] >> sh) & np.uint64(1)) + 2 * ((s1[inv] >> sh) & np.uint64(1))).astype(np.uint8)
+    sel = (((s0[inv] >> sh) & np.uint64(1)) + 2 * ((s1[inv] >> sh) & np.uint64(1)) + 4 * ((s2[inv] >> sh) & np.uint64(1))).astype(np.uint8)
     for i, k in enumerate(ks):
         if k == 1:
             sel[:, i] = 0

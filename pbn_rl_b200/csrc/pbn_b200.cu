@@ -148,6 +148,8 @@ struct pbn_handle {
   uint64_t host_graph_clock = 0;
   cudaStream_t s_origin = nullptr;
   cudaEvent_t ev_done = nullptr, ev_fork = nullptr;
+  uint32_t* d_packed = nullptr;   // device staging of the packed results (copy-engine download, PBN_B200_PACKED_DMA)
+  int64_t d_packed_envs = 0;
   cudaEvent_t ev_entry = nullptr, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
 };
 
@@ -288,6 +290,7 @@ static int resident_supported(const pbn_handle* h) {
   if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state needs the sliced kernel");
   if (h->net.n_attr > 254) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: %d attractors > 254", h->net.n_attr);
   if (h->net.r_wrong != 0.0f) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: the wrong-attractor reward term (r_wrong) needs the row-format kernels");
+  if (jit::sel_bits(h->gen) == 3) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: genes with more than 4 predictors need the row-format kernels");
   if (h->net.n_attr > 0 && !h->net.attr_simple && h->net.n_attr_states > 256)
     return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: attractor table with %d (care, value) entries > 256 and several states per attractor", h->net.n_attr_states);
   return PBN_OK;
@@ -406,6 +409,7 @@ void pbn_destroy(pbn_handle* h) {
     if (h->s_origin) cudaStreamDestroy(h->s_origin);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    cudaFree(h->d_packed);
     if (h->ev_entry) cudaEventDestroy(h->ev_entry);
     for (int i = 0; i < pbn_handle::kMaxChunks; ++i) {
       if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -780,7 +784,7 @@ int pbn_jit_precompile(const pbn_net_desc* d) {
   for (int inj = 0; inj < 2; ++inj) {
     std::vector<char> cubin;
     std::string err;
-    for (int part = 0; part < 2; ++part)
+    for (int part = 0; part < (jit::sel_bits(g) == 3 ? 1 : 2); ++part)   // (no plane-resident program with three selection planes)
       if (jit::compile(g, inj != 0, part, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
   }
   return PBN_OK;
@@ -799,7 +803,7 @@ int pbn_rollout(pbn_handle* h, uint64_t* state, int64_t n_steps, uint64_t step_c
   int rc = load_sliced(h, 0);
   if (rc != PBN_OK) return rc;
   const int N = h->net.n_genes, NW = (N + 31) / 32, NSEL = jit::n_sel_slots(h->gen);
-  const uint32_t smem = (uint32_t)(2 * NW * 1024 + 2 * NSEL * 32 + 128 * (8 * N < 255 ? 1 : 2) + 32 + 8) * 4u;
+  const uint32_t smem = (uint32_t)(2 * NW * 1024 + jit::sel_bits(h->gen) * NSEL * 32 + 128 * (8 * N < 255 ? 1 : 2) + 32 + 8) * 4u;
   if (smem > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "pbn_rollout needs %u B of shared memory", smem);
   if (smem > h->rollout_smem_opt_in) {
     PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(h->rollout_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -826,7 +830,7 @@ int64_t pbn_planes_words(const pbn_handle* h, int64_t n_envs) {
   if (!h || n_envs < 0) return fail(PBN_ERR_INVALID, "bad arguments");
   if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "selection planes exist for the sliced kernel only");
   const int64_t tiles = (n_envs + 1023) / 1024;
-  const int64_t words = tiles * 2 * jit::n_sel_slots(h->gen) * 32;
+  const int64_t words = tiles * jit::sel_bits(h->gen) * jit::n_sel_slots(h->gen) * 32;
   return words > 0 ? words : 4;  // never an empty buffer
 }
 
@@ -942,16 +946,38 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
     for (int c = 2; c < lanes; ++c)
       if (!h->s_lane[c]) PBN_CUDA(cudaStreamCreateWithFlags(&h->s_lane[c], cudaStreamNonBlocking));
     // everything of one step on the library's streams, forked from and joined into s_origin
+    // PBN_B200_HOST_TRACE=1 (development; eager launches only): time stamps after every operation of every lane
+    static const bool trace = getenv("PBN_B200_HOST_TRACE") != nullptr;
+    static cudaEvent_t tev[pbn_handle::kMaxLanes][5], tev0;
+    static bool tev_made = false;
+    if (trace && !tev_made) {
+      cudaEventCreate(&tev0);
+      for (auto& row : tev) for (auto& e : row) cudaEventCreate(&e);
+      tev_made = true;
+    }
+    static const bool dma = getenv("PBN_B200_PACKED_DMA") != nullptr;
+    static const int export_ctas = getenv("PBN_B200_EXPORT_CTAS") ? atoi(getenv("PBN_B200_EXPORT_CTAS")) : 16;
+    if (dma && h->d_packed_envs < E) {
+      cudaFree(h->d_packed);
+      h->d_packed = nullptr;
+      h->d_packed_envs = 0;
+      PBN_CUDA(cudaMalloc(&h->d_packed, (size_t)E * 4));
+      h->d_packed_envs = E;
+    }
     auto enqueue = [&]() -> int {
       PBN_CUDA(cudaEventRecord(h->ev_fork, h->s_origin));
+      if (trace) cudaEventRecord(tev0, h->s_origin);
       for (int c = 0; c < lanes; ++c) {
         const int64_t e0 = c * per, n = (E - e0 < per) ? E - e0 : per;
         if (n <= 0) continue;
         cudaStream_t S = c == 0 ? h->s_h2d : (c == 1 ? h->s_d2h : h->s_lane[c]);
         PBN_CUDA(cudaStreamWaitEvent(S, h->ev_fork, 0));
+        if (trace) cudaEventRecord(tev[c][0], S);
         PBN_CUDA(cudaMemcpyAsync(io->actions16_dev + e0, io->actions16 + e0, (size_t)n * 2, cudaMemcpyHostToDevice, S));
+        if (trace) cudaEventRecord(tev[c][1], S);
         unpack_actions16_kernel<<<grid_for(h, n / 4 + 1, 256, 4), 256, 0, S>>>(io->actions16_dev + e0, io->actions_dev + e0 * h->net.bins, n);
         PBN_CUDA(cudaGetLastError());
+        if (trace) cudaEventRecord(tev[c][2], S);
         pbn_step_args s = *a;
         s.state = a->state + e0 * h->W;
         s.actions = io->actions_dev + e0 * h->net.bins;
@@ -967,14 +993,17 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
         s.flags = (a->flags & ~PBN_STEP_PDL) | PBN_STEP_NO_COUNT;
         const int rc = step_common(h, &s, S, false);
         if (rc != PBN_OK) return rc;
+        if (trace) cudaEventRecord(tev[c][3], S);
         ExportArgs x{};
         x.state64 = a->state + e0;
         x.term = a->terminated + e0;
         x.trunc = a->truncated + e0;
-        x.packed = zc_packed + e0;
+        x.packed = dma ? h->d_packed + e0 : zc_packed + e0;
         x.n_envs = n;
-        export_kernel<<<16, 256, 0, S>>>(x);
+        export_kernel<<<dma ? 4 * h->num_sms : export_ctas, 256, 0, S>>>(x);
         PBN_CUDA(cudaGetLastError());
+        if (dma) PBN_CUDA(cudaMemcpyAsync(io->packed + e0, h->d_packed + e0, (size_t)n * 4, cudaMemcpyDeviceToHost, S));
+        if (trace) cudaEventRecord(tev[c][4], S);
         h->launches += 2;   // (+ the step kernel, counted by step_common)
         PBN_CUDA(cudaEventRecord(h->ev_k[c], S));
         PBN_CUDA(cudaStreamWaitEvent(h->s_origin, h->ev_k[c], 0));
@@ -1037,6 +1066,14 @@ int pbn_step_host(pbn_handle* h, const pbn_step_args* a, const pbn_host_io* io, 
     PBN_CUDA(cudaEventRecord(h->ev_done, h->s_origin));
     PBN_CUDA(cudaStreamWaitEvent(stream, h->ev_done, 0));   // later work on the caller's stream sees the step
     PBN_CUDA(cudaEventSynchronize(h->ev_done));
+    if (trace && !(slot && slot->exec)) {
+      for (int c = 0; c < lanes; ++c) {
+        float t[5];
+        for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&t[k], tev0, tev[c][k]);
+        fprintf(stderr, "[pbn host trace] lane %d: start %.1f  upload done %.1f  unpack %.1f  step %.1f  export %.1f us\n", c,
+                t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f);
+      }
+    }
     return PBN_OK;
   }
   int64_t nc = io->n_chunks > 0 ? io->n_chunks : (E >= (1 << 18) ? 2 : 1);  // measured best on B200 / PCIe Gen5 (scripts/host_path_probe.py)

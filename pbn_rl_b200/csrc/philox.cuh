@@ -94,4 +94,42 @@ __device__ __forceinline__ void draw_weighted(uint64_t gid, uint64_t step, const
   hi = g1;
 }
 
+// The same draw for genes with up to 8 predictors (networks with such a gene carry three selection planes,
+// PBN_SELBITS == 3): up to 7 thresholds, sel = lo + 2 hi + 4 h2.  For K <= 4 it returns what draw_weighted returns.
+__device__ __forceinline__ void draw_weighted8(uint64_t gid, uint64_t step, const uint32_t (&rk)[20], uint32_t r, uint32_t K,
+                                               const uint32_t* cum, uint32_t& lo, uint32_t& hi, uint32_t& h2) {
+  uint32_t c[7], eq[7], lt[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    c[k] = cum[k];
+    const bool active = (uint32_t)k + 1u < K;
+    eq[k] = active ? 0xFFFFFFFFu : 0u;   // still equal to the threshold
+    lt[k] = active ? 0u : 0xFFFFFFFFu;   // decided: u < threshold
+  }
+#pragma unroll 1
+  for (uint32_t i = 0; i < 8u; ++i) {
+    const Philox4 P = philox_stream_rk(gid, step, PBN_RNG_SELECT, 128u + 8u * r + i, rk);
+    uint32_t open = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t u = j == 0 ? P.x : j == 1 ? P.y : j == 2 ? P.z : P.w;
+      const uint32_t sh = 4u * i + (uint32_t)j;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const uint32_t b = (uint32_t)((int32_t)(c[k] << sh) >> 31);
+        lt[k] |= eq[k] & ~u & b;
+        eq[k] &= ~(u ^ b);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) open |= eq[k];
+    if (!__any_sync(0xFFFFFFFFu, open != 0u)) break;
+  }
+  // thermometer code (g0 >= g1 >= ... >= g6, g_k = u >= threshold k) -> binary
+  const uint32_t g0 = ~lt[0], g1 = ~lt[1], g2 = ~lt[2], g3 = ~lt[3], g4 = ~lt[4], g5 = ~lt[5], g6 = ~lt[6];
+  h2 = g3;
+  hi = (g1 & ~g3) | g5;
+  lo = (g0 & ~g1) | (g2 & ~g3) | (g4 & ~g5) | g6;
+}
+
 }  // namespace pbn

@@ -48,8 +48,9 @@ struct GenNet {
 };
 
 // ---- eligibility ---------------------------------------------------------------------------
-// The sliced kernels take K in {1,2,3,4} predictors per gene: uniform selection from 2-bit pairs (exact 1-of-3 by
-// rejection), any other probabilities by a bit-serial comparison of a 32-bit uniform with the gene's thresholds.
+// The sliced kernels take K in 1..8 predictors per gene: uniform selection among 2, 3 or 4 from 2-bit pairs (exact
+// 1-of-3 by rejection), any other probabilities -- and every gene with 5..8 predictors, which makes the network carry
+// a third selection plane (PBN_SELBITS == 3) -- by a bit-serial comparison of a 32-bit uniform with the thresholds.
 // Predictors of up to kSlicedMaxArity inputs (7 and more: the multi-word tables of pbn_net_desc::wide_lut).
 inline bool eligible(const pbn_net_desc* d, std::string* why) {
   if (d->n_genes > 96) {
@@ -58,8 +59,8 @@ inline bool eligible(const pbn_net_desc* d, std::string* why) {
   }
   for (int i = 0; i < d->n_genes; ++i) {
     const int f0 = d->func_offset[i], K = d->func_offset[i + 1] - f0;
-    if (K < 1 || K > 4) {
-      if (why) *why = "gene with more than 4 predictors";
+    if (K < 1 || K > 8) {
+      if (why) *why = "gene with more than 8 predictors";
       return false;
     }
     for (int k = 0; k < K; ++k) {
@@ -213,11 +214,18 @@ inline int n_sel_slots(const GenNet& g) {
   return n;
 }
 
+// selection planes per slot: 2, or 3 when some gene has more than 4 predictors
+inline int sel_bits(const GenNet& g) {
+  size_t k = 1;
+  for (const auto& fs : g.funcs) k = std::max(k, fs.size());
+  return k > 4 ? 3 : 2;
+}
+
 inline int scratch_words(const GenNet& g) {
   const int NW = (g.n_genes + 31) / 32;
   // + pre-drawn perturbation events: one packed word per thread (8 N < 255 slots), else two
   // + the model-A event mask of the column (32 words)
-  return 2 * NW * 32 * 32 + 2 * n_sel_slots(g) * 32 + 8 + 128 * (8 * g.n_genes < 255 ? 1 : 2) + 32;
+  return 2 * NW * 32 * 32 + sel_bits(g) * n_sel_slots(g) * 32 + 8 + 128 * (8 * g.n_genes < 255 ? 1 : 2) + 32;
 }
 
 inline int sliced_threads(const GenNet&) { return 128; }  // four warps per 1024-env tile
@@ -239,11 +247,21 @@ inline int sliced_min_blocks(const GenNet& g) {
 // pair-plane draw applies.  Anything else is "weighted".
 inline bool uniform_selection(const std::vector<GenFunc>& fs) {
   const int K = (int)fs.size();
+  if (K > 4) return false;   // 5..8 predictors: always by threshold comparison
   for (int k = 0; k + 1 < K; ++k) {
     const double want = std::floor((double)(k + 1) / K * 4294967296.0 + 0.5);
     if (std::fabs((double)fs[k].cum - want) > 2.0) return false;
   }
   return true;
+}
+
+// 1-of-K (K = 5..8) from three selection planes s0, s1, s2 (the unused upper choices repeat the last predictor)
+inline std::string mux8(std::vector<std::string> f) {
+  while (f.size() < 8) f.push_back(f.back());
+  auto mux4 = [&](int b) {
+    return "bmux(s1, bmux(s0, " + f[b + 3] + ", " + f[b + 2] + "), bmux(s0, " + f[b + 1] + ", " + f[b] + "))";
+  };
+  return "bmux(s2, " + mux4(4) + ", " + mux4(0) + ")";
 }
 
 inline void generate_parts(const GenNet& g, std::string& u) {
@@ -272,6 +290,8 @@ inline void generate_parts(const GenNet& g, std::string& u) {
   // four groups agree on it, else it comes from the kSelK table.
   const int NSEL = slot;
   const int MAXS4 = (NSEL + 3) / 4 > 0 ? (NSEL + 3) / 4 : 1;
+  const bool sel3 = sel_bits(g) == 3;
+  const int CS = sel3 ? 7 : 3;   // thresholds per slot in kSelCum
   u += "\n#define PBN_CLAIM(k, m3, px, py) { const uint32_t rj_ = lo[k] & hi[k] & (m3); const uint32_t tk_ = rj_ & av; av &= ~rj_; "
        "lo[k] = bmux(tk_, px, lo[k]); hi[k] = bmux(tk_, py, hi[k]); }\n";
   {
@@ -280,20 +300,21 @@ inline void generate_parts(const GenNet& g, std::string& u) {
     for (int i = 0; i < N; ++i)
       if (g.funcs[i].size() > 1) {
         tw += (uniform_selection(g.funcs[i]) ? "0, " : "1, ");
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < CS; ++k) {
           snprintf(buf, sizeof(buf), "0x%08Xu, ", k + 1 < (int)g.funcs[i].size() ? g.funcs[i][k].cum : 0xFFFFFFFFu);
           tc += buf;
         }
         ++slot_i;
       }
     if (slot_i == 0) { tw = "0"; tc = "0u"; }
-    u += "// slot r draws by threshold comparison (kSelWeighted[r] != 0) against kSelCum[3r .. 3r+K-2]\n";
+    u += "// slot r draws by threshold comparison (kSelWeighted[r] != 0) against kSelCum[CS r .. CS r + K - 2], CS = 3 (7 with PBN_SELBITS == 3)\n";
     u += "__device__ __constant__ unsigned char kSelWeighted[] = {" + tw + "};\n";
     u += "__device__ __constant__ uint32_t kSelCum[] = {" + tc + "};\n";
   }
   u += "// selection planes of group q (slots r = q + 4k): lo[k] + 2*hi[k] = predictor index, bit-sliced over the column's 32 envs\n";
   u += "__device__ __forceinline__ void pbn_draw_group(uint32_t q, uint64_t gid, uint64_t step, const uint32_t (&rk)[20],\n"
-       "                                               uint32_t (&lo)[PBN_MAXS4], uint32_t (&hi)[PBN_MAXS4]) {\n";
+       "                                               uint32_t (&lo)[PBN_MAXS4], uint32_t (&hi)[PBN_MAXS4]";
+  u += sel3 ? ", uint32_t (&h2)[PBN_MAXS4]) {\n" : ") {\n";
   std::vector<int> kof(NSEL, 1), wof(NSEL, 0);
   std::vector<uint32_t> cumof(3 * (NSEL > 0 ? NSEL : 1), 0xFFFFFFFFu);
   for (int i = 0; i < N; ++i)
@@ -316,6 +337,10 @@ inline void generate_parts(const GenNet& g, std::string& u) {
     }
     snprintf(buf, sizeof(buf), "  lo[%d] = 0u; hi[%d] = 0u;\n", k, k);
     u += buf;
+    if (sel3) {
+      snprintf(buf, sizeof(buf), "  h2[%d] = 0u;\n", k);
+      u += buf;
+    }
     if (same && Kq[0] == 1) {
       m3[k] = "";
       continue;
@@ -334,7 +359,10 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       if (anyw) {
         snprintf(buf, sizeof(buf), "  const bool W%d = (q + %du < %du) && kSelWeighted[q + %du] != 0;\n", k, 4 * k, NSEL, 4 * k);
         u += buf;
-        snprintf(buf, sizeof(buf), "  if (W%d) draw_weighted(gid, step, rk, q + %du, K%d, kSelCum + 3u * (q + %du), lo[%d], hi[%d]);\n  else ", k, 4 * k, k, 4 * k, k, k);
+        if (sel3)
+          snprintf(buf, sizeof(buf), "  if (W%d) draw_weighted8(gid, step, rk, q + %du, K%d, kSelCum + 7u * (q + %du), lo[%d], hi[%d], h2[%d]);\n  else ", k, 4 * k, k, 4 * k, k, k, k);
+        else
+          snprintf(buf, sizeof(buf), "  if (W%d) draw_weighted(gid, step, rk, q + %du, K%d, kSelCum + 3u * (q + %du), lo[%d], hi[%d]);\n  else ", k, 4 * k, k, 4 * k, k, k);
         u += buf;
       } else {
         u += "  ";
@@ -390,7 +418,8 @@ inline void generate_parts(const GenNet& g, std::string& u) {
   u += "template <int PM>\n";
   u += "// lo / hi: the selection planes of group q mod 4 (pbn_draw_group); slot r of the group sits at index r >> 2\n";
   u += "__device__ __forceinline__ uint32_t pbn_eval_part(uint32_t q, const uint32_t* x, uint32_t* o, const uint32_t* tg, uint32_t m,\n"
-       "                                                  const uint32_t (&lo)[PBN_MAXS4], const uint32_t (&hi)[PBN_MAXS4]) {\n";
+       "                                                  const uint32_t (&lo)[PBN_MAXS4], const uint32_t (&hi)[PBN_MAXS4]";
+  u += sel3 ? ", const uint32_t (&h2)[PBN_MAXS4]) {\n" : ") {\n";
   u += "  uint32_t d = 0u;\n  (void)m;\n#define X(g) x[(g) * 32]\n";
   for (int q = 0; q < 8; ++q) {
     bool has = false;
@@ -447,6 +476,11 @@ inline void generate_parts(const GenNet& g, std::string& u) {
         if (K == 2) val = "bmux(s0, " + names[1] + ", " + names[0] + ")", u += "      (void)s1;\n";
         if (K == 3) val = "bmux(s1, " + names[2] + ", bmux(s0, " + names[1] + ", " + names[0] + "))";
         if (K == 4) val = "bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " + names[0] + "))";
+        if (K > 4) {
+          snprintf(buf, sizeof(buf), "      const uint32_t s2 = h2[%d];\n", k);
+          u += buf;
+          val = mux8(names);
+        }
       }
       snprintf(buf, sizeof(buf), "      PBN_FINISH(%d, ", i);
       u += buf + val + ")\n    }\n";
@@ -477,6 +511,9 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
   // slots per selection group; plane-resident kernel (step_planes.cuh): CTAs per SM of the two variants
   snprintf(buf, sizeof(buf), "#define PBN_MAXS4 %d\n#define PBN_PLANES_MIN_BLOCKS_W4 %d\n#define PBN_PLANES_MIN_BLOCKS_W8 %d\n",
            (NSEL + 3) / 4 > 0 ? (NSEL + 3) / 4 : 1, planes_min_blocks(g, 4), planes_min_blocks(g, 8));
+  h += buf;
+  // selection planes per slot (3: some gene has 5..8 predictors)
+  snprintf(buf, sizeof(buf), "#define PBN_SELBITS %d\n", sel_bits(g));
   h += buf;
   *gen_h = h;
 
@@ -515,7 +552,8 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
   u += "// x: input planes, o: out planes, sel0/sel1: selection planes; all [row][lane], lane folded in\n";
   u += "// keep: envs of the column (bits) that take their input value instead of the update (perturbation model A)\n";
   u += "__device__ __forceinline__ void pbn_update_part(uint32_t w, const uint32_t* x, uint32_t* o,\n"
-       "                                                const uint32_t* sel0, const uint32_t* sel1, uint32_t keep = 0u) {\n";
+       "                                                const uint32_t* sel0, const uint32_t* sel1, ";
+  u += sel_bits(g) == 3 ? "const uint32_t* sel2, uint32_t keep = 0u) {\n" : "uint32_t keep = 0u) {\n";
   u += "#define X(g) x[(g) * 32]\n";
   for (int q = 0; q < 4; ++q) {
     snprintf(buf, sizeof(buf), "  %sif (w == %du) {\n", q ? "else " : "", q);
@@ -573,6 +611,11 @@ inline void generate(const GenNet& g, bool injected, std::string* gen_h, std::st
       if (K == 4)
         u += "      " + dst + "bmux(s1, bmux(s0, " + names[3] + ", " + names[2] + "), bmux(s0, " + names[1] + ", " +
              names[0] + ")));\n";
+      if (K > 4) {
+        snprintf(buf, sizeof(buf), "      const uint32_t s2 = sel2[%d];\n", slot_of[i] * 32);
+        u += buf;
+        u += "      " + dst + mux8(names) + ");\n";
+      }
       u += "    }\n";
     }
     if (q == 0)

@@ -64,7 +64,8 @@ constexpr int kScrRows = 0;                          // s1 rows                 
 constexpr int kScrPl = kScrRows + kNW * 32 * 32;     // PL input planes              [kNW*32][32]
 constexpr int kScrSel0 = kScrPl + kNW * 32 * 32;     // selection planes s0          [PBN_NSEL][32]
 constexpr int kScrSel1 = kScrSel0 + PBN_NSEL * 32;   // selection planes s1          [PBN_NSEL][32]
-constexpr int kScrStat = kScrSel1 + PBN_NSEL * 32;   // 8 block-level statistics counters
+// (PBN_SELBITS == 3, networks with a gene of 5..8 predictors: a third plane set s2 follows s1 -- sel1 + PBN_NSEL * 32)
+constexpr int kScrStat = kScrSel1 + (PBN_SELBITS - 1) * PBN_NSEL * 32;   // 8 block-level statistics counters
 constexpr int kEvWords = (8 * PBN_N < 255) ? 1 : 2;  // packed words of pre-drawn perturbation events per thread
 constexpr int kScrEv = kScrStat + 8;                 // pre-drawn perturbation events              [kEvWords][128]
 constexpr int kScrPm = kScrEv + 128 * kEvWords;      // model A: envs with a perturbation event, byte w of word [lane] = rows 8w..8w+7
@@ -78,7 +79,12 @@ constexpr uint32_t kEvCap = kEvPerWord * kEvWords;   // 4 events for N <= 31, el
 constexpr uint32_t kEvMask = (1u << kEvBits) - 1u;
 constexpr uint32_t kPreEvOverflow = 0u;
 static_assert(kSlots < (int)kEvMask, "pre-drawn event positions do not fit their field");
-constexpr int kPlaneWords = 2 * PBN_NSEL * 32;       // pre-drawn selection planes of one tile: [sel0 | sel1][slot][lane]
+constexpr int kPlaneWords = PBN_SELBITS * PBN_NSEL * 32;   // pre-drawn selection planes of one tile: [sel0 | sel1 (| sel2)][slot][lane]
+#if PBN_SELBITS == 3
+#define PBN_SEL2_OF(sel1) (sel1) + PBN_NSEL * 32,
+#else
+#define PBN_SEL2_OF(sel1)
+#endif
 static_assert((kScrSel0 * 4) % 16 == 0, "TMA destination of the selection planes must be 16-byte aligned");
 static_assert(kScrWords == PBN_SCRATCH_WORDS, "host and device disagree on the scratch size");
 static_assert(PBN_THREADS == 32 * kWarps, "one tile per 4-warp CTA");
@@ -315,13 +321,21 @@ __device__ __forceinline__ void stage_tables(const NetParams& n, const SlicedSme
 __device__ __noinline__ void draw_group_to_scratch(const uint32_t (&rk)[20], uint32_t* sel0, uint32_t* sel1, uint64_t gid,
                                                   uint64_t step_ctr, uint32_t w) {
   uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];
+#if PBN_SELBITS == 3
+  uint32_t h2[PBN_MAXS4];
+  pbn_draw_group(w, gid, step_ctr, rk, lo, hi, h2);
+#else
   pbn_draw_group(w, gid, step_ctr, rk, lo, hi);
+#endif
 #pragma unroll
   for (int k = 0; k < PBN_MAXS4; ++k) {
     const int r = (int)w + 4 * k;
     if (r < PBN_NSEL) {
       sel0[r * 32] = lo[k];
       sel1[r * 32] = hi[k];
+#if PBN_SELBITS == 3
+      sel1[(PBN_NSEL + r) * 32] = h2[k];
+#endif
     }
   }
 }
@@ -337,16 +351,22 @@ __device__ __forceinline__ void draw_selection_planes(const pbn_step_args& a, co
 #pragma unroll 1
   for (int r = (int)w; r < PBN_NSEL; r += kWarps) {
     const uint32_t g = kSelGene[r], K = kSelK[r];
-    uint32_t s0 = 0u, s1 = 0u;
+    uint32_t s0 = 0u, s1 = 0u, s2 = 0u;
     for (int b = 0; b < 32; ++b) {
       const int64_t env = e0 + 128 * (b >> 2) + (b & 3);
       uint32_t v = (env < E) ? a.sel[env * PBN_N + g] : 0u;
       v = v < K ? v : K - 1u;
       s0 |= (v & 1u) << b;
       s1 |= ((v >> 1) & 1u) << b;
+      s2 |= ((v >> 2) & 1u) << b;
     }
     sel0[r * 32] = s0;
     sel1[r * 32] = s1;
+#if PBN_SELBITS == 3
+    sel1[(PBN_NSEL + r) * 32] = s2;
+#else
+    (void)s2;
+#endif
   }
 #else
   draw_group_to_scratch(n.rk, sel0, sel1, gid, step_ctr, w);
@@ -576,12 +596,15 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
     for (int r = (int)w; r < PBN_NSEL; r += kWarps) {
       sel0[r * 32] = gp[r * 32];
       sel1[r * 32] = gp[(PBN_NSEL + r) * 32];
+#if PBN_SELBITS == 3
+      sel1[(PBN_NSEL + r) * 32] = gp[(2 * PBN_NSEL + r) * 32];
+#endif
     }
   }
   __syncthreads();  // (2) all input planes (and selection planes) are in scratch; S1 rows are dead
 
   // ---- C2. synchronous update of this warp's genes: generated LOP3 trees -> OPL planes ----------
-  pbn_update_part(w, pl, opl, sel0, sel1, pert_in_rows ? scr[kScrPm + lane] : 0u);
+  pbn_update_part(w, pl, opl, sel0, sel1, PBN_SEL2_OF(sel1) pert_in_rows ? scr[kScrPm + lane] : 0u);
   phase_stamp(a, 7);
   __syncthreads();  // (3) all out planes are in scratch
   phase_stamp(a, 8);
@@ -1062,7 +1085,7 @@ pbn_step_sliced_gen(const __grid_constant__ StepParams p, const SlicedSmemLayout
 constexpr int kRollPlanes = kNW * 32 * 32;                      // one set of planes [kNW*32][32]
 constexpr int kRollSel0 = 2 * kRollPlanes;
 constexpr int kRollSel1 = kRollSel0 + PBN_NSEL * 32;
-constexpr int kRollEv = kRollSel1 + PBN_NSEL * 32;
+constexpr int kRollEv = kRollSel1 + (PBN_SELBITS - 1) * PBN_NSEL * 32;
 constexpr int kRollAny = kRollEv + 128 * kEvWords;              // mode A: rows of the column with an event [32]
 constexpr int kRollStat = kRollAny + 32;
 constexpr int kRollWords = kRollStat + 8;
@@ -1119,7 +1142,7 @@ pbn_rollout_sliced(const __grid_constant__ RolloutParams p) {
         if (pert_mode == PBN_PERT_A && w == 0u) anym[lane] = 0u;
       }
       __syncthreads();   // planes `cur` complete (transpose / previous update), selection planes drawn
-      pbn_update_part(w, cur + lane, nxt + lane, sel0, sel1);
+      pbn_update_part(w, cur + lane, nxt + lane, sel0, sel1, PBN_SEL2_OF(sel1) 0u);
       if (pert_mode != PBN_PERT_NONE) {
         // this thread's events: (gene, row 8w + ib) of its column
         uint32_t evw[kEvWords];

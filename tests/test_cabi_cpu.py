@@ -94,8 +94,12 @@ def test_sliced_eligibility():
     nonuniform = PBNNetwork.from_expressions(["a", "b"], [[("a | b", 0.9), ("a & b", 0.1)], ["a"]])
     assert "draw_weighted" in jit_source(nonuniform)   # arbitrary probabilities: threshold comparison, still bit-sliced
     five = PBNNetwork.from_expressions(["a", "b"], [["a", "b", "a|b", "a&b", "~a"], ["a"]])
+    src = jit_source(five)                            # 5..8 predictors: a third selection plane
+    assert "#define PBN_SELBITS 3" in src and "draw_weighted8" in src
+    assert "#define PBN_SELBITS 2" in jit_source(nonuniform)
+    nine = PBNNetwork.from_expressions(["a", "b"], [["a", "b", "a|b", "a&b", "~a", "~b", "a & ~b", "~a & b", "~a | b"], ["a"]])
     with pytest.raises(_cabi.PbnError):
-        jit_source(five)
+        jit_source(nine)
 
 
 HOST_HARNESS = r"""
@@ -112,6 +116,7 @@ static inline bool __any_sync(unsigned, bool p) { return p; }   // one column = 
 using pbn::Philox4;
 using pbn::philox_stream_rk;
 using pbn::draw_weighted;
+using pbn::draw_weighted8;
 template <int IMM> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r = 0;
   for (int i = 0; i < 32; ++i) {
@@ -131,13 +136,22 @@ int main(int argc, char** argv) {
   int n, nsel, cases;
   if (scanf("%d %d %d", &n, &nsel, &cases) != 3) return 1;
   const int nw = (n + 31) / 32;
-  static uint32_t x[128 * 32], o[128 * 32], o2[128 * 32], tg[128 * 32], s0[128 * 32], s1[128 * 32];
+  // (PBN_SELBITS == 3: a third selection plane per slot, read after s1 and laid out behind it)
+  static uint32_t x[128 * 32], o[128 * 32], o2[128 * 32], tg[128 * 32], s0[128 * 32], s1[2 * 128 * 32];
+  uint32_t* const s2 = s1 + 128 * 32;
   for (int c = 0; c < cases; ++c) {
     for (int i = 0; i < n; ++i) if (scanf("%u", &x[i * 32]) != 1) return 1;
     for (int i = 0; i < nsel; ++i) if (scanf("%u", &s0[i * 32]) != 1) return 1;
     for (int i = 0; i < nsel; ++i) if (scanf("%u", &s1[i * 32]) != 1) return 1;
+#if PBN_SELBITS == 3
+    for (int i = 0; i < nsel; ++i) if (scanf("%u", &s2[i * 32]) != 1) return 1;
+#endif
     for (int i = 0; i < nw * 32; ++i) o[i * 32] = 0xDEADBEEFu;
+#if PBN_SELBITS == 3
+    for (uint32_t w = 0; w < 4; ++w) pbn::pbn_update_part(w, x, o, s0, s1, s2);
+#else
     for (uint32_t w = 0; w < 4; ++w) pbn::pbn_update_part(w, x, o, s0, s1);
+#endif
     for (int i = 0; i < nw * 32; ++i) printf("%u ", o[i * 32]);
     printf("\n");
     uint32_t d = 0;
@@ -145,7 +159,13 @@ int main(int argc, char** argv) {
     for (uint32_t q = 0; q < 8; ++q) {
       uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];   // the planes of group q mod 4
       for (int k = 0; k < PBN_MAXS4; ++k) { const int r = (int)(q & 3u) + 4 * k; lo[k] = r < nsel ? s0[r * 32] : 0u; hi[k] = r < nsel ? s1[r * 32] : 0u; }
+#if PBN_SELBITS == 3
+      uint32_t h2[PBN_MAXS4];
+      for (int k = 0; k < PBN_MAXS4; ++k) { const int r = (int)(q & 3u) + 4 * k; h2[k] = r < nsel ? s2[r * 32] : 0u; }
+      d |= pbn::pbn_eval_part<0>(q, x, o2, tg, 0u, lo, hi, h2);
+#else
       d |= pbn::pbn_eval_part<0>(q, x, o2, tg, 0u, lo, hi);
+#endif
     }
     for (int i = 0; i < n; ++i) printf("%u ", o2[i * 32]);
     printf("%u\n", d);
@@ -157,13 +177,17 @@ int main(int argc, char** argv) {
     if (scanf("%llu %llu %llu", &gid, &step, &seed) != 3) return 1;
     uint32_t rk[20];
     for (int r = 0; r < 10; ++r) { rk[2 * r] = (uint32_t)seed + r * 0x9E3779B9u; rk[2 * r + 1] = (uint32_t)(seed >> 32) + r * 0xBB67AE85u; }
-    static uint32_t L[1024], H[1024];
+    static uint32_t L[1024], H[1024], H2[1024];
     for (uint32_t q = 0; q < 4; ++q) {
-      uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];
+      uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4], h2[PBN_MAXS4] = {};
+#if PBN_SELBITS == 3
+      pbn::pbn_draw_group(q, gid, step, rk, lo, hi, h2);
+#else
       pbn::pbn_draw_group(q, gid, step, rk, lo, hi);
-      for (int k = 0; k < PBN_MAXS4; ++k) { const int r = (int)q + 4 * k; if (r < nsel) { L[r] = lo[k]; H[r] = hi[k]; } }
+#endif
+      for (int k = 0; k < PBN_MAXS4; ++k) { const int r = (int)q + 4 * k; if (r < nsel) { L[r] = lo[k]; H[r] = hi[k]; H2[r] = h2[k]; } }
     }
-    for (int r = 0; r < nsel; ++r) printf("%u %u ", L[r], H[r]);
+    for (int r = 0; r < nsel; ++r) printf("%u %u %u ", L[r], H[r], H2[r]);
     printf("\n");
   }
   return 0;
@@ -186,6 +210,23 @@ def _mixed_network():
         ["g8"],                                                      # K=1
         [("g9 & g10", 0.999), ("g0", 0.001)],                        # K=2 weighted, extreme
         ["g10", "g5", "g6 & g7"],                                    # K=3 uniform
+    ]
+    return genes, fs
+
+
+def _many_predictor_network():
+    """Genes with 5..8 predictors (uniform and weighted) next to 1..4: three selection planes (PBN_SELBITS == 3)."""
+    genes = ["m%d" % i for i in range(9)]
+    fs = [
+        ["m1", "m2", "m3", "m4", "m5"],                                                   # K=5 uniform
+        [("m0", 0.05), ("m2", 0.1), ("m3", 0.15), ("m4", 0.2), ("m5", 0.2), ("m6 & m7", 0.3)],   # K=6 weighted
+        ["m0 | m1", "m3", "m4", "m5", "m6", "m7", "~m8"],                                 # K=7 uniform
+        [("m%d" % j, 0.125) for j in range(8)],                                           # K=8 uniform
+        ["m0", "m1", "m2"],                                                               # K=3 uniform (pair-plane draw)
+        ["m8"],                                                                           # K=1
+        [("m1 & m2", 0.7), ("m3", 0.3)],                                                  # K=2 weighted
+        ["m2", "m3 | m4", "m5", "m6"],                                                    # K=4 uniform
+        [("m0", 0.01), ("m1", 0.01), ("m2", 0.01), ("m3", 0.01), ("m4", 0.01), ("m5", 0.01), ("m6", 0.01), ("m7", 0.93)],  # K=8 skewed
     ]
     return genes, fs
 
@@ -218,7 +259,7 @@ def _wide_network():
     return genes, fs
 
 
-@pytest.mark.parametrize("name", NETS + ("mixed", "wide"))
+@pytest.mark.parametrize("name", NETS + ("mixed", "wide", "many"))
 def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     """Compile the generated net_gen.cuh / net_update.inc with g++: the predictor trees of both kernels against the
     truth tables on random bit-planes, and the generated selection draw (pbn_draw_group, with csrc/philox.cuh compiled
@@ -227,8 +268,8 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     from oracle import pbn_oracle as O
     from helpers import oracle_net
     from pbn_rl_b200.vec_env import jit_source
-    if name in ("mixed", "wide"):
-        genes, fs = _mixed_network() if name == "mixed" else _wide_network()
+    if name in ("mixed", "wide", "many"):
+        genes, fs = {"mixed": _mixed_network, "wide": _wide_network, "many": _many_predictor_network}[name]()
         net = PBNNetwork.from_expressions(genes, fs)
         onet = O.OracleNetwork(genes, [[(f, 1.0 / len(g)) if isinstance(f, str) else f for f in g] for g in fs])
     else:
@@ -243,6 +284,7 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
     subprocess.run(["g++", "-O1", "-std=c++17", "-I", str(csrc), "-o", str(exe), str(tmp_path / "h.cpp")], check=True)
     n = net.n_genes
     slots = [i for i, fs in enumerate(net.functions) if len(fs) > 1]
+    three = max(len(fs) for fs in net.functions) > 4   # the network carries a third selection plane
     rng = np.random.default_rng(1)
     cases = 6
     lines = ["%d %d %d" % (n, len(slots), cases)]
@@ -252,7 +294,9 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
         sel = np.stack([rng.integers(0, len(net.functions[i]), size=32) for i in slots], axis=0) if slots else np.zeros((0, 32), int)
         s0 = [(int(sum(int(v & 1) << b for b, v in enumerate(row)))) for row in sel]
         s1 = [(int(sum(int((v >> 1) & 1) << b for b, v in enumerate(row)))) for row in sel]
-        lines.append(" ".join(str(int(v)) for v in x) + " " + " ".join(map(str, s0)) + " " + " ".join(map(str, s1)))
+        s2 = [(int(sum(int((v >> 2) & 1) << b for b, v in enumerate(row)))) for row in sel]
+        lines.append(" ".join(str(int(v)) for v in x) + " " + " ".join(map(str, s0)) + " " + " ".join(map(str, s1))
+                     + ((" " + " ".join(map(str, s2))) if three else ""))
         data.append((x, sel))
     draws = [(5, 0, 0x5EED), (1234567, 3, 0x5EED), ((1 << 33) + 9, (1 << 40) + 7, 0xDEADBEEF12345678)]
     lines.append(str(len(draws)))
@@ -280,6 +324,6 @@ def test_generated_lop3_trees_match_truth_tables(name, tmp_path):
         ids = np.array([tile * 1024 + 128 * (b >> 2) + 4 * lane + (b & 3) for b in range(32)], dtype=np.uint64)
         sel, _ = O.sliced_stream(onet, 0.0, ids, step, seed)
         for r, i in enumerate(slots):
-            lo, hi = got[2 * r], got[2 * r + 1]
-            have = [((lo >> b) & 1) + 2 * ((hi >> b) & 1) for b in range(32)]
+            lo, hi, h2 = got[3 * r], got[3 * r + 1], got[3 * r + 2]
+            have = [((lo >> b) & 1) + 2 * ((hi >> b) & 1) + 4 * ((h2 >> b) & 1) for b in range(32)]
             assert have == [int(v) for v in sel[:, i]], (name, gid, step, r)

@@ -72,7 +72,9 @@ CASES = [
     (96, 2, 3, 4, True, ("sliced", "scalar")),
     (97, 3, 3, 3, True, ("scalar",)),           # more than 96 genes: general kernel only
     (128, 2, 4, 5, True, ("scalar",)),
-    (20, 5, 3, 3, False, ("scalar",)),           # five predictors, real selection probabilities
+    (20, 5, 3, 3, False, ("sliced", "scalar")),  # five predictors, real selection probabilities: third selection plane
+    (26, 8, 4, 3, True, ("sliced", "scalar")),   # up to eight predictors, uniform
+    (12, 9, 3, 3, True, ("scalar",)),            # more than eight predictors: general kernel only
     (24, 2, 9, 3, False, ("sliced", "scalar")),  # wide predictors (7..9 inputs), weighted selection
     (40, 3, 12, 3, True, ("sliced", "scalar")),  # up to 12 inputs, two-word states
     (20, 2, 14, 3, True, ("scalar",)),           # more than 12 inputs: general kernel only
