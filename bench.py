@@ -592,8 +592,18 @@ def run_extra_configs(args, device, stream, peak):
     attrs_big = AttractorSet(list(attrs28.attractors) + [sorted(big)[:8192]], 28)
     us_h = short_run(a28, net28, attrs_big, 640, 8) * 1e3
     out["membership_hashset_pbn28"] = {"us_per_step": us_h, "value": (1 << 20) / us_h * 1e6, "unit": UNIT, "attractors": 15, "largest_attractor": 8192,
-                                       "note": "targets uniform over 14 single-state attractors + one 8192-state attractor: every env's target test "
-                                               "is one probe of the L2-resident hash set over the 8206 states (pbn_update_attractors)"}
+                                       "note": "targets uniform over 14 single-state attractors + one 8192-state attractor: single-state targets are "
+                                               "compared in shared memory, the envs of the large target probe the L2-resident hash set over "
+                                               "its 8192 states (pbn_update_attractors)"}
+    # ---- real selection probabilities (what ASSA-format PBNs carry): the headline network with weights 0.5 / 0.3 / 0.2 on
+    # every gene's three predictors -- bit-sliced threshold comparison instead of the pair-plane draw
+    from pbn_rl_b200 import PBNNetwork
+    net_w = PBNNetwork(list(net28.genes), [list(fs) for fs in net28.functions],
+                       [[0.5, 0.3, 0.2][:len(fs)] if len(fs) == 3 else [1.0 / len(fs)] * len(fs) for fs in net28.functions], "pbn28_weighted")
+    us_w = short_run(a28, net_w, attrs28, 640, 8) * 1e3
+    out["weighted_pbn28"] = {"us_per_step": us_w, "value": (1 << 20) / us_w * 1e6, "unit": UNIT,
+                             "note": "Bittner-28 with selection probabilities 0.5 / 0.3 / 0.2 per gene (train_assa_matlab_BQN.py:72-171 style): "
+                                     "bit-sliced kernel, predictor index = number of 32-bit thresholds <= a bit-sliced 32-bit uniform"}
     # ---- the headline workload with plane-resident env state (same random streams, bit-identical results)
     if not (args.resident or args.chain):
         try:
