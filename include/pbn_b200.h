@@ -254,7 +254,13 @@ typedef struct {
  * concurrently on two library-owned copy streams and the caller's stream (envs are independent,
  * so the result does not depend on n_chunks).  Unlike the device entry points this call BLOCKS
  * until the host outputs are complete (like the reference's env.step it returns values); it waits
- * on its own streams only, never on the whole device. */
+ * on its own streams only, never on the whole device.
+ * Lane form: when only `packed` is requested, with actions16, n_chunks <= 0 and n_envs >= 2^18, the batch is cut into
+ * lanes (library streams) that each run upload -> unpack -> step -> export in order.  With args->step_ctr_dev set and
+ * without PBN_STEP_PDL the lanes share one counter value and the call adds 1 to *step_ctr_dev when they have joined;
+ * the arguments are then the same from call to call, and the library captures the whole step the second time it sees
+ * an (args, io) pair and replays it as one CUDA graph launch afterwards (8 pairs are kept; keep the buffers alive
+ * while the handle may still replay them). */
 int pbn_step_host(pbn_handle* h, const pbn_step_args* args, const pbn_host_io* io, void* stream);
 
 /* reward = table[n_flips + (bins + 1) * terminated], n_flips = number of distinct action values in 1..N of the env
