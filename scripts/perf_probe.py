@@ -13,7 +13,7 @@ import bench  # noqa: E402
 from pbn_rl_b200 import VecPBNEnv  # noqa: E402
 
 
-def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20, pdl=False, split=False, resident=False, chain=False):
+def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches=8, graph_steps=32, reps=20, pdl=False, split=False, resident=False, chain=False, streams=1):
     dev = torch.device("cuda:0")
     es = []
     for b in range(batches):
@@ -49,11 +49,20 @@ def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches
             e.advance_counter()
         s.synchronize()
         gr = torch.cuda.CUDAGraph()
+        side = [torch.cuda.Stream() for _ in range(streams - 1)]
         with torch.cuda.graph(gr, stream=s):
+            # streams > 1: env batch b steps on stream b % streams -- independent sequences in flight together
+            for t in side:
+                t.wait_stream(s)
+            lanes = [s] + side
             for i in range(graph_steps):
-                step(i, graph_steps)
-            for e in es:
-                e.advance_counter()
+                with torch.cuda.stream(lanes[(i % batches) % streams]):
+                    step(i, graph_steps)
+            for b, e in enumerate(es):
+                with torch.cuda.stream(lanes[b % streams]):
+                    e.advance_counter()
+            for t in side:
+                s.wait_stream(t)
         gr.replay()
         s.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -78,6 +87,7 @@ def main():
     ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--split", default="", help="'pipe': pbn_predraw on a side stream + pbn_step with pre-drawn planes; 'main' / 'draw': either kernel alone")
     ap.add_argument("--graph-steps", type=int, default=32)
+    ap.add_argument("--streams", type=int, default=1, help="env batches stepped concurrently on this many streams")
     ap.add_argument("--chain", action="store_true", help="tile-level chaining of resident steps (PBN_STEP_CHAIN)")
     ap.add_argument("--batches", type=int, default=8)
     ap.add_argument("--resident", action="store_true", help="plane-resident env state (step_planes.cuh)")

@@ -308,3 +308,30 @@ def test_packed_lane_form_and_graph_replay_equal_step(mode):
     assert per_step == (13 if mode != "host_counter" else 6)
     assert np.array_equal(dut.state.cpu().numpy(), ref.state.cpu().numpy())
     ref.close(); dut.close()
+
+
+def test_packed_graph_cache_survives_more_buffers_than_slots():
+    """Ten distinct pinned action buffers against the library's eight graph slots: entries are evicted and captured
+    again, every call still returns what pbn_step returns."""
+    import torch
+    name, e = "pbn28", 1 << 18
+    ref, dut = _mk(name, e, auto_reset=True, device_counter=True), _mk(name, e, auto_reset=True, device_counter=True)
+    for env in (ref, dut):
+        _seed_env(env, name, e, 21)
+    rng = np.random.default_rng(22)
+    bufs, acts = [], []
+    for k in range(10):
+        act = rng.integers(0, 29, size=(e, 3), dtype=np.uint8)
+        b = torch.empty((e,), dtype=torch.int16, pin_memory=True)
+        b.numpy().view(np.uint16)[...] = dut.pack_actions16(act)
+        bufs.append(b)
+        acts.append(torch.from_numpy(act).cuda())
+    for step in range(25):
+        k = (step * 7) % 10 if step >= 10 else step
+        out = dut.step_host(None, compact="packed", actions16=bufs[k])
+        ref.step(acts[k])
+        torch.cuda.synchronize()
+        want = ref.state.cpu().numpy().astype(np.uint64)[:, 0].astype(np.uint32)
+        assert np.array_equal(out["packed"] & np.uint32((1 << 30) - 1), want), f"state at step {step}"
+    assert dut.stats() == ref.stats()   # episode statistics accumulated on the device by both paths
+    ref.close(); dut.close()
