@@ -48,27 +48,37 @@ def time_config(net, attrs, envs, kernel, p, auto_reset, stats, actions, batches
         for e in es:
             e.advance_counter()
         s.synchronize()
-        gr = torch.cuda.CUDAGraph()
-        side = [torch.cuda.Stream() for _ in range(streams - 1)]
-        with torch.cuda.graph(gr, stream=s):
-            # streams > 1: env batch b steps on stream b % streams -- independent sequences in flight together
-            for t in side:
-                t.wait_stream(s)
-            lanes = [s] + side
-            for i in range(graph_steps):
-                with torch.cuda.stream(lanes[(i % batches) % streams]):
-                    step(i, graph_steps)
-            for b, e in enumerate(es):
-                with torch.cuda.stream(lanes[b % streams]):
-                    e.advance_counter()
-            for t in side:
-                s.wait_stream(t)
-        gr.replay()
+        # streams > 1: env batch b belongs to stream b % streams; every stream replays its own graph (a PDL sequence over
+        # its batches), the graphs of a round are in flight together
+        lanes = [s] + [torch.cuda.Stream() for _ in range(streams - 1)]
+        graphs = []
+        for k, ls in enumerate(lanes):
+            gr = torch.cuda.CUDAGraph()
+            ls.wait_stream(s)
+            with torch.cuda.graph(gr, stream=ls):
+                for i in range(graph_steps):
+                    if (i % batches) % streams == k:
+                        step(i, graph_steps)
+                for b, e in enumerate(es):
+                    if b % streams == k:
+                        e.advance_counter()
+            graphs.append(gr)
+
+        def replay_all():
+            for ls in lanes[1:]:
+                ls.wait_stream(s)
+            for gr, ls in zip(graphs, lanes):
+                with torch.cuda.stream(ls):
+                    gr.replay()
+            for ls in lanes[1:]:
+                s.wait_stream(ls)
+
+        replay_all()
         s.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s)
         for _ in range(reps):
-            gr.replay()
+            replay_all()
         e1.record(s)
         s.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * graph_steps)
