@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -117,6 +119,7 @@ struct pbn_handle {
   jit::GenNet gen;
   cudaLibrary_t jit_lib[2] = {nullptr, nullptr};
   cudaLibrary_t jit_lib_planes[2] = {nullptr, nullptr};   // the plane-resident kernels' program, loaded on first use
+  std::string jit_key[2], jit_key_planes[2];               // shared-module registry keys (release_module)
   cudaKernel_t jit_kernel[2] = {nullptr, nullptr};      // pbn_step_sliced (attractor table in shared memory)
   cudaKernel_t jit_kernel_gen[2] = {nullptr, nullptr};  // pbn_step_sliced_gen (hash set / global table / r_wrong)
   cudaKernel_t planes_kernel[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [injected][0: 4 warps, 1: 8 warps] pbn_step_planes_w*
@@ -153,24 +156,100 @@ struct pbn_handle {
   cudaEvent_t ev_entry = nullptr, ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
 };
 
+// Loaded specialisations are shared between the handles of a process: env batches of the same network (the bench
+// rotates eight of them, an RL loop holds a train and an eval batch) then launch ONE copy of the kernel code, which
+// stays warm in the instruction caches, instead of one copy per handle.  A module is identified by its cubin and by the
+// survival table its constant memory holds (handles with another perturbation rate get their own).
+struct SharedModule {
+  cudaLibrary_t lib = nullptr;
+  int refs = 0;
+};
+static std::mutex g_modules_mutex;
+static std::map<std::string, SharedModule> g_modules;
+
+static uint64_t fnv1a(const void* data, size_t n, uint64_t hsh = 1469598103934665603ull) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) hsh = (hsh ^ p[i]) * 1099511628211ull;
+  return hsh;
+}
+
+// returns the module (loading it and filling its survival table on first use) and the key to release it with
+static int acquire_module(pbn_handle* h, const std::vector<char>& cubin, bool own_rng, cudaLibrary_t* lib, std::string* key) {
+  uint64_t a = fnv1a(cubin.data(), cubin.size());
+  uint64_t b = own_rng ? fnv1a(h->surv_sliced_host.data(), h->surv_sliced_host.size() * sizeof(uint32_t)) : 0ull;
+  char buf[96];
+  snprintf(buf, sizeof(buf), "%d:%zu:%016llx:%016llx", h->device, cubin.size(), (unsigned long long)a, (unsigned long long)b);
+  std::lock_guard<std::mutex> lock(g_modules_mutex);
+  SharedModule& m = g_modules[buf];
+  if (!m.lib) {
+    cudaLibrary_t l = nullptr;
+    const cudaError_t e = cudaLibraryLoadData(&l, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) {
+      g_modules.erase(buf);
+      return fail(PBN_ERR_CUDA, "cudaLibraryLoadData: %s", cudaGetErrorString(e));
+    }
+    if (own_rng) {  // the survival table of the perturbation sub-streams lives in the specialisation's constant memory
+      void* dptr = nullptr;
+      size_t bytes = 0;
+      cudaError_t e2 = cudaLibraryGetGlobal(&dptr, &bytes, l, "_ZN3pbn10kSurvTableE");
+      if (e2 == cudaSuccess && bytes != h->surv_sliced_host.size() * sizeof(uint32_t)) e2 = cudaErrorInvalidValue;
+      if (e2 == cudaSuccess) e2 = cudaMemcpy(dptr, h->surv_sliced_host.data(), bytes, cudaMemcpyHostToDevice);
+      if (e2 != cudaSuccess) {
+        cudaLibraryUnload(l);
+        g_modules.erase(buf);
+        return fail(PBN_ERR_JIT, "kSurvTable of the specialisation: %s (%zu bytes, expected %zu)", cudaGetErrorString(e2), bytes,
+                    h->surv_sliced_host.size() * sizeof(uint32_t));
+      }
+    }
+    m.lib = l;
+  }
+  m.refs += 1;
+  *lib = m.lib;
+  *key = buf;
+  return PBN_OK;
+}
+
+static void release_module(const std::string& key) {
+  if (key.empty()) return;
+  std::lock_guard<std::mutex> lock(g_modules_mutex);
+  auto it = g_modules.find(key);
+  if (it == g_modules.end()) return;
+  if (--it->second.refs <= 0) {
+    cudaLibraryUnload(it->second.lib);
+    g_modules.erase(it);
+  }
+}
+
+// Dynamic shared memory above 48 KB must be opted into per kernel -- and the kernels are shared between handles, so the
+// handle's cached value is only a shortcut: the kernel's own attribute decides, and it is only ever raised.
+static int ensure_dynamic_smem(cudaKernel_t k, uint32_t bytes, uint32_t* cached) {
+  if (bytes <= *cached) return PBN_OK;
+  cudaFuncAttributes fa{};
+  PBN_CUDA(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(k)));
+  uint32_t cur = fa.maxDynamicSharedSizeBytes > 0 ? (uint32_t)fa.maxDynamicSharedSizeBytes : 0u;
+  if (cur < 48u * 1024u) cur = 48u * 1024u;
+  if (bytes > cur) {
+    PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+  *cached = cur;
+  return PBN_OK;
+}
+
 // Compile (or fetch from the cubin cache) and load one specialisation of the sliced kernel.
 static int load_sliced(pbn_handle* h, int injected) {
   if (h->jit_kernel[injected]) return PBN_OK;
   std::vector<char> cubin;
   std::string err;
   if (jit::compile(h->gen, injected != 0, 0, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
-  PBN_CUDA(cudaLibraryLoadData(&h->jit_lib[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  {
+    const int rc = acquire_module(h, cubin, !injected, &h->jit_lib[injected], &h->jit_key[injected]);
+    if (rc != PBN_OK) return rc;
+  }
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel[injected], h->jit_lib[injected], "pbn_step_sliced"));
   PBN_CUDA(cudaLibraryGetKernel(&h->jit_kernel_gen[injected], h->jit_lib[injected], "pbn_step_sliced_gen"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->predraw_kernel, h->jit_lib[0], "pbn_predraw_sliced"));
   if (!injected) PBN_CUDA(cudaLibraryGetKernel(&h->rollout_kernel, h->jit_lib[0], "pbn_rollout_sliced"));
-  if (!injected) {  // the survival table of the perturbation sub-streams lives in the specialisation's constant memory
-    void* dptr = nullptr;
-    size_t bytes = 0;
-    PBN_CUDA(cudaLibraryGetGlobal(&dptr, &bytes, h->jit_lib[injected], "_ZN3pbn10kSurvTableE"));
-    if (bytes != h->surv_sliced_host.size() * sizeof(uint32_t)) return fail(PBN_ERR_JIT, "kSurvTable has %zu bytes, expected %zu", bytes, h->surv_sliced_host.size() * sizeof(uint32_t));
-    PBN_CUDA(cudaMemcpy(dptr, h->surv_sliced_host.data(), bytes, cudaMemcpyHostToDevice));
-  }
   h->sliced_threads = jit::sliced_threads(h->gen);
   h->sliced_min_blocks = jit::sliced_min_blocks(h->gen);
   return PBN_OK;
@@ -182,15 +261,11 @@ static int load_planes(pbn_handle* h, int injected) {
   std::vector<char> cubin;
   std::string err;
   if (jit::compile(h->gen, injected != 0, 1, &cubin, &err) != 0) return fail(PBN_ERR_JIT, "%s", err.c_str());
-  PBN_CUDA(cudaLibraryLoadData(&h->jit_lib_planes[injected], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][1], h->jit_lib_planes[injected], "pbn_step_planes_w8"));
-  if (!injected) {
-    void* dptr = nullptr;
-    size_t bytes = 0;
-    PBN_CUDA(cudaLibraryGetGlobal(&dptr, &bytes, h->jit_lib_planes[injected], "_ZN3pbn10kSurvTableE"));
-    if (bytes != h->surv_sliced_host.size() * sizeof(uint32_t)) return fail(PBN_ERR_JIT, "kSurvTable has %zu bytes, expected %zu", bytes, h->surv_sliced_host.size() * sizeof(uint32_t));
-    PBN_CUDA(cudaMemcpy(dptr, h->surv_sliced_host.data(), bytes, cudaMemcpyHostToDevice));
+  {
+    const int rc = acquire_module(h, cubin, !injected, &h->jit_lib_planes[injected], &h->jit_key_planes[injected]);
+    if (rc != PBN_OK) return rc;
   }
+  PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][1], h->jit_lib_planes[injected], "pbn_step_planes_w8"));
   PBN_CUDA(cudaLibraryGetKernel(&h->planes_kernel[injected][0], h->jit_lib_planes[injected], "pbn_step_planes_w4"));
   return PBN_OK;
 }
@@ -255,10 +330,7 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
   if (L.total > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "sliced kernel needs %u B of shared memory", L.total);
   const int gen = L.attractors_in_smem ? 0 : 1;
   cudaKernel_t k = gen ? h->jit_kernel_gen[injected ? 1 : 0] : h->jit_kernel[injected ? 1 : 0];
-  if (L.total > h->jit_smem_opt_in[injected ? 1 : 0][gen]) {
-    PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    h->jit_smem_opt_in[injected ? 1 : 0][gen] = L.total;
-  }
+  if ((rc = ensure_dynamic_smem(k, L.total, &h->jit_smem_opt_in[injected ? 1 : 0][gen])) != PBN_OK) return rc;
   // one CTA per 1024-env tile; beyond a few waves the CTAs loop over tiles
   int64_t grid = (a.n_envs + 1023) / 1024;
   const int64_t cap = (int64_t)h->num_sms * h->sliced_min_blocks * 8;
@@ -330,10 +402,7 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
   L.total = o;
   if (L.total > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "plane-resident kernel needs %u B of shared memory", L.total);
   cudaKernel_t k = h->planes_kernel[injected ? 1 : 0][v];
-  if (L.total > h->planes_smem_opt_in[injected ? 1 : 0][v]) {
-    PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    h->planes_smem_opt_in[injected ? 1 : 0][v] = L.total;
-  }
+  if ((rc = ensure_dynamic_smem(k, L.total, &h->planes_smem_opt_in[injected ? 1 : 0][v])) != PBN_OK) return rc;
   // Tile-chained sequences (PBN_STEP_CHAIN) run best with CTAs that walk several tiles: a launch then occupies a
   // fraction of the SMs' CTA slots, the next launches of the sequence become resident beside it, and the device
   // always holds tiles of two or three steps in different phases (Philox draws, memory waits, logic).
@@ -397,8 +466,8 @@ void pbn_destroy(pbn_handle* h) {
     cudaFree(h->d_wide);
     cudaFree(h->d_wide_lut);
     for (int i = 0; i < 2; ++i) {
-      if (h->jit_lib[i]) cudaLibraryUnload(h->jit_lib[i]);
-      if (h->jit_lib_planes[i]) cudaLibraryUnload(h->jit_lib_planes[i]);
+      release_module(h->jit_key[i]);
+      release_module(h->jit_key_planes[i]);
     }
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -805,10 +874,7 @@ int pbn_rollout(pbn_handle* h, uint64_t* state, int64_t n_steps, uint64_t step_c
   const int N = h->net.n_genes, NW = (N + 31) / 32, NSEL = jit::n_sel_slots(h->gen);
   const uint32_t smem = (uint32_t)(2 * NW * 1024 + jit::sel_bits(h->gen) * NSEL * 32 + 128 * (8 * N < 255 ? 1 : 2) + 32 + 8) * 4u;
   if (smem > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "pbn_rollout needs %u B of shared memory", smem);
-  if (smem > h->rollout_smem_opt_in) {
-    PBN_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(h->rollout_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->rollout_smem_opt_in = smem;
-  }
+  if ((rc = ensure_dynamic_smem(h->rollout_kernel, smem, &h->rollout_smem_opt_in)) != PBN_OK) return rc;
   RolloutParams p;
   p.n = h->net;
   p.state = state;
