@@ -380,7 +380,7 @@ def run_gpu(args):
         sval = per * world * Ks / (sms * 1e-3)
         strong = {"value": sval, "unit": UNIT, "ms_per_step": sms / Ks, "steps": Ks, "envs_per_gpu": per, "total_envs": per * world,
                   "efficiency": sval / value, "efficiency_basis": "this value / the weak-scaling `value` of the same run (N x 2^20 envs)",
-                  "kernel_variant": ("plane-resident state, 8 warps per 1024-env tile, tile-chained launches (PBN_STEP_CHAIN)" if small
+                  "kernel_variant": ("plane-resident state, 4 warps per 1024-env tile, tile-chained launches (PBN_STEP_CHAIN)" if small
                                      else "same kernel and launch form as the weak-scaling line")}
         for e in senvs:
             e.close()

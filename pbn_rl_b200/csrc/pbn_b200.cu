@@ -378,9 +378,12 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
   const NetParams& n = h->net;
   const int N = n.n_genes, NW = (N + 31) / 32;
   const int64_t tiles = (a.n_envs + 1023) / 1024;
-  // 8 warps per tile halve a tile's latency (small batches: one CTA per SM or less); 4 warps per tile keep 8 tiles
-  // per SM in flight (large batches).  Both draw the same streams.
-  int v = (N > 32 || tiles < 2 * (int64_t)h->num_sms) ? 1 : 0;
+  // 4 warps per tile (the selection planes stay in registers) for one-word states; 8 warps per tile where the
+  // planes of a group would not fit the register file (N > 32: they are handed over through shared memory).  Both draw
+  // the same streams.  (Measured with one shared code module per process, chained sequences: 3.69 vs 3.81 us per
+  // 2^17-env step and 5.70 vs 6.51 us per 2^18-env step for 4 vs 8 warps.)
+  int v = N > 32 ? 1 : 0;
+  (void)tiles;
   if (const char* env = getenv("PBN_B200_PLANES_WARPS")) v = atoi(env) == 8 ? 1 : 0;
   const int maxs4 = (jit::n_sel_slots(h->gen) + 3) / 4 > 0 ? (jit::n_sel_slots(h->gen) + 3) / 4 : 1;
   PlanesLayout L{};
@@ -403,10 +406,10 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
   if (L.total > 227u * 1024u) return fail(PBN_ERR_UNSUPPORTED, "plane-resident kernel needs %u B of shared memory", L.total);
   cudaKernel_t k = h->planes_kernel[injected ? 1 : 0][v];
   if ((rc = ensure_dynamic_smem(k, L.total, &h->planes_smem_opt_in[injected ? 1 : 0][v])) != PBN_OK) return rc;
-  // Tile-chained sequences (PBN_STEP_CHAIN) run best with CTAs that walk several tiles: a launch then occupies a
-  // fraction of the SMs' CTA slots, the next launches of the sequence become resident beside it, and the device
-  // always holds tiles of two or three steps in different phases (Philox draws, memory waits, logic).
-  int tpc = (a.flags & PBN_STEP_CHAIN) ? 2 : 1;
+  // One tile per CTA.  (CTAs that walk two tiles were the better form for tile-chained sequences while every handle ran
+  // its own copy of the kernel code -- 7.1 vs 7.6 us per 2^17-env step; with the shared module one tile per CTA wins,
+  // 3.8 vs 4.25 us.)
+  int tpc = 1;
   if (const char* env = getenv("PBN_B200_PLANES_TILES_PER_CTA")) tpc = atoi(env) > 0 ? atoi(env) : tpc;
   int64_t grid = (tiles + tpc - 1) / tpc;
   const int64_t cap = (int64_t)h->num_sms * 64;
