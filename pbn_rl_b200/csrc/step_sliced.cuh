@@ -739,30 +739,76 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
   // ASMEM (compile time): the table sits in shared memory and neither the hash set nor the wrong-attractor term is in
   // play (the host clears the flag otherwise): the out-of-line test below is then not even compiled in
   constexpr bool fast_attr = ASMEM;
-  // hash set without wildcard entries and without the wrong-attractor term: first probes of the 8 envs up front
+  // hash set without wildcard entries and without the wrong-attractor term: probes compacted over the warp (below)
   const bool hash_first = !fast_attr && !simple && n.ahash_tags != nullptr && n.awild_any == 0u && n.r_wrong == 0.0f;
   // ... and single-state targets are tested against their entry in shared memory, no probe at all
   const bool singles = !fast_attr && L.singles_in_smem != 0u;
-  unsigned long long htag[8], hcur[8];
-  uint32_t hslot[8];
   uint32_t single = 0u;   // bit i: env i's target is a single-state attractor
   if (singles) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (tg[i] < n_attr && s_aoffs[tg[i]] == 1) single |= 1u << i;
   }
+  // Hash-set probes, warp-cooperative: the envs of the warp whose target needs a probe (a fraction of its 256 when most
+  // targets are single states) are compacted into a queue -- state words in the warp's own s1 rows, target ids in its
+  // own input planes, both dead by now -- and dealt out one per lane: the fingerprint arithmetic and the probe sequence
+  // then run once per 32 queued envs at full lane occupancy instead of once per env slot of every thread for the few
+  // lanes that need it.  The probing lane writes the verdict over the queued target id.
+  uint32_t hq = 0u;       // bit i: env i lies in its target attractor (decided through the queue)
+  uint32_t queued = 0u;   // bit i: env i went through the queue
   if (hash_first) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      htag[i] = 0ull; hcur[i] = 0ull; hslot[i] = 0u;
-      if ((single >> i) & 1u) continue;
-      uint64_t y64[kW64];
+    for (int i = 0; i < 8; ++i)
+      if (tg[i] < n_attr && !((single >> i) & 1u)) queued |= 1u << i;
+    const uint32_t cnt = (uint32_t)__popc(queued);
+    uint32_t incl = cnt;
 #pragma unroll
-      for (int wd = 0; wd < kW64; ++wd)
-        y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
-      htag[i] = attr_tag(y64, kW64);
-      hslot[i] = attr_slot(htag[i], n.ahash_mask);
-      hcur[i] = n.ahash_tags[hslot[i]];
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if ((int)lane >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);   // <= 256: the warp's chunk of rows holds them all
+    if (total != 0u) {   // warp-uniform
+      uint32_t* qst = scr + kScrRows + 8u * w * 32u;   // word wd of entry q: qst[wd * 1024 + q]
+      uint32_t* qtg = scr + kScrPl + 8u * w * 32u;
+      uint32_t pos = incl - cnt;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((queued >> i) & 1u) {
+#pragma unroll
+          for (int wd = 0; wd < kNW; ++wd) qst[wd * 1024 + pos] = o[i][wd];
+          qtg[pos] = tg[i];
+          ++pos;
+        }
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t j = lane; j < total; j += 32u) {
+        uint64_t y64[kW64];
+#pragma unroll
+        for (int wd = 0; wd < kW64; ++wd)
+          y64[wd] = ((uint64_t)((2 * wd + 1 < kNW) ? qst[((2 * wd + 1 < kNW) ? 2 * wd + 1 : 0) * 1024 + j] : 0u) << 32) | qst[2 * wd * 1024 + j];
+        const int at = (int)qtg[j];
+        const uint64_t tag = attr_tag(y64, kW64);
+        uint32_t slot = attr_slot(tag, n.ahash_mask);
+        uint32_t found = 0u;
+#pragma unroll 1
+        for (uint32_t probe = 0; probe <= n.ahash_mask; ++probe, slot = (slot + 1u) & n.ahash_mask) {
+          const unsigned long long cur = n.ahash_tags[slot];
+          if (cur == 0ull) break;
+          if (cur == tag && n.ahash_attr[slot] == at) {
+            bool same = true;
+#pragma unroll
+            for (int wd = 0; wd < kW64; ++wd) same = same && n.ahash_state[(size_t)slot * kW64 + wd] == y64[wd];
+            if (same) { found = 1u; break; }
+          }
+        }
+        qtg[j] = found;
+      }
+      __syncwarp();
+      pos = incl - cnt;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((queued >> i) & 1u) hq |= qtg[pos++] << i;
     }
   }
 #pragma unroll
@@ -778,9 +824,9 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
       if (tg[i] < n_attr) {  // unsigned compare: negative ids never match
         if (!fast_attr) {
           // large attractors (hash set), tables too large for shared memory, or the wrong-attractor reward term.
-          // The hash set's first probe was issued for all 8 envs of the thread before this loop (independent L2
-          // round trips in flight together): an empty slot is a miss, a slot holding this state under this target
-          // is a hit, anything else goes through the full probe sequence out of line.
+          // Single-state targets are compared with their entry in shared memory; the hash-set probes of the plain
+          // case (no wildcard entries, no wrong-attractor term) were decided through the warp's queue above; anything
+          // else goes through the out-of-line test.
           bool decided = false;
           if ((single >> i) & 1u) {
             const uint32_t* ent = s_aent + tg[i] * (2 * kNW);
@@ -789,19 +835,9 @@ __device__ __forceinline__ void tile_step(const StepParams& p, const SlicedSmemL
             for (int wd = 0; wd < kNW; ++wd) diff |= (o[i][wd] & ent[wd]) ^ ent[kNW + wd];
             hit = diff == 0u;
             decided = true;
-          } else if (hash_first) {
-            if (hcur[i] == 0ull) {
-              decided = true;
-            } else if (hcur[i] == htag[i] && n.ahash_attr[hslot[i]] == (int)tg[i]) {
-              bool same = true;
-#pragma unroll
-              for (int wd = 0; wd < kW64; ++wd) {
-                const uint64_t y = ((uint64_t)((2 * wd + 1 < kNW) ? o[i][(2 * wd + 1 < kNW) ? 2 * wd + 1 : 0] : 0u) << 32) | o[i][2 * wd];
-                same = same && n.ahash_state[(size_t)hslot[i] * kW64 + wd] == y;
-              }
-              hit = same;
-              decided = same;
-            }
+          } else if ((queued >> i) & 1u) {
+            hit = ((hq >> i) & 1u) != 0u;
+            decided = true;
           }
           if (!decided) {
           const uint32_t hw = rare_membership(n, (int)tg[i], o[i][0], o[i][kNW > 1 ? 1 : 0], o[i][kNW > 2 ? 2 : 0], o[i][kNW > 3 ? 3 : 0]);
