@@ -361,6 +361,7 @@ static int launch_sliced(pbn_handle* h, StepParams& p, bool injected, cudaStream
 static int resident_supported(const pbn_handle* h) {
   if (h->kernel != PBN_KERNEL_SLICED) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state needs the sliced kernel");
   if (h->net.n_attr > 254) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: %d attractors > 254", h->net.n_attr);
+  if (h->net.n_attr_states >= (1 << 24)) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: %d attractor table entries >= 2^24", h->net.n_attr_states);
   if (h->net.r_wrong != 0.0f) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: the wrong-attractor reward term (r_wrong) needs the row-format kernels");
   if (jit::sel_bits(h->gen) == 3) return fail(PBN_ERR_UNSUPPORTED, "plane-resident state: genes with more than 4 predictors need the row-format kernels");
   if (h->net.n_attr > 0 && !h->net.attr_simple && h->net.n_attr_states > 256)
@@ -387,8 +388,8 @@ static int launch_planes(pbn_handle* h, StepParams& p, bool injected, cudaStream
   if (const char* env = getenv("PBN_B200_PLANES_WARPS")) v = atoi(env) == 8 ? 1 : 0;
   const int maxs4 = (jit::n_sel_slots(h->gen) + 3) / 4 > 0 ? (jit::n_sel_slots(h->gen) + 3) / 4 : 1;
   PlanesLayout L{};
-  // dummy row | IN block | O planes | misc | reset job list | SELX (8-warp variant)   (step_planes.cuh)
-  uint32_t o = (uint32_t)(32 + 32 * resident_rows(N) + 32 * N + 256 + 512 + (v ? 4 * maxs4 * 2 * 32 : 0)) * 4u;
+  // dummy row | IN block | O planes | misc | reset job list | reset draws | SELX (8-warp variant)   (step_planes.cuh)
+  uint32_t o = (uint32_t)(32 + 32 * resident_rows(N) + 32 * N + 256 + 512 + 1024 + (v ? 4 * maxs4 * 2 * 32 : 0)) * 4u;
   const uint32_t tab = (uint32_t)n.n_attr_states * NW * 4u * (n.attr_simple ? 1u : 2u) + (uint32_t)(n.n_attr + 1) * 4u + (uint32_t)n.n_attr_states + 64u;
   L.attr_in_smem = (n.n_attr > 0 && (tab <= 24u * 1024u || !n.attr_simple)) ? 1u : 0u;
   if (L.attr_in_smem) {

@@ -56,7 +56,8 @@ constexpr int kPlMisc = kPlO + PBN_N * 32;
 constexpr int kPlDiff = kPlMisc, kPlHit = kPlMisc + 32, kPlGe = kPlMisc + 64, kPlHt = kPlMisc + 96, kPlM = kPlMisc + 128;
 constexpr int kPlStat = kPlMisc + 160, kPlRew = kPlMisc + 168, kPlMbar = kPlMisc + 192;
 constexpr int kPlJobs = kPlMisc + 256;                 // [warp][envs per warp] u16 job list of the auto-reset (2 KB)
-constexpr int kPlSelx = kPlJobs + 512;                 // [group][k][lo | hi][lane]: planes of the parts of warps 4..7
+constexpr int kPlRinfo = kPlJobs + 512;                // [bit][lane] auto-reset draw of a finished env: source entry | target id << 24 (4 KB)
+constexpr int kPlSelx = kPlRinfo + 1024;               // [group][k][lo | hi][lane]: planes of the parts of warps 4..7
 constexpr int kPlSelxWords = 4 * PBN_MAXS4 * 2 * 32;
 static_assert(2 * (PBN_BINS + 1) <= 24, "reward table does not fit its slot");
 
@@ -503,11 +504,16 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
         if (x2) atomicAdd(&s_stat[PBN_STAT_EP_LEN_SUM], x2);
       }
     }
-    // ---- auto-reset: the finished envs of the warp are listed in shared memory and dealt out over its lanes (one
-    //      Philox pass per 32), then each lane writes its env's new state / target into the planes gene by gene
-    //      (branch-free: AND clears the bit unless it is to be set, OR sets it)
+    // ---- auto-reset.  R1: the finished envs of the warp are listed in shared memory and dealt out over its lanes (one
+    //      Philox pass per 32); the lane leaves its env's draw -- source entry, target id -- at [bit][column].  R2: the
+    //      planes are rewritten gene by gene, a warp takes the genes g = w (mod WARPS) of ALL 32 envs of the column:
+    //      thread (w, L) gathers the bits of gene g over the finished envs of column L and replaces them in one plain
+    //      read-modify-write of its own word -- no atomics (two finished envs of a column share the word, but the
+    //      thread owns the whole word), no bank conflicts (lane == bank).  [the first form wrote every bit of a
+    //      finished env with a pair of shared-memory atomics: 4 N + 16 per env, a third of the step at N = 70]
     if ((a.flags & PBN_STEP_AUTORESET) && PBN_EXP != 2) {
       uint16_t* const jobs = reinterpret_cast<uint16_t*>(sm + kPlJobs) + w * (32 * 4 * GPT);
+      uint32_t* const rinfo = sm + kPlRinfo;
       const uint32_t cnt = (uint32_t)__popc(Dm);
       uint32_t incl = cnt;
 #pragma unroll
@@ -533,47 +539,69 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
           const Philox4 r = philox_stream_rk((uint64_t)(a.env_offset + env), step_ctr, PBN_RNG_RESET, 0, n.rk);
           int src, tgt;
           reset_pair(n, r, src, tgt);
-          int so, se, to;
-          if (L.attr_in_smem) { so = s_aoffs[src]; se = s_aoffs[src + 1]; to = s_aoffs[tgt]; }
-          else { so = n.attr_offset[src]; se = n.attr_offset[src + 1]; to = n.attr_offset[tgt]; }
+          int so, se;
+          if (L.attr_in_smem) { so = s_aoffs[src]; se = s_aoffs[src + 1]; }
+          else { so = n.attr_offset[src]; se = n.attr_offset[src + 1]; }
           const int js = so + (int)__umulhi(r.y, (uint32_t)(se - so));
           if (a.source_id != nullptr) a.source_id[env] = src;
-          const uint32_t bit = 1u << b;
-          uint32_t* const po = sm + kPlO + Lo;
-          uint32_t* const pt = sm + kPlIn + kRowTarget * 32 + Lo;
+          rinfo[b * 32u + Lo] = (uint32_t)js | ((uint32_t)tgt << 24);
+        }
+      }
+      __syncthreads();   // every finished env of the tile has its draw
+      if (D != 0u) {
+        constexpr int GW = (PBN_N + WARPS - 1) / WARPS;      // genes per warp
+        constexpr int CH = GW <= 12 ? GW : 8;                // ... gathered CH at a time (registers)
+        constexpr int TW = (kTidPlanes + WARPS - 1) / WARPS;  // target id planes per warp
 #pragma unroll
-          for (int wd = 0; wd < kNW; ++wd) {
-            uint32_t sv, tv;
-            if (L.attr_in_smem) {
-              sv = s_aval[js * kNW + wd];
-              tv = s_aval[to * kNW + wd];
-            } else {
-              sv = (uint32_t)(n.attr_val[(size_t)js * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
-              tv = (uint32_t)(n.attr_val[(size_t)to * kW64 + (wd >> 1)] >> (32 * (wd & 1)));
-            }
+        for (int c0 = 0; c0 < GW; c0 += CH) {
+          uint32_t ns[CH], nt[CH], ni[TW];
 #pragma unroll
-            for (int gb = 0; gb < 32; ++gb) {
-              const int g = 32 * wd + gb;
-              if (g < PBN_N) {
-                const uint32_t ms = (uint32_t)((int32_t)(sv << (31 - gb)) >> 31), mt = (uint32_t)((int32_t)(tv << (31 - gb)) >> 31);
-#if PBN_EXP == 3
-                po[g * 32] = (po[g * 32] & (~bit | ms)) | (bit & ms);   // experiment: plain read-modify-write (races)
-                pt[g * 32] = (pt[g * 32] & (~bit | mt)) | (bit & mt);
-#else
-                atomicAnd(po + g * 32, ~bit | ms);
-                atomicOr(po + g * 32, bit & ms);
-                atomicAnd(pt + g * 32, ~bit | mt);
-                atomicOr(pt + g * 32, bit & mt);
-#endif
+          for (int i = 0; i < CH; ++i) { ns[i] = 0u; nt[i] = 0u; }
+#pragma unroll
+          for (int i = 0; i < TW; ++i) ni[i] = 0u;
+          uint32_t mm = D;
+#pragma unroll 1
+          while (mm) {
+            const uint32_t b = (uint32_t)__ffs(mm) - 1u;
+            mm &= mm - 1u;
+            const uint32_t info = rinfo[b * 32u + lane];
+            const uint32_t js = info & 0x00FFFFFFu, tgt = info >> 24;
+            const uint32_t to = (uint32_t)(L.attr_in_smem ? s_aoffs[tgt] : n.attr_offset[tgt]);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const uint32_t g = w + (uint32_t)(WARPS * (c0 + i));
+              if (c0 + i < GW && (GW * WARPS <= PBN_N || g < (uint32_t)PBN_N)) {
+                uint32_t sv, tv;
+                if (L.attr_in_smem) {
+                  sv = s_aval[js * kNW + (g >> 5)];
+                  tv = s_aval[to * kNW + (g >> 5)];
+                } else {
+                  sv = (uint32_t)(n.attr_val[(size_t)js * kW64 + (g >> 6)] >> (32u * ((g >> 5) & 1u)));
+                  tv = (uint32_t)(n.attr_val[(size_t)to * kW64 + (g >> 6)] >> (32u * ((g >> 5) & 1u)));
+                }
+                ns[i] |= ((sv >> (g & 31u)) & 1u) << b;
+                nt[i] |= ((tv >> (g & 31u)) & 1u) << b;
               }
+            }
+            if (c0 == 0) {
+#pragma unroll
+              for (int i = 0; i < TW; ++i) ni[i] |= ((tgt >> (w + (uint32_t)(WARPS * i))) & 1u) << b;
             }
           }
 #pragma unroll
-          for (int k = 0; k < kTidPlanes; ++k) {
-            uint32_t* const pi = sm + kPlIn + kRowTid * 32 + k * 32 + Lo;
-            const uint32_t mk = 0u - (((uint32_t)tgt >> k) & 1u);
-            atomicAnd(pi, ~bit | mk);
-            atomicOr(pi, bit & mk);
+          for (int i = 0; i < CH; ++i) {
+            const uint32_t g = w + (uint32_t)(WARPS * (c0 + i));
+            if (c0 + i < GW && (GW * WARPS <= PBN_N || g < (uint32_t)PBN_N)) {
+              O[g * 32] = (O[g * 32] & ~D) | ns[i];
+              TG[g * 32] = (TG[g * 32] & ~D) | nt[i];
+            }
+          }
+          if (c0 == 0) {
+#pragma unroll
+            for (int i = 0; i < TW; ++i) {
+              const uint32_t k = w + (uint32_t)(WARPS * i);
+              if (k < (uint32_t)kTidPlanes) TID[k * 32] = (TID[k * 32] & ~D) | ni[i];
+            }
           }
         }
       }
