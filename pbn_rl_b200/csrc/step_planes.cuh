@@ -201,6 +201,7 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
       sm[kPlHit + lane] = 0u;
       sm[kPlM + lane] = 0u;
     }
+    if (pm != PBN_PERT_NONE) __syncthreads();   // O and M are zero (before the draws: in the 8-warp variant warps 4..7 go straight on to the perturbation walks)
     // selection planes of group w & 3 (slots r = (w & 3) + 4k): the 4-warp variant draws its own; in the 8-warp
     // variant warps 0..3 draw and hand the planes of the parts of warps 4..7 over through SELX (read after B1)
     uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];
@@ -239,7 +240,6 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
 #endif
     uint32_t npert = 0u;
     if (pm != PBN_PERT_NONE) {
-      __syncthreads();   // O and M are zero
 #if PBN_INJECTED
       if (a.pert_mask != nullptr) {
         uint32_t mb = 0u;
@@ -262,22 +262,24 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
         if (mb) atomicOr(&sm[kPlM + lane], mb);
       }
 #else
-      if (w < 4u && n.pert_rng) {
-        // sub-stream w of the column: geometric skipping over the slots gene*8 + (b & 7) of slice bits 8w..8w+7
+      // (8-warp variant: warps 4..7 walk the four sub-streams while warps 0..3 are still drawing selection planes)
+      if ((WARPS == 8 ? w >= 4u : w < 4u) && n.pert_rng) {
+        // sub-stream ws of the column: geometric skipping over the slots gene*8 + (b & 7) of slice bits 8ws..8ws+7
         // (the next event lies pos + 1 + j slots on, j = #{i >= 1 : u < S[i]}: none is left in the rem slots after
         // pos iff u < S[rem] -- one table read settles the usual case, the search runs for real events only)
+        const uint32_t ws = w & 3u;
         uint32_t mb = 0u, k = 0u;
-        Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
+        Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * ws, n.rk);
         int pos = -1;
         uint32_t s_rem = kSurvTable[kSlots];
         while (true) {
-          if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((k >> 2) & 63u), n.rk);
+          if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * ws + ((k >> 2) & 63u), n.rk);
           const uint32_t u = pick4(blk, k & 3u);
           ++k;
           if (u < s_rem) break;
           pos += pert_search(n, u);
           if (pos >= kSlots) break;
-          const uint32_t b = 8u * w + ((uint32_t)pos & 7u);
+          const uint32_t b = 8u * ws + ((uint32_t)pos & 7u);
           atomicOr(&O[(pos >> 3) * 32], 1u << b);
           mb |= 1u << b;
           npert += (VALID >> b) & 1u;
