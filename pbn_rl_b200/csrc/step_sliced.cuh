@@ -258,15 +258,19 @@ __device__ __forceinline__ void draw_pert_events(const NetParams& n, uint32_t* e
   uint32_t m8 = 0u;
   if (n.pert_rng && n.pert_mode != PBN_PERT_NONE) {
     const bool whole_walk = rows8 != nullptr && n.pert_mode == PBN_PERT_A;
-    const uint32_t s_last = kSurvTable[kSlots];
+    // none is left in the rem slots after pos iff u < S[rem]: one table read settles the usual case, the search runs
+    // for real events only
+    uint32_t s_rem = kSurvTable[kSlots];
     Philox4 blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w, n.rk);
     int pos = -1;
 #pragma unroll 1
     for (uint32_t k = 0;; ++k) {   // up to kEvCap events are packed
       if (k != 0u && (k & 3u) == 0u) blk = philox_stream_rk(gid, step_ctr, PBN_RNG_PERTURB, 64u * w + ((k >> 2) & 63u), n.rk);   // rare
       const uint32_t u = pick4(blk, k & 3u);
-      pos += (u < s_last) ? kSlots + 1 : pert_search(n, u);
+      if (u < s_rem) break;
+      pos += pert_search(n, u);
       if (pos >= kSlots) break;
+      s_rem = __ldg(n.surv_sliced + (kSlots - 1 - pos));
       m8 |= 1u << ((uint32_t)pos & 7u);
       if (k < kEvCap) {
         const uint32_t sh = kEvBits * (k % kEvPerWord);
