@@ -312,6 +312,10 @@ inline void generate_parts(const GenNet& g, std::string& u) {
     u += "__device__ __constant__ uint32_t kSelCum[] = {" + tc + "};\n";
   }
   u += "// selection planes of group q (slots r = q + 4k): lo[k] + 2*hi[k] = predictor index, bit-sliced over the column's 32 envs\n";
+  u += "// PH: which part of the work (the 8-warp plane-resident kernel splits a group over two warps): -1 everything; 0 / 1 the\n"
+       "// private blocks of the even / odd k only; 2 the shared pool only (lo / hi hold the private results of every k)\n";
+  u += "#define PBN_DRAWS(k) (PH < 0 || PH == ((k) & 1))\n";
+  u += "template <int PH = -1>\n";
   u += "__device__ __forceinline__ void pbn_draw_group(uint32_t q, uint64_t gid, uint64_t step, const uint32_t (&rk)[20],\n"
        "                                               uint32_t (&lo)[PBN_MAXS4], uint32_t (&hi)[PBN_MAXS4]";
   u += sel3 ? ", uint32_t (&h2)[PBN_MAXS4]) {\n" : ") {\n";
@@ -335,10 +339,10 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       some3 = some3 || (Kq[q] == 3 && !(r < NSEL && wof[r]));
       anyw = anyw || (r < NSEL && wof[r]);
     }
-    snprintf(buf, sizeof(buf), "  lo[%d] = 0u; hi[%d] = 0u;\n", k, k);
+    snprintf(buf, sizeof(buf), "  if (PBN_DRAWS(%d)) { lo[%d] = 0u; hi[%d] = 0u; }\n", k, k, k);
     u += buf;
     if (sel3) {
-      snprintf(buf, sizeof(buf), "  h2[%d] = 0u;\n", k);
+      snprintf(buf, sizeof(buf), "  if (PBN_DRAWS(%d)) h2[%d] = 0u;\n", k, k);
       u += buf;
     }
     if (same && Kq[0] == 1) {
@@ -346,7 +350,7 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       continue;
     }
     if (same && !anyw) {
-      snprintf(buf, sizeof(buf), "  { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, q + %du, rk);  // K = %d in every group\n", 4 * k, Kq[0]);
+      snprintf(buf, sizeof(buf), "  if (PBN_DRAWS(%d)) { const Philox4 A = philox_stream_rk(gid, step, PBN_RNG_SELECT, q + %du, rk);  // K = %d in every group\n", k, 4 * k, Kq[0]);
       u += buf;
       if (Kq[0] == 2) snprintf(buf, sizeof(buf), "    lo[%d] = A.x; }\n", k);
       else if (Kq[0] == 4) snprintf(buf, sizeof(buf), "    lo[%d] = A.x; hi[%d] = A.y; }\n", k, k);
@@ -359,6 +363,10 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       if (anyw) {
         snprintf(buf, sizeof(buf), "  const bool W%d = (q + %du < %du) && kSelWeighted[q + %du] != 0;\n", k, 4 * k, NSEL, 4 * k);
         u += buf;
+      }
+      snprintf(buf, sizeof(buf), "  if (PBN_DRAWS(%d)) {\n", k);
+      u += buf;
+      if (anyw) {
         if (sel3)
           snprintf(buf, sizeof(buf), "  if (W%d) draw_weighted8(gid, step, rk, q + %du, K%d, kSelCum + 7u * (q + %du), lo[%d], hi[%d], h2[%d]);\n  else ", k, 4 * k, k, 4 * k, k, k, k);
         else
@@ -371,7 +379,7 @@ inline void generate_parts(const GenNet& g, std::string& u) {
       u += buf;
       snprintf(buf, sizeof(buf), "    lo[%d] = A.x; if (K%d == 4u) hi[%d] = A.y;\n", k, k, k);
       u += buf;
-      snprintf(buf, sizeof(buf), "    if (K%d == 3u) { const uint32_t rj = A.x & A.y; lo[%d] = bmux(rj, A.z, A.x); hi[%d] = bmux(rj, A.w, A.y); } }\n", k, k, k);
+      snprintf(buf, sizeof(buf), "    if (K%d == 3u) { const uint32_t rj = A.x & A.y; lo[%d] = bmux(rj, A.z, A.x); hi[%d] = bmux(rj, A.w, A.y); } }\n  }\n", k, k, k);
       u += buf;
       if (some3) {
         if (anyw) snprintf(buf, sizeof(buf), "  const uint32_t m3_%d = (K%d == 3u && !W%d) ? 0xFFFFFFFFu : 0u;\n", k, k, k);
@@ -390,7 +398,7 @@ inline void generate_parts(const GenNet& g, std::string& u) {
     }
   }
   if (!any.empty()) {
-    u += "#pragma unroll 1\n  for (uint32_t i = 0u; i < 1024u; ++i) {  // the group's pool of pair-planes: FIX blocks 1024 q + i\n";
+    u += "  if (PH < 0 || PH == 2) {\n#pragma unroll 1\n  for (uint32_t i = 0u; i < 1024u; ++i) {  // the group's pool of pair-planes: FIX blocks 1024 q + i\n";
     u += "    if (!__any_sync(0xFFFFFFFFu, (" + any + ") != 0u)) break;\n";
     u += "    const Philox4 P = philox_stream_rk(gid, step, PBN_RNG_FIX, 1024u * q + i, rk);\n    uint32_t av = 0xFFFFFFFFu;\n";
     for (int pass = 0; pass < 2; ++pass) {
@@ -401,9 +409,9 @@ inline void generate_parts(const GenNet& g, std::string& u) {
           u += buf;
         }
     }
-    u += "  }\n";
+    u += "  }\n  }\n";
   }
-  u += "}\n#undef PBN_CLAIM\n\n";
+  u += "}\n#undef PBN_CLAIM\n#undef PBN_DRAWS\n\n";
 
   // ---- evaluation of a part's genes in the plane-resident kernel
   u += "// x: s1 planes, o: out planes (on entry: the perturbation planes of the step), tg: target planes; all [gene][lane]\n"

@@ -203,7 +203,8 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     }
     if (pm != PBN_PERT_NONE) __syncthreads();   // O and M are zero (before the draws: in the 8-warp variant warps 4..7 go straight on to the perturbation walks)
     // selection planes of group w & 3 (slots r = (w & 3) + 4k): the 4-warp variant draws its own; in the 8-warp
-    // variant warps 0..3 draw and hand the planes of the parts of warps 4..7 over through SELX (read after B1)
+    // variant warps g and g + 4 share the private blocks of group g, warp g runs the group's pool and hands the planes
+    // of the parts of warps 4..7 over through SELX (read after B1)
     uint32_t lo[PBN_MAXS4], hi[PBN_MAXS4];
 #if PBN_INJECTED
 #pragma unroll
@@ -227,14 +228,32 @@ __device__ __forceinline__ void step_planes_body(const StepParams& p, const Plan
     if (PBN_EXP == 5) {
 #pragma unroll
       for (int k = 0; k < PBN_MAXS4; ++k) { lo[k] = (uint32_t)gid * 2654435761u + k; hi[k] = ~lo[k] & ((uint32_t)step_ctr + k * 77u); }
-    } else if (WARPS == 4 || w < 4u) {
+    } else if (WARPS == 4) {
       pbn_draw_group(w, gid, step_ctr, n.rk, lo, hi);
-      if (WARPS == 8) {
+    } else if (w >= 4u) {
+      // 8-warp variant: warp g + 4 draws the private blocks of group g's odd slots while warp g draws the even ones,
+      // hands their results over through SELX (a barrier of the two warps) and goes on to the perturbation walk
+      const uint32_t g = w & 3u;
+      pbn_draw_group<1>(g, gid, step_ctr, n.rk, lo, hi);
 #pragma unroll
-        for (int k = 0; k < PBN_MAXS4; ++k) {
-          sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2) * 32 + lane] = lo[k];
-          sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2 + 1) * 32 + lane] = hi[k];
-        }
+      for (int k = 1; k < PBN_MAXS4; k += 2) {
+        sm[kPlSelx + ((g * PBN_MAXS4 + k) * 2) * 32 + lane] = lo[k];
+        sm[kPlSelx + ((g * PBN_MAXS4 + k) * 2 + 1) * 32 + lane] = hi[k];
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1u + g) : "memory");
+    } else {
+      pbn_draw_group<0>(w, gid, step_ctr, n.rk, lo, hi);
+      asm volatile("bar.sync %0, 64;" ::"r"(1u + w) : "memory");
+#pragma unroll
+      for (int k = 1; k < PBN_MAXS4; k += 2) {
+        lo[k] = sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2) * 32 + lane];
+        hi[k] = sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2 + 1) * 32 + lane];
+      }
+      pbn_draw_group<2>(w, gid, step_ctr, n.rk, lo, hi);   // the group's shared pool, over all its slots
+#pragma unroll
+      for (int k = 0; k < PBN_MAXS4; ++k) {
+        sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2) * 32 + lane] = lo[k];
+        sm[kPlSelx + ((w * PBN_MAXS4 + k) * 2 + 1) * 32 + lane] = hi[k];
       }
     }
 #endif
