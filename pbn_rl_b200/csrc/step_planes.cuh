@@ -20,13 +20,15 @@
 // selection planes never leave the register file.  Thread (w, L) handles the per-env inputs/outputs of the column's
 // bits [32/WARPS * w, ...).  The tile's block arrives by one TMA bulk copy and leaves by bulk stores.
 //   P0  (before the wait) selection planes of the warp's parts; perturbation planes of the step -> O; zero scratch
+//       (8-warp variant: warps g / g + 4 share the private blocks of group g, warp g + 4 then walks sub-stream g)
 //   P1  TMA load of the tile block -> IN; action bytes -> flips: atomicXor into the state planes (duplicates dropped,
 //       so XOR == the OR-mask of the contract); one warp: t' = min(t+1, 65535), t' >= horizon, "has target" plane
 //   B1
 //   P2  generated LOP3 trees of the warp's genes on s1 -> perturbation -> O; difference to the target planes
 //   B2
 //   P5  hit / truncated planes -> per-env reward, terminated, truncated (vector stores); statistics; auto-reset:
-//       one Philox block per finished env, new state / target scattered into the planes lane-per-gene
+//       one Philox block per finished env (dealt out over the lanes), then the planes are rewritten gene by gene
+//       (warp = genes mod WARPS, lane = column: a gather over the column's finished envs, no atomics)
 //   B3  bulk stores of the tile block
 // Two instantiations (WARPS = 4 for large batches: 8 CTAs per SM; WARPS = 8 for small ones: half the latency per
 // tile) draw identical streams and give identical results.
