@@ -557,9 +557,12 @@ class VecPBNEnv:
         io = hb[key]
         io.actions, io.actions16 = None, None
         if actions16 is not None:
-            if not (isinstance(actions16, torch.Tensor) and actions16.is_pinned() and actions16.dtype == torch.int16
-                    and actions16.is_contiguous() and actions16.numel() == self.num_envs):
-                raise ValueError("actions16 must be a pinned contiguous int16 tensor with one entry per env")
+            # (the checks cost a driver query per call -- is_pinned -- so a buffer that passed them is remembered)
+            if hb.get("a16_checked") is not actions16:
+                if not (isinstance(actions16, torch.Tensor) and actions16.is_pinned() and actions16.dtype == torch.int16
+                        and actions16.is_contiguous() and actions16.numel() == self.num_envs):
+                    raise ValueError("actions16 must be a pinned contiguous int16 tensor with one entry per env")
+                hb["a16_checked"] = actions16
             if "d_actions16" not in hb:
                 hb["d_actions16"] = torch.empty((self.num_envs,), dtype=torch.int16, device=self.device)
             io.actions16 = actions16.data_ptr()
