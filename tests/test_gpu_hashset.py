@@ -12,8 +12,8 @@ def _identity_net(n):
     return PBNNetwork.from_expressions(genes, [[g] for g in genes])   # every gene keeps its value: next state = state
 
 
-def _big_table(n, rng, sizes=(5000, 300, 1, 17)):
-    """Attractors of `sizes` distinct random states + one attractor made of two wildcard patterns."""
+def _big_table(n, rng, sizes=(5000, 300, 1, 17), wildcards=True):
+    """Attractors of `sizes` distinct random states + (wildcards) one attractor made of two wildcard patterns."""
     from pbn_rl_b200 import AttractorSet
     seen, attractors = set(), []
     for size in sizes:
@@ -25,7 +25,8 @@ def _big_table(n, rng, sizes=(5000, 300, 1, 17)):
                 states.append(s)
         attractors.append(states)
     wild = [tuple([1, 0, "*", 1] + ["*"] * 2 + [0] * (n - 6)), tuple([0, 1, 1, "*"] + [1] * (n - 4))]
-    attractors.insert(2, wild)
+    if wildcards:
+        attractors.insert(2, wild)
     return AttractorSet(attractors, n)
 
 
@@ -69,6 +70,43 @@ def test_membership_with_a_5000_state_attractor(n, kernel):
     env.step(None)
     torch.cuda.synchronize()
     assert np.array_equal(env.terminated.cpu().numpy().astype(bool), want_in)
+    env.close()
+
+
+@pytest.mark.parametrize("n", [28, 70])
+@pytest.mark.parametrize("e", [6000, 3 * 1024])
+def test_step_membership_without_wildcards_probes_through_the_warp_queue(n, e):
+    """Fully specified tables (no wildcard entry): the row kernel tests single-state targets in shared memory and
+    compacts the envs of the larger targets into a per-warp queue for the hash-set probes -- ragged and full tiles,
+    one- and two-word states, targets of every size, envs without a target."""
+    import torch
+    from oracle import pbn_oracle as O
+    from pbn_rl_b200 import VecPBNEnv
+    rng = np.random.default_rng(100 + n)
+    net, attrs = _identity_net(n), _big_table(n, rng, sizes=(5000, 1, 300, 1, 17, 1), wildcards=False)
+    env = VecPBNEnv(net, e, attrs, device="cuda:0", horizon=0, kernel="sliced")
+    assert env.lib.pbn_attractor_hash_slots(env._h) > 0
+    A = len(attrs.attractors)
+    rows, target = [], rng.integers(0, A, size=e).astype(np.int32)
+    for k in range(e):
+        r = k % 4
+        if r == 0:      # a state of the env's own target
+            at = attrs.attractors[int(target[k])]
+            rows.append(at[int(rng.integers(0, len(at)))])
+        elif r == 1:    # a state of some attractor, usually not the target
+            at = attrs.attractors[int(rng.integers(0, A))]
+            rows.append(at[int(rng.integers(0, len(at)))])
+        else:
+            rows.append(tuple(int(v) for v in rng.integers(0, 2, size=n)))
+    target[5::97] = -1   # no target: never terminated
+    env.set_state(np.array(rows, dtype=np.uint8))
+    env.set_target(torch.from_numpy(target))
+    want = np.array([t >= 0 and O.attractor_contains(attrs.attractors[int(t)], r) for r, t in zip(rows, target)])
+    assert want.sum() > e // 5 and (~want).sum() > e // 3
+    for _ in range(2):   # the network keeps every state: the second step sees the same states
+        env.step(None)
+        torch.cuda.synchronize()
+        assert np.array_equal(env.terminated.cpu().numpy().astype(bool), want)
     env.close()
 
 
