@@ -186,6 +186,26 @@ int main(int argc, char** argv) {
       pbn::pbn_draw_group(q, gid, step, rk, lo, hi);
 #endif
       for (int k = 0; k < PBN_MAXS4; ++k) { const int r = (int)q + 4 * k; if (r < nsel) { L[r] = lo[k]; H[r] = hi[k]; H2[r] = h2[k]; } }
+      // the split form of the 8-warp plane-resident kernel: even private blocks (PH = 0) and odd ones (PH = 1) drawn
+      // apart, the odd results handed over, then the shared pool alone (PH = 2) -- must equal the one-call form
+      uint32_t lo_e[PBN_MAXS4], hi_e[PBN_MAXS4], h2_e[PBN_MAXS4], lo_o[PBN_MAXS4], hi_o[PBN_MAXS4], h2_o[PBN_MAXS4];
+      for (int k = 0; k < PBN_MAXS4; ++k) { lo_e[k] = hi_e[k] = h2_e[k] = 0xA5A5A5A5u; lo_o[k] = hi_o[k] = h2_o[k] = 0x5A5A5A5Au; }
+#if PBN_SELBITS == 3
+      pbn::pbn_draw_group<0>(q, gid, step, rk, lo_e, hi_e, h2_e);
+      pbn::pbn_draw_group<1>(q, gid, step, rk, lo_o, hi_o, h2_o);
+#else
+      pbn::pbn_draw_group<0>(q, gid, step, rk, lo_e, hi_e);
+      pbn::pbn_draw_group<1>(q, gid, step, rk, lo_o, hi_o);
+      for (int k = 0; k < PBN_MAXS4; ++k) { h2_e[k] = 0u; h2_o[k] = 0u; }
+#endif
+      for (int k = 1; k < PBN_MAXS4; k += 2) { lo_e[k] = lo_o[k]; hi_e[k] = hi_o[k]; h2_e[k] = h2_o[k]; }
+#if PBN_SELBITS == 3
+      pbn::pbn_draw_group<2>(q, gid, step, rk, lo_e, hi_e, h2_e);
+#else
+      pbn::pbn_draw_group<2>(q, gid, step, rk, lo_e, hi_e);
+#endif
+      for (int k = 0; k < PBN_MAXS4; ++k)
+        if (lo_e[k] != lo[k] || hi_e[k] != hi[k] || h2_e[k] != h2[k]) { fprintf(stderr, "split draw differs: group %u slot index %d\n", q, k); return 3; }
     }
     for (int r = 0; r < nsel; ++r) printf("%u %u %u ", L[r], H[r], H2[r]);
     printf("\n");
